@@ -1,0 +1,238 @@
+"""Pins the numpy oracle (oracle/linmpc.py, oracle/qp.py) to every inline known answer the
+reference's own tests / doctests hold for the LinMPC path.
+Each test cites the reference assertion it restates; tolerances are the reference's own."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import qp
+from oracle.linmpc import (ExplicitMPC, LinModel, LinMPC, ManualEstimator, SteadyKalmanFilter,
+                           move_blocking, zoh_first_order)
+
+
+def first_order(gain, tau, Ts, **op):
+    A, B, C = zoh_first_order(gain, tau, Ts)
+    return LinModel(A, B, C, Ts=Ts, **op)
+
+
+def test_move_blocking():
+    # docstring example src/controller/construct.jl:624-627 and the Int method :653-660
+    assert move_blocking(10, [1, 2, 3, 6, 7]) == [1, 2, 3, 4]
+    assert move_blocking(10, [1, 2, 3]) == [1, 2, 3, 4]
+    assert move_blocking(20, 5) == [1, 1, 1, 1, 16]
+
+
+def test_moveinput_known_answer():
+    # test/3_test_predictive_control.jl:93-106 and the moveinput! doctest execute.jl:49-57
+    linmodel = first_order(5, 2, 3.0, yop=[10])
+    mpc1 = LinMPC(linmodel, Nwt=[0], Hp=1000, Hc=1)
+    r = [15]
+    mpc1.preparestate([10])
+    u = mpc1.moveinput(r)
+    assert u == pytest.approx([1], abs=1e-2)
+    u = mpc1.moveinput(r, lastu=[-1])
+    assert u == pytest.approx([1], abs=1e-2)
+    info = mpc1.getinfo()
+    assert info["u"] == pytest.approx(u)
+    assert info["Yhat"][-1] == pytest.approx(r[0], abs=1e-2)
+    assert info["DU"] == pytest.approx([2.0], abs=1e-2)
+    assert info["J"] == pytest.approx(info["J_quad"], rel=1e-9, abs=1e-9)  # construct.jl:821-833
+    mpc2 = LinMPC(linmodel, Nwt=[0], Cwt=np.inf, Hp=1000, Hc=1)
+    mpc2.preparestate([10])
+    assert mpc2.moveinput(r) == pytest.approx([1], abs=1e-2)
+    # :111-114  input-setpoint tracking
+    mpc3 = LinMPC(linmodel, Mwt=[0], Nwt=[0], Lwt=[1])
+    mpc3.preparestate([10])
+    u = mpc3.moveinput([0], Rhat_u=np.full(mpc3.Hp, 12.0))
+    assert u == pytest.approx([12], abs=1e-2)
+
+
+def test_measured_disturbance_feedforward():
+    # :128-134  LinModel([tf(5,[2000,1]) tf(7,[8000,1])], 3000, i_d=[2]); d=0.1 -> y->0.7, u ~ 0
+    Ts = 3000.0
+    a1, b1, c1 = zoh_first_order(5, 2000, Ts)
+    a2, b2, c2 = zoh_first_order(7, 8000, Ts)
+    model = LinModel(np.diag([a1[0, 0], a2[0, 0]]), [[b1[0, 0]], [0]], [[c1[0, 0], c2[0, 0]]],
+                     Bd=[[0], [b2[0, 0]]], Dd=[[0]], Ts=Ts)
+    mpc6 = LinMPC(model, Nwt=[0], Hp=1000, Hc=1)
+    mpc6.preparestate([0], [0])
+    d = np.array([0.1])
+    u = mpc6.moveinput(7 * d, d)
+    assert u == pytest.approx([0], abs=1e-2)
+    # :142-150 infeasible problem -> error status -> shifted last solution (zeros) is returned
+    mpc_inf = LinMPC(model, Hp=1, Hc=1, Cwt=np.inf).setconstraint(umin=[+1], umax=[-1])
+    mpc_inf.preparestate([0], [0])
+    u = mpc_inf.moveinput([0], [0])
+    assert mpc_inf.last_status == qp.INFEASIBLE
+    assert u == pytest.approx([0.0])
+
+
+def test_move_blocking_zeros():
+    # :135-140  Hc=[1,2,3,4], Nwt=10: the held moves are exactly zero
+    linmodel = first_order(5, 2, 3.0, yop=[10])
+    mpc7 = LinMPC(linmodel, Hp=10, Hc=[1, 2, 3, 4], Nwt=[10])
+    mpc7.preparestate([10])
+    mpc7.moveinput([15])
+    dU = np.diff(mpc7.getinfo()["U"])
+    assert dU[[1, 3, 4, 6, 7, 8]] == pytest.approx(np.zeros(6), abs=1e-9)
+    assert np.abs(dU[[0, 2, 5]]).min() > 1e-6
+
+
+def test_manual_estimator_equals_default():
+    # :211-237  atol 1e-9
+    linmodel = first_order(5, 2, 3.0, yop=[10])
+    plant = first_order(5, 2, 3.0, yop=[10])
+    r, outdist = [15], np.array([5.0])
+    mpc_man = LinMPC(ManualEstimator(linmodel))
+    skf = SteadyKalmanFilter(linmodel)
+    mpc_def = LinMPC(linmodel)
+    U_man, U_def = np.zeros(25), np.zeros(25)
+    for i in range(25):
+        ym = plant.evaloutput() - outdist
+        xhat = skf.preparestate(ym)
+        mpc_man.setstate(xhat)
+        mpc_def.preparestate(ym)
+        u_man, u_def = mpc_man.moveinput(r), mpc_def.moveinput(r)
+        U_man[i], U_def[i] = u_man[0], u_def[0]
+        skf.updatestate(u_man, ym)
+        mpc_def.updatestate(u_def, ym)
+        plant.updatestate(u_man)
+    assert U_man == pytest.approx(U_def, abs=1e-9)
+    # closed loop reaches the setpoint despite the output disturbance (integral action)
+    assert plant.evaloutput()[0] - outdist[0] == pytest.approx(15, abs=1e-1)
+
+
+def test_golden_doctest_17_577311():
+    # ext/LinearMPCext.jl:252-261: LinMPC(LinModel(tf(2,[10,1]),1.0)); preparestate!(mpc,[1.0]);
+    # moveinput!(mpc,[10.0]) -> 17.577311.  Realisation xdot=-0.1x+0.5u, y=0.4x.
+    A, B, C = zoh_first_order(2, 10, 1.0, b=0.5)
+    mpc = LinMPC(LinModel(A, B, C, Ts=1.0))
+    assert (mpc.Hp, mpc.Hc, mpc.estim.nxhat) == (10, 2, 2)
+    mpc.preparestate([1.0])
+    u = mpc.moveinput([10.0])
+    assert round(float(u[0]), 6) == 17.577311
+
+
+def test_lqr_equivalence():
+    # test/3_test_predictive_control.jl:498-527  atol 1e-5 (terminal cost = DARE solution)
+    A = np.array([[0.5, -0.4], [0.6, 0.5]])
+    B = C = np.eye(2)
+    model, plant = LinModel(A, B, C), LinModel(A, B, C)
+    Q, R = np.eye(2), 0.5 * np.eye(2)
+    P = scipy.linalg.solve_discrete_are(A, B, Q, R)
+    K = np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
+    M_Hp = np.block([[np.eye(4), np.zeros((4, 2))], [np.zeros((2, 4)), P]])
+    mpc = LinMPC(model, Hp=3, Hc=3, M_Hp=M_Hp, Nwt=[0, 0], Lwt=[0.5, 0.5], nint_ym=0)
+    mpc.setstate([1, 1])
+    plant.setstate([1, 1])
+    X_mpc, X_lqr = np.zeros((2, 20)), np.zeros((2, 20))
+    for i in range(20):
+        y = plant.evaloutput()
+        mpc.preparestate(y)
+        u = mpc.moveinput([0, 0])
+        X_mpc[:, i] = plant.x0
+        mpc.updatestate(u, y)
+        plant.updatestate(u)
+    x = np.array([1.0, 1.0])
+    for i in range(20):
+        X_lqr[:, i] = x
+        x = A @ x + B @ (-K @ x)
+    assert np.abs(X_mpc - X_lqr).max() < 1e-5
+
+
+@pytest.mark.parametrize("Cwt", [1e5, np.inf])
+def test_constraint_violation(Cwt):
+    # test/3_test_predictive_control.jl:391-464 (test_bound_violation, soft then hard), atol 1e-1
+    A, B, C = zoh_first_order(2, 10, 3.0)
+    mpc = LinMPC(LinModel(A, B, C, Ts=3.0), Hp=50, Hc=5, Cwt=Cwt)
+    mpc.setconstraint(xhatmin=[-1e6, -np.inf], xhatmax=[1e6, np.inf])
+    mpc.setconstraint(umin=[-10], umax=[10])
+    mpc.setconstraint(dumin=[-15], dumax=[15])
+    mpc.setconstraint(ymin=[-100], ymax=[100])
+    if np.isfinite(Cwt):
+        mpc.setconstraint(c_xhatmin=[1, 1], c_xhatmax=[1, 1])
+        mpc.setconstraint(c_umin=[0.1], c_umax=[0.1])
+        mpc.setconstraint(c_dumin=[0.1], c_dumax=[0.1])
+        mpc.setconstraint(c_ymin=[1], c_ymax=[1])
+    mpc.preparestate([0])
+    tol = 1e-1
+
+    def info_after(r):
+        mpc.moveinput(r)
+        assert mpc.last_status == qp.OPTIMAL and mpc.last_qp["kkt"] < 1e-8
+        return mpc.getinfo()
+    mpc.setconstraint(umin=[-3], umax=[4])
+    assert np.allclose(info_after([-100])["U"], -3, atol=tol)
+    assert np.allclose(info_after([100])["U"], 4, atol=tol)
+    mpc.setconstraint(umin=[-10], umax=[10])
+    mpc.setconstraint(dumin=[-1.5], dumax=[1.25])
+    assert np.allclose(info_after([-100])["DU"], -1.5, atol=tol)
+    assert np.allclose(info_after([100])["DU"], 1.25, atol=tol)
+    mpc.setconstraint(dumin=[-15], dumax=[15])
+    mpc.setconstraint(ymin=[-0.5], ymax=[0.9])
+    assert np.allclose(info_after([-100])["Yhat"], -0.5, atol=tol)
+    assert np.allclose(info_after([100])["Yhat"], 0.9, atol=tol)
+    mpc.setconstraint(ymin=[-100], ymax=[100])
+    mpc.setconstraint(Ymin=np.r_[-0.5, np.full(49, -100.0)], Ymax=np.r_[0.9, np.full(49, 100.0)])
+    info = info_after([-10])
+    assert info["Yhat"][0] == pytest.approx(-0.5, abs=tol) and info["Yhat"][-1] == pytest.approx(-10, abs=tol)
+    info = info_after([10])
+    assert info["Yhat"][0] == pytest.approx(0.9, abs=tol) and info["Yhat"][-1] == pytest.approx(10, abs=tol)
+    mpc.setconstraint(ymin=[-100], ymax=[100])
+    mpc.setconstraint(xhatmin=[-1e-6, -np.inf], xhatmax=[1e-6, np.inf])
+    assert info_after([-100])["xhatend"][0] == pytest.approx(0, abs=tol)
+    assert info_after([100])["xhatend"][0] == pytest.approx(0, abs=tol)
+    mpc.setconstraint(xhatmin=[-1e6, -np.inf], xhatmax=[1e6, np.inf])
+    # construct.jl:548-551
+    with pytest.raises(RuntimeError):
+        mpc.setconstraint(umin=[-np.inf])
+
+
+def test_explicit_equals_linmpc_unconstrained():
+    # test/3_test_predictive_control.jl:1593-1634 (ExplicitMPC == LinMPC), explicitmpc.jl:209
+    rng = np.random.default_rng(0)
+    A = np.diag([0.9, 0.7, 0.5]) + 0.05 * rng.standard_normal((3, 3))
+    model = LinModel(A, rng.standard_normal((3, 2)), rng.standard_normal((2, 3)))
+    lin, exp = LinMPC(model, Hp=12, Hc=[1, 2, 3]), ExplicitMPC(model, Hp=12, Hc=[1, 2, 3])
+    for mpc in (lin, exp):
+        mpc.preparestate([0.3, -0.2])
+    u1, u2 = lin.moveinput([1, -1]), exp.moveinput([1, -1])
+    assert u1 == pytest.approx(u2, rel=1e-9, abs=1e-9)
+    assert lin.Ztilde[-1] == pytest.approx(0.0, abs=1e-12)
+
+
+def test_qp_solver_against_bruteforce():
+    # exactness of oracle/qp.py itself: enumerate active sets of small random QPs
+    import itertools
+    rng = np.random.default_rng(1)
+    for trial in range(20):
+        n, m = 3, 5
+        M = rng.standard_normal((n, n))
+        H = M @ M.T + 0.1 * np.eye(n)
+        q = rng.standard_normal(n) * 3
+        G = rng.standard_normal((m, n))
+        h = rng.random(m) + 0.1
+        best, bz = np.inf, None
+        for k in range(0, n + 1):
+            for act in itertools.combinations(range(m), k):
+                act = list(act)
+                if act:
+                    Ga = G[act]
+                    KKT = np.block([[H, Ga.T], [Ga, np.zeros((k, k))]])
+                    try:
+                        sol = np.linalg.solve(KKT, np.r_[-q, h[act]])
+                    except np.linalg.LinAlgError:
+                        continue
+                    z, lam = sol[:n], sol[n:]
+                    if (lam < -1e-12).any():
+                        continue
+                else:
+                    z = np.linalg.solve(H, -q)
+                if (G @ z - h > 1e-10).any():
+                    continue
+                J = 0.5 * z @ H @ z + q @ z
+                if J < best:
+                    best, bz = J, z
+        sol = qp.solve_qp(H, q, G, h)
+        assert sol["status"] == qp.OPTIMAL
+        assert sol["z"] == pytest.approx(bz, abs=1e-9)
