@@ -1,0 +1,168 @@
+/*
+ * bmpc.h -- C ABI of the B200-native batched LinMPC / linear-MHE step (libbmpc.so).
+ *
+ * Drop-in boundary for ONE hot path of JuliaControl/ModelPredictiveControl.jl v2.11.0:
+ * the per-period `moveinput!` of `LinMPC` (reference src/controller/execute.jl:59-80 =
+ * initpred! :247-277 + linconstraint! src/controller/transcription.jl:811-848 +
+ * optim_objective! execute.jl:466-505 + getinput! :536-546), executed for a batch of N
+ * independent controller instances in one launch of hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI of its own (100 % Julia).  The seam this ABI plugs into is the
+ * one `ExplicitMPC` already uses (src/controller/explicitmpc.jl:198-209): the generic
+ * functions initpred!/linconstraint!/optim_objective!/getinput! called by moveinput!
+ * (execute.jl:75-79), with the state estimate supplied from outside exactly like
+ * `LinMPC(ManualEstimator(model))` + `setstate!` (src/estimator/manual.jl:60-64,150-154).
+ * INTEGRATION.md shows the Julia `ccall` binding; `modelpredictivecontrol.jl_b200/` holds
+ * the ctypes mirror used by this repo's tests and bench.
+ *
+ * Conventions
+ *   - all reals are IEEE fp64; matrices are COLUMN-MAJOR exactly as the Julia fields;
+ *   - batch arrays are instance-major: element k of instance i is  arr[i*len + k];
+ *   - "0" suffix = deviation from the operating point, as in the reference
+ *     (mpc.estim.x̂0, mpc.lastu0, con.U0min = umin - Uop, ...: construct.jl:356-409);
+ *   - nYhat = ny*Hp, nU = nu*Hp, nDU = nu*Hc, n = nDU + neps (Z̃ = [ΔU; ϵ], slack LAST,
+ *     construct.jl:1000-1004);
+ *   - +-Inf in a bound array means "no constraint" (i_b mask, transcription.jl:692-700); the
+ *     finiteness pattern is shared by all instances of a handle and frozen after the first
+ *     step (construct.jl:548-551);
+ *   - functions return BMPC_OK or a negative error code and never throw; bmpc_last_error()
+ *     returns a thread-local message.  Per-instance solver outcome is in `status`.
+ *   - there is NO CPU fallback: every entry point that computes requires a CUDA device.
+ */
+#ifndef BMPC_H
+#define BMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMPC_OK 0
+#define BMPC_ERR_ARG (-1)         /* bad dimension / null pointer / inconsistent pattern        */
+#define BMPC_ERR_CUDA (-2)        /* CUDA runtime failure (message in bmpc_last_error)           */
+#define BMPC_ERR_STATE (-3)       /* call order, or +-Inf pattern changed after the first step   */
+#define BMPC_ERR_UNSUPPORTED (-4) /* feature outside the hot-path scope          */
+
+/* per-instance solver status, mirrors the reference policy in optim_objective!
+ * (execute.jl:482-503, general.jl:45-61) */
+#define BMPC_STATUS_OPTIMAL 0         /* solved to tolerance                                    */
+#define BMPC_STATUS_ITERATION_LIMIT 1 /* not converged, iterate kept (cf. @warn branch :490-496) */
+#define BMPC_STATUS_INFEASIBLE 2      /* infeasible / numerical failure: Ztilde = shifted previous
+                                         solution Z̃s, exactly like :499-500                     */
+
+typedef struct bmpc_handle bmpc_handle;
+
+/* Dimensions of a batch of identically-structured LinMPC controllers
+ * (mirrors the allocation in the LinMPC inner constructor, src/controller/linmpc.jl:50-111). */
+typedef struct {
+    int32_t N;            /* controller instances in the batch                                  */
+    int32_t nu, ny, nd;   /* manipulated inputs, outputs, measured disturbances of the LinModel */
+    int32_t nxhat;        /* augmented state size (augment_model, estimator/construct.jl:305-323) */
+    int32_t Hp, Hc;       /* prediction horizon; number of move blocks (length of nb)           */
+    int32_t neps;         /* 1 if Cwt is finite (slack variable present), else 0                */
+    int32_t shared_model; /* 1: model-dependent constants are given ONCE and shared by all N    */
+    int32_t max_iter;     /* interior-point iteration cap (0 -> 50); replaces the Ts time limit */
+    int32_t device;       /* CUDA device ordinal                                                */
+    int32_t team;         /* threads per instance: 0 = auto, else 8/16/32/64/128/256           */
+    double tol;           /* relative KKT tolerance (0 -> 1e-11)                                */
+} bmpc_dims;
+
+/* Softness (ECR) vectors, shared by all instances; NULL member -> reference default
+ * (c_u = c_du = 0 hard, c_y = c_xhat = 1 soft: construct.jl:909-913). Ignored when neps = 0. */
+typedef struct {
+    const double *C_umin, *C_umax;   /* nU   */
+    const double *C_dumin, *C_dumax; /* nDU  */
+    const double *C_ymin, *C_ymax;   /* nYhat */
+    const double *c_xmin, *c_xmax;   /* nxhat */
+} bmpc_softness;
+
+/* Inputs / outputs of one control period for the whole batch (= moveinput! arguments,
+ * execute.jl:59-70).  Pointers are HOST pointers unless device_ptrs = 1. */
+typedef struct {
+    const double *xhat0;  /* N x nxhat   current state estimate, deviation (mpc.estim.x̂0)        */
+    double *lastu0;       /* N x nu      in: u0(k-1); out: u0(k)  (mpc.lastu0, getinput! :544)   */
+    const double *ry;     /* N x ny      output setpoint, repeated over Hp when Rhat_y is NULL   */
+    const double *Rhat_y; /* N x nYhat   or NULL                                                 */
+    const double *Rhat_u; /* N x nU      or NULL (= Uop, execute.jl:66)                          */
+    const double *d0;     /* N x nd      measured disturbance deviation d0(k), NULL if nd = 0    */
+    const double *Dhat0;  /* N x nd*Hp   predicted deviations D̂0, NULL -> repeat(d0, Hp)         */
+    double *Ztilde;       /* N x n       in: previous solution (warm start / fallback); out: Z̃   */
+    double *u;            /* N x nu      out: u(k) = Z̃[1:nu] + lastu0 + uop                      */
+    double *J;            /* N           out: objective 1/2 Z̃'H̃Z̃ + q̃'Z̃ + r, or NULL             */
+    int32_t *status;      /* N           out: BMPC_STATUS_*                                      */
+    int32_t *iters;       /* N           out: interior-point iterations (0 = unconstrained exit) */
+    int32_t device_ptrs;  /* 1: every pointer above is a device pointer on dims.device           */
+    int32_t sync;         /* 1: block until the results are complete                             */
+} bmpc_step_io;
+
+/* Diagnostics of the last step (= getinfo, execute.jl:145-198); any pointer may be NULL.
+ * Host pointers. */
+typedef struct {
+    double *Yhat0;      /* N x nYhat  Ŷ0 = Ẽ Z̃ + F   (predict!, transcription.jl:1136-1145)      */
+    double *U0;         /* N x nU     U0 = P̃u Z̃ + Tu lastu0                                      */
+    double *xhat0end;   /* N x nxhat  x̂0(k+Hp) = ẽx̂ Z̃ + fx̂                                       */
+    double *F;          /* N x nYhat  (initpred! output)                                          */
+    double *qtilde;     /* N x n      (initpred! output, reference coordinates)                   */
+    double *r;          /* N                                                                      */
+} bmpc_info;
+
+const char *bmpc_last_error(void);
+int bmpc_version(void);
+
+/* nb: move-blocking vector (move_blocking, construct.jl:629-660), length Hc, sum = Hp. */
+int bmpc_create(bmpc_handle **out, const bmpc_dims *dims, const int32_t *nb);
+int bmpc_destroy(bmpc_handle *h);
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL -> the handle's own. */
+int bmpc_set_stream(bmpc_handle *h, void *stream);
+
+/* Route A -- give the augmented model (estim.Â,B̂u,Ĉ,B̂d,D̂d, f̂op-x̂op) and the weights; the
+ * prediction matrices and the Hessian are built ON THE DEVICE (init_predmat
+ * transcription.jl:115-194 + init_quadprog construct.jl:837-845).  This is also the
+ * batched `setmodel!` (execute.jl:621-790).  M_diag nYhat, N_diag nDU, L_diag nU.
+ * Arrays are N x len, or 1 x len when dims.shared_model = 1. */
+int bmpc_set_model(bmpc_handle *h, const double *Ahat, const double *Buhat, const double *Chat,
+                   const double *Bdhat, const double *Ddhat, const double *fop_minus_xop,
+                   const double *M_diag, const double *N_diag, const double *L_diag, double Cwt);
+
+/* Route B -- the host (Julia) already holds the matrices: mpc.Ẽ (without the slack column:
+ * nYhat x nDU), mpc.K, .V, .B, .G, .J, mpc.H̃ (n x n, lower triangle authoritative,
+ * construct.jl:842) and the terminal matrices con.ẽx̂ (nxhat x nDU), kx̂, vx̂, bx̂, gx̂, jx̂
+ * (linmpc.jl:31-38, construct.jl:128-134).  G/J/gx/jx may be NULL when nd = 0; the
+ * terminal set may be NULL when no x̂ bound is ever finite. */
+int bmpc_set_predmat(bmpc_handle *h, const double *E, const double *K, const double *V,
+                     const double *B, const double *G, const double *J, const double *Htilde,
+                     const double *ex, const double *kx, const double *vx, const double *bx,
+                     const double *gx, const double *jx);
+
+/* Weights needed per step for q̃ and r (ControllerWeights, construct.jl:45-93).
+ * M: nYhat (diag) or nYhat x nYhat when M_dense = 1; L_diag: nU or NULL (= 0). */
+int bmpc_set_weights(bmpc_handle *h, const double *M, int32_t M_dense, const double *L_diag);
+
+/* Operating points uop (nu), yop (ny) per instance (Uop/Yop = repeat, linmpc.jl:90).
+ * NULL = zeros. */
+int bmpc_set_oppoints(bmpc_handle *h, const double *uop, const double *yop);
+
+/* Bounds in deviation form, N x len each (NULL = all infinite) -- the state that
+ * setconstraint! leaves in mpc.con (construct.jl:152-161). */
+int bmpc_set_constraints(bmpc_handle *h, const double *U0min, const double *U0max,
+                         const double *DUmin, const double *DUmax, const double *Y0min,
+                         const double *Y0max, const double *xhat0min, const double *xhat0max,
+                         const bmpc_softness *soft);
+
+/* One control period for all N instances (= moveinput!). */
+int bmpc_step(bmpc_handle *h, const bmpc_step_io *io);
+
+/* getinfo quantities of the last step. */
+int bmpc_getinfo(bmpc_handle *h, const bmpc_info *info);
+
+/* Launch geometry actually used: {team, teams_per_cta, grid, smem_bytes_per_cta,
+ * pd_in_smem, n_rows_m, n_sparse_rows, n_dense_rows} -- for DESIGN.md / bench reporting. */
+int bmpc_launch_info(bmpc_handle *h, int32_t out[8]);
+/* Number of kernel launches issued by this handle since creation (bench `gpu_launches`). */
+int64_t bmpc_launch_count(bmpc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMPC_H */

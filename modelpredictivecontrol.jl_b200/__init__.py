@@ -1,0 +1,12 @@
+"""B200-native batched LinMPC / linear-MHE step behind the reference's API names.
+
+The compute path is libbmpc.so (hand-written sm_100a CUDA behind the C ABI in include/bmpc.h);
+this package is only the host-side mirror of the reference interface for that path.
+"""
+from . import _lib
+from ._lib import (BmpcError, STATUS_INFEASIBLE, STATUS_ITERATION_LIMIT, STATUS_OPTIMAL)
+from .batch import BatchLinMPC
+from .host import move_blocking
+
+__all__ = ["BatchLinMPC", "BmpcError", "move_blocking", "STATUS_OPTIMAL", "STATUS_ITERATION_LIMIT",
+           "STATUS_INFEASIBLE"]

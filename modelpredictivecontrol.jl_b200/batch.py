@@ -1,0 +1,181 @@
+"""BatchLinMPC: thin object wrapper over the libbmpc.so handle (one batch of N controllers).
+
+Array convention on the Python side: numpy arrays shaped (N, rows, cols) / (N, len) with the
+usual (row, col) meaning; they are converted to the ABI's instance-major column-major layout
+here.  With ``shared_model=True`` model-dependent arrays carry a leading dimension of 1.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BmpcError, check, colmajor, dptr
+
+
+def _vec(a, N, length, name):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if a.shape == (length,):
+        a = np.ascontiguousarray(np.broadcast_to(a, (N, length)))
+    if a.shape != (N, length):
+        raise ValueError(f"{name} must have shape ({N}, {length}) or ({length},), got {a.shape}")
+    return a
+
+
+class BatchLinMPC:
+    """N identically-structured LinMPC controllers stepping in lock-step on one B200."""
+
+    def __init__(self, N, nu, ny, nxhat, Hp, Hc=2, nd=0, Cwt=1e5, shared_model=False, device=0, team=0,
+                 max_iter=0, tol=0.0):
+        from .host import move_blocking
+        self.nb = move_blocking(Hp, Hc)
+        self.N, self.nu, self.ny, self.nd, self.nxhat, self.Hp, self.Hc = N, nu, ny, nd, nxhat, Hp, len(self.nb)
+        self.neps = 0 if np.isinf(Cwt) else 1
+        self.Cwt = float(Cwt)
+        self.nDU = nu * self.Hc
+        self.n = self.nDU + self.neps
+        self.nY, self.nU = ny * Hp, nu * Hp
+        self.shared_model = bool(shared_model)
+        self.NM = 1 if shared_model else N
+        self.device = device
+        self._h = C.c_void_p()
+        dims = _lib.Dims(N=N, nu=nu, ny=ny, nd=nd, nxhat=nxhat, Hp=Hp, Hc=self.Hc, neps=self.neps,
+                         shared_model=int(shared_model), max_iter=max_iter, device=device, team=team, tol=tol)
+        nb = (C.c_int32 * self.Hc)(*self.nb)
+        check(_lib.lib().bmpc_create(C.byref(self._h), C.byref(dims), nb))
+        # controller state owned by the caller, exactly as mpc.Z̃ / mpc.lastu0 in the reference
+        self.Ztilde = np.zeros((N, self.n))
+        self.lastu0 = np.zeros((N, nu))
+        self.u = np.zeros((N, nu))
+        self.J = np.zeros(N)
+        self.status = np.zeros(N, dtype=np.int32)
+        self.iters = np.zeros(N, dtype=np.int32)
+        self.uop = np.zeros((self.NM, nu))
+        self.yop = np.zeros((self.NM, ny))
+
+    def close(self):
+        if self._h:
+            _lib.lib().bmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- model-dependent constants ---------------------------------------------------------
+    def _mat(self, a, rows, cols, name):
+        if a is None:
+            return None
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 2:
+            a = a[None]
+        if a.shape != (self.NM, rows, cols):
+            raise ValueError(f"{name} must have shape ({self.NM}, {rows}, {cols}), got {a.shape}")
+        return colmajor(a)
+
+    def set_predmat(self, E, K, V, B, Htilde, G=None, J=None, ex=None, kx=None, vx=None, bx=None, gx=None, jx=None):
+        """Route B: host-computed mpc.Ẽ (without slack column), K, V, B, G, J, H̃ and terminal matrices."""
+        nY, nDU, nx, nu, nd, Hp, n = self.nY, self.nDU, self.nxhat, self.nu, self.nd, self.Hp, self.n
+        v = lambda a, ln, nm: None if a is None else _vec(a, self.NM, ln, nm)
+        args = [self._mat(E, nY, nDU, "E"), self._mat(K, nY, nx, "K"), self._mat(V, nY, nu, "V"), v(B, nY, "B"),
+                self._mat(G, nY, nd, "G") if nd else None, self._mat(J, nY, nd * Hp, "J") if nd else None,
+                self._mat(Htilde, n, n, "Htilde"), self._mat(ex, nx, nDU, "ex"), self._mat(kx, nx, nx, "kx"),
+                self._mat(vx, nx, nu, "vx"), v(bx, nx, "bx"), self._mat(gx, nx, nd, "gx") if nd else None,
+                self._mat(jx, nx, nd * Hp, "jx") if nd else None]
+        check(_lib.lib().bmpc_set_predmat(self._h, *[dptr(a) for a in args]))
+
+    def set_model(self, Ahat, Buhat, Chat, Bdhat=None, Ddhat=None, fop_minus_xop=None, M_diag=None, N_diag=None,
+                  L_diag=None):
+        """Route A: augmented model + diagonal weights; prediction matrices and Hessian are built on the GPU."""
+        nx, nu, ny, nd = self.nxhat, self.nu, self.ny, self.nd
+        NM = self.NM
+        f = np.zeros((NM, nx)) if fop_minus_xop is None else _vec(fop_minus_xop, NM, nx, "fop_minus_xop")
+        M = _vec(np.ones(self.nY) if M_diag is None else M_diag, NM, self.nY, "M_diag")
+        Nw = _vec(np.full(self.nDU, 0.1) if N_diag is None else N_diag, NM, self.nDU, "N_diag")
+        L = _vec(np.zeros(self.nU) if L_diag is None else L_diag, NM, self.nU, "L_diag")
+        args = [self._mat(Ahat, nx, nx, "Ahat"), self._mat(Buhat, nx, nu, "Buhat"), self._mat(Chat, ny, nx, "Chat"),
+                self._mat(Bdhat, nx, nd, "Bdhat") if nd else None, self._mat(Ddhat, ny, nd, "Ddhat") if nd else None,
+                f, M, Nw, L]
+        check(_lib.lib().bmpc_set_model(self._h, *[dptr(a) for a in args], C.c_double(self.Cwt)))
+
+    def set_weights(self, M, L_diag=None):
+        M = np.asarray(M, dtype=np.float64)
+        dense = M.ndim >= 2 and M.shape[-1] == self.nY and M.shape[-2] == self.nY and self.nY > 1
+        if dense:
+            Mc = self._mat(M, self.nY, self.nY, "M_Hp")
+        else:
+            Mc = _vec(M, self.NM, self.nY, "M_diag")
+        L = None if L_diag is None else _vec(L_diag, self.NM, self.nU, "L_diag")
+        check(_lib.lib().bmpc_set_weights(self._h, dptr(Mc), int(dense), dptr(L)))
+
+    def set_oppoints(self, uop=None, yop=None):
+        if uop is not None:
+            self.uop = _vec(uop, self.NM, self.nu, "uop")
+        if yop is not None:
+            self.yop = _vec(yop, self.NM, self.ny, "yop")
+        check(_lib.lib().bmpc_set_oppoints(self._h, dptr(self.uop), dptr(self.yop)))
+
+    def set_constraints(self, U0min=None, U0max=None, DUmin=None, DUmax=None, Y0min=None, Y0max=None,
+                        xhat0min=None, xhat0max=None, soft=None):
+        """Bounds in deviation form (the content of mpc.con after setconstraint!); None = unbounded."""
+        N = self.N
+        v = lambda a, ln, nm: None if a is None else _vec(a, N, ln, nm)
+        arrs = [v(U0min, self.nU, "U0min"), v(U0max, self.nU, "U0max"), v(DUmin, self.nDU, "DUmin"),
+                v(DUmax, self.nDU, "DUmax"), v(Y0min, self.nY, "Y0min"), v(Y0max, self.nY, "Y0max"),
+                v(xhat0min, self.nxhat, "xhat0min"), v(xhat0max, self.nxhat, "xhat0max")]
+        S = _lib.Softness()
+        keep = []
+        if soft:
+            lens = dict(C_umin=self.nU, C_umax=self.nU, C_dumin=self.nDU, C_dumax=self.nDU, C_ymin=self.nY,
+                        C_ymax=self.nY, c_xmin=self.nxhat, c_xmax=self.nxhat)
+            for k, val in soft.items():
+                if val is None:
+                    continue
+                a = np.ascontiguousarray(np.asarray(val, dtype=np.float64).reshape(lens[k]))
+                keep.append(a)
+                setattr(S, k, dptr(a))
+        check(_lib.lib().bmpc_set_constraints(self._h, *[dptr(a) for a in arrs], C.byref(S)))
+
+    # ---- per-period call (= moveinput!) ----------------------------------------------------
+    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None):
+        N = self.N
+        x = _vec(xhat0, N, self.nxhat, "xhat0")
+        ryv = None if ry is None else _vec(ry, N, self.ny, "ry")
+        Ry = None if Rhat_y is None else _vec(Rhat_y, N, self.nY, "Rhat_y")
+        Ru = None if Rhat_u is None else _vec(Rhat_u, N, self.nU, "Rhat_u")
+        d0v = None if d0 is None or self.nd == 0 else _vec(d0, N, self.nd, "d0")
+        Dh = None if Dhat0 is None or self.nd == 0 else _vec(Dhat0, N, self.nd * self.Hp, "Dhat0")
+        p = lambda a: None if a is None else a.ctypes.data
+        io = _lib.StepIO(xhat0=p(x), lastu0=p(self.lastu0), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v),
+                         Dhat0=p(Dh), Ztilde=p(self.Ztilde), u=p(self.u), J=p(self.J), status=p(self.status),
+                         iters=p(self.iters), device_ptrs=0, sync=1)
+        check(_lib.lib().bmpc_step(self._h, C.byref(io)))
+        return self.u
+
+    def step_device(self, ptrs, sync=False):
+        """Device-pointer variant: ``ptrs`` maps StepIO field names to raw device addresses (ints)."""
+        io = _lib.StepIO(device_ptrs=1, sync=int(sync), **ptrs)
+        check(_lib.lib().bmpc_step(self._h, C.byref(io)))
+
+    def set_stream(self, stream_ptr):
+        check(_lib.lib().bmpc_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def getinfo(self):
+        N = self.N
+        out = dict(Yhat0=np.zeros((N, self.nY)), U0=np.zeros((N, self.nU)), xhat0end=np.zeros((N, self.nxhat)),
+                   F=np.zeros((N, self.nY)), qtilde=np.zeros((N, self.n)), r=np.zeros(N))
+        info = _lib.Info(**{k: v.ctypes.data for k, v in out.items()})
+        check(_lib.lib().bmpc_getinfo(self._h, C.byref(info)))
+        out.update(DU=self.Ztilde[:, :self.nDU].copy(), eps=self.Ztilde[:, -1].copy() if self.neps else np.zeros(N),
+                   J=self.J.copy(), status=self.status.copy(), iters=self.iters.copy())
+        return out
+
+    def launch_info(self):
+        out = (C.c_int32 * 8)()
+        check(_lib.lib().bmpc_launch_info(self._h, out))
+        keys = ("team", "teams_per_cta", "grid", "smem_bytes_per_cta", "pd_in_smem", "rows_m", "sparse_rows", "dense_rows")
+        return dict(zip(keys, list(out)))
+
+    def launch_count(self):
+        return int(_lib.lib().bmpc_launch_count(self._h))

@@ -1,0 +1,809 @@
+// Host side of libbmpc.so: the C ABI declared in include/bmpc.h.
+//  - owns all device memory of a batch of LinMPC controllers,
+//  - "compiles" the constraint structure (setconstraint!, construct.jl:324-559 and
+//    init_matconstraint_mpc, transcription.jl:667-703) into merged row tables in input-level
+//    coordinates,
+//  - launches the step kernel (bmpc_device.cuh).
+// No CPU fallback exists: without a CUDA device bmpc_create fails with BMPC_ERR_CUDA.
+#include "../../include/bmpc.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "bmpc_device.cuh"
+#include "bmpc_setup.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(BMPC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+inline int even(int v) { return (v + 1) & ~1; }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct bmpc_handle {
+    bmpc_dims d;
+    std::vector<int> nb, blk_of_t, blk_start;
+    int nz, n, nY, nU, nHp2, nEv2;
+    const double *last_Z = nullptr, *last_xhat0 = nullptr;  // device pointers used by the last step (getinfo)
+    long NM;  // number of model copies: N or 1 (shared_model)
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    int num_sms = 148;
+    bool have_predmat = false, have_weights = false, have_constraints = false, stepped = false;
+    bool has_terminal_mats = false, M_dense = false, has_L = false;
+    // model-dependent constants
+    DevBuf<double> E, ex, Ht;                         // reference coordinates (kept for getinfo)
+    DevBuf<double> Ev, exv, Hv, Lv, Hee, K, V, B, G, J, kx, vx, bx, gx, jx, Mw, Lw, uop, yop;
+    DevBuf<int> lv_ok;
+    // constraint tables
+    bmpc::RowTables rt{};
+    DevBuf<int> t_si1, t_si2, t_sch, t_varptr, t_varrow, t_varsgn, t_dbrmax, t_dbrmin, t_drbase, t_drsrc, t_blk,
+        t_blkstart, t_pdsrc;
+    DevBuf<short> t_pi, t_pj;
+    DevBuf<double> t_sig, t_c, sbase, dbound, Pd;
+    std::vector<unsigned char> pattern;  // finiteness pattern of the bounds (frozen after first step)
+    int nPd2 = 0;
+    bool pd_is_ev = false, pd_in_smem = false, has_terminal_rows = false;
+    // io staging
+    DevBuf<double> xhat0, lastu0, ry, Rhat_y, Rhat_u, d0, Dhat0, Z, u, Jv, F, qt, r, lastu_prev;
+    DevBuf<int> status, iters;
+    DevBuf<unsigned int> counters;
+    // launch geometry
+    int team = 0, teams_per_cta = 0, grid = 0, smem_bytes = 0;
+    bmpc::SmemLayout sm{};
+    int64_t launches = 0;
+};
+
+namespace {
+
+int choose_team(const bmpc_handle* h) {
+    if (h->d.team) return h->d.team;
+    const int n = h->n;
+    if (n <= 16) return 16;
+    if (n <= 48) return 32;
+    if (n <= 112) return 128;
+    return 256;
+}
+
+// shared-memory slice of one team, in doubles (every offset even => 16-byte aligned)
+void layout_smem(bmpc_handle* h, bool pd_in_smem) {
+    const int n = h->n, nz = h->nz, m = h->rt.m, nDb = h->rt.nDb, nY = h->nY, nx = h->d.nxhat;
+    bmpc::SmemLayout& L = h->sm;
+    int o = 0;
+    auto take = [&](int cnt) {
+        int at = o;
+        o += even(std::max(cnt, 1));
+        return at;
+    };
+    L.Pd = take(pd_in_smem ? h->nPd2 : 0);
+    L.Hv = take(h->nHp2);
+    L.Phi = take(std::max(even(n * (n + 1) / 2), h->nHp2));
+    L.x = take(n);
+    L.q = take(n);
+    L.rd = take(n);
+    L.rhs = take(n);
+    L.dx = take(n);
+    L.invd = take(n);
+    L.F = take(nY);
+    L.tY = take(nY);
+    L.fx = take(nx);
+    L.yb = take(nDb);
+    L.ybd = take(nDb);
+    L.wd = take(nDb);
+    L.s = take(m);
+    L.lam = take(m);
+    L.h = take(m);
+    L.rp = take(m);
+    L.t = take(m);
+    L.ds = take(m);
+    L.dl = take(std::max(m, nY));
+    L.xhat = take(nx);
+    L.lastu = take(h->d.nu);
+    L.dd = take(h->d.nd);
+    L.Dh = take(h->d.nd * h->d.Hp);
+    L.red = take(40);
+    L.bar = take(2);
+    L.total = o;
+    (void)nz;
+}
+
+template <int TEAM>
+int configure(bmpc_handle* h) {
+    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    const size_t pd_bytes = (size_t)h->nPd2 * 8;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
+    h->team = TEAM;
+    h->teams_per_cta = CTA / TEAM;
+    bool in_smem = h->rt.nDb > 0 && pd_bytes <= 96 * 1024;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        layout_smem(h, in_smem);
+        h->smem_bytes = h->sm.total * 8 * h->teams_per_cta;
+        if (h->smem_bytes <= max_optin) break;
+        if (!in_smem) return fail(BMPC_ERR_UNSUPPORTED, "problem too large for shared memory (%d B per CTA)", h->smem_bytes);
+        in_smem = false;
+    }
+    h->pd_in_smem = in_smem;
+    CK(cudaFuncSetAttribute(bmpc::step_kernel<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmpc::step_kernel<TEAM>, CTA, h->smem_bytes));
+    if (occ < 1) return fail(BMPC_ERR_UNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", h->smem_bytes);
+    const int need = (h->d.N + h->teams_per_cta - 1) / h->teams_per_cta;
+    h->grid = std::max(1, std::min(need, occ * h->num_sms));
+    return BMPC_OK;
+}
+
+int configure_launch(bmpc_handle* h) {
+    switch (choose_team(h)) {
+        case 8: return configure<8>(h);
+        case 16: return configure<16>(h);
+        case 32: return configure<32>(h);
+        case 64: return configure<64>(h);
+        case 128: return configure<128>(h);
+        case 256: return configure<256>(h);
+        default: return fail(BMPC_ERR_ARG, "team must be one of 0,8,16,32,64,128,256");
+    }
+}
+
+template <int TEAM>
+cudaError_t launch_step(bmpc_handle* h, const bmpc::StepParams& P) {
+    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    bmpc::step_kernel<TEAM><<<h->grid, CTA, h->smem_bytes, h->stream>>>(P);
+    return cudaGetLastError();
+}
+
+// copy N*len doubles from a host array (or replicate nothing): returns device pointer via buf
+cudaError_t up(DevBuf<double>& buf, const double* src, size_t count, cudaStream_t s) { return buf.upload(src, count, s); }
+
+}  // namespace
+
+extern "C" {
+
+const char* bmpc_last_error(void) { return g_err.c_str(); }
+int bmpc_version(void) { return 100; }
+
+int bmpc_create(bmpc_handle** out, const bmpc_dims* dims, const int32_t* nb) {
+    if (!out || !dims || !nb) return fail(BMPC_ERR_ARG, "null argument");
+    const bmpc_dims& d = *dims;
+    if (d.N < 1 || d.nu < 1 || d.ny < 1 || d.nd < 0 || d.nxhat < 1 || d.Hp < 1 || d.Hc < 1 || d.Hc > d.Hp ||
+        (d.neps != 0 && d.neps != 1))
+        return fail(BMPC_ERR_ARG, "invalid dimensions");
+    int sum = 0;
+    for (int i = 0; i < d.Hc; ++i) {
+        if (nb[i] < 1) return fail(BMPC_ERR_ARG, "move blocking entries must be >= 1");
+        sum += nb[i];
+    }
+    if (sum != d.Hp) return fail(BMPC_ERR_ARG, "sum(nb) = %d must equal Hp = %d (move_blocking, construct.jl:629-660)", sum, d.Hp);
+    if (d.nu * d.Hc + d.neps > 30000) return fail(BMPC_ERR_UNSUPPORTED, "too many decision variables");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BMPC_ERR_CUDA, "no CUDA device: libbmpc has no CPU fallback (%s)", cudaGetErrorString(e));
+    if (d.device < 0 || d.device >= ndev) return fail(BMPC_ERR_ARG, "device %d out of range", d.device);
+    CK(cudaSetDevice(d.device));
+    bmpc_handle* h = new bmpc_handle();
+    h->d = d;
+    if (h->d.max_iter <= 0) h->d.max_iter = 50;
+    if (!(h->d.tol > 0)) h->d.tol = 1e-11;
+    h->nb.assign(nb, nb + d.Hc);
+    h->blk_start.assign(d.Hc + 1, 0);
+    for (int l = 0; l < d.Hc; ++l) {
+        h->blk_start[l + 1] = h->blk_start[l] + nb[l];
+        for (int t = 0; t < nb[l]; ++t) h->blk_of_t.push_back(l);
+    }
+    h->nz = d.nu * d.Hc;
+    h->n = h->nz + d.neps;
+    h->nY = d.ny * d.Hp;
+    h->nU = d.nu * d.Hp;
+    h->nHp2 = even(h->nz * (h->nz + 1) / 2);
+    h->nEv2 = even(h->nY * h->nz);
+    h->NM = d.shared_model ? 1 : d.N;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, d.device);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(BMPC_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    h->stream = h->own_stream;
+    const size_t N = d.N;
+    cudaError_t a = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (a == cudaSuccess) a = r; };
+    A(h->xhat0.alloc(N * d.nxhat));
+    A(h->lastu0.alloc(N * d.nu));
+    A(h->ry.alloc(N * d.ny));
+    A(h->Z.alloc(N * h->n));
+    A(h->u.alloc(N * d.nu));
+    A(h->Jv.alloc(N));
+    A(h->F.alloc(N * h->nY));
+    A(h->qt.alloc(N * h->n));
+    A(h->r.alloc(N));
+    A(h->lastu_prev.alloc(N * d.nu));
+    A(h->status.alloc(N));
+    A(h->iters.alloc(N));
+    A(h->counters.alloc(2));
+    A(h->t_blk.upload(h->blk_of_t, h->stream));
+    A(h->t_blkstart.upload(h->blk_start, h->stream));
+    if (a == cudaSuccess) a = cudaMemsetAsync(h->counters.p, 0, 2 * sizeof(unsigned), h->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(h->Z.p, 0, N * h->n * sizeof(double), h->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(h->lastu0.p, 0, N * d.nu * sizeof(double), h->stream);
+    if (a == cudaSuccess) a = cudaStreamSynchronize(h->stream);
+    if (a != cudaSuccess) {
+        bmpc_destroy(h);
+        return fail(BMPC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(a));
+    }
+    *out = h;
+    return BMPC_OK;
+}
+
+int bmpc_destroy(bmpc_handle* h) {
+    if (!h) return BMPC_OK;
+    cudaSetDevice(h->d.device);
+    cudaDeviceSynchronize();
+    DevBuf<double>* bufs[] = {&h->E, &h->ex, &h->Ht, &h->Ev, &h->exv, &h->Hv, &h->Lv, &h->Hee, &h->K, &h->V, &h->B,
+                              &h->G, &h->J, &h->kx, &h->vx, &h->bx, &h->gx, &h->jx, &h->Mw, &h->Lw, &h->uop,
+                              &h->yop, &h->t_sig, &h->t_c, &h->sbase, &h->dbound, &h->Pd, &h->xhat0, &h->lastu0,
+                              &h->ry, &h->Rhat_y, &h->Rhat_u, &h->d0, &h->Dhat0, &h->Z, &h->u, &h->Jv, &h->F,
+                              &h->qt, &h->r, &h->lastu_prev};
+    for (auto* b : bufs) b->release();
+    DevBuf<int>* ibufs[] = {&h->lv_ok, &h->t_si1, &h->t_si2, &h->t_sch, &h->t_varptr, &h->t_varrow, &h->t_varsgn,
+                            &h->t_dbrmax, &h->t_dbrmin, &h->t_drbase, &h->t_drsrc, &h->t_blk, &h->t_blkstart,
+                            &h->t_pdsrc, &h->status, &h->iters};
+    for (auto* b : ibufs) b->release();
+    h->t_pi.release();
+    h->t_pj.release();
+    h->counters.release();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return BMPC_OK;
+}
+
+int bmpc_set_stream(bmpc_handle* h, void* stream) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return BMPC_OK;
+}
+
+int bmpc_set_predmat(bmpc_handle* h, const double* E, const double* K, const double* V, const double* B,
+                     const double* G, const double* J, const double* Htilde, const double* ex, const double* kx,
+                     const double* vx, const double* bx, const double* gx, const double* jx) {
+    if (!h || !E || !K || !V || !B || !Htilde) return fail(BMPC_ERR_ARG, "null argument");
+    const bmpc_dims& d = h->d;
+    if (d.nd > 0 && (!G || !J)) return fail(BMPC_ERR_ARG, "G and J are required when nd > 0");
+    const bool term = ex && kx && vx && bx;
+    if (term && d.nd > 0 && (!gx || !jx)) return fail(BMPC_ERR_ARG, "gx and jx are required when nd > 0");
+    if (h->have_constraints && h->has_terminal_rows && !term)
+        return fail(BMPC_ERR_STATE, "terminal constraints are active: the terminal matrices are required");
+    CK(cudaSetDevice(d.device));
+    cudaStream_t s = h->stream;
+    const size_t NM = h->NM, nY = h->nY, nz = h->nz, n = h->n, nx = d.nxhat, nu = d.nu, nd = d.nd, Hp = d.Hp;
+    CK(up(h->E, E, NM * nY * nz, s));
+    CK(up(h->K, K, NM * nY * nx, s));
+    CK(up(h->V, V, NM * nY * nu, s));
+    CK(up(h->B, B, NM * nY, s));
+    CK(up(h->Ht, Htilde, NM * n * n, s));
+    if (nd > 0) {
+        CK(up(h->G, G, NM * nY * nd, s));
+        CK(up(h->J, J, NM * nY * nd * Hp, s));
+    }
+    h->has_terminal_mats = term;
+    if (term) {
+        CK(up(h->ex, ex, NM * nx * nz, s));
+        CK(up(h->kx, kx, NM * nx * nx, s));
+        CK(up(h->vx, vx, NM * nx * nu, s));
+        CK(up(h->bx, bx, NM * nx, s));
+        if (nd > 0) {
+            CK(up(h->gx, gx, NM * nx * nd, s));
+            CK(up(h->jx, jx, NM * nx * nd * Hp, s));
+        }
+    }
+    // level coordinates: Ev = E*D, exv = ex*D, Hv = D'H̃D (packed), Lv = chol(Hv)
+    CK(h->Ev.alloc(NM * h->nEv2));
+    CK(cudaMemsetAsync(h->Ev.p, 0, NM * h->nEv2 * sizeof(double), s));
+    CK(h->Hv.alloc(NM * h->nHp2));
+    CK(h->Lv.alloc(NM * h->nHp2));
+    CK(h->Hee.alloc(NM));
+    CK(h->lv_ok.alloc(NM));
+    CK(cudaMemsetAsync(h->Hv.p, 0, NM * h->nHp2 * sizeof(double), s));
+    CK(cudaMemsetAsync(h->Lv.p, 0, NM * h->nHp2 * sizeof(double), s));
+    const int TB = 256;
+    {
+        const long tot = (long)NM * nY * nz;
+        bmpc::k_level_cols<<<(unsigned)((tot + TB - 1) / TB), TB, 0, s>>>(h->E.p, h->Ev.p, (int)nY, (int)nz, (int)nu, (long)h->nEv2, tot);
+        h->launches++;
+    }
+    if (term) {
+        CK(h->exv.alloc(NM * nx * nz));
+        const long tot = (long)NM * nx * nz;
+        bmpc::k_level_cols<<<(unsigned)((tot + TB - 1) / TB), TB, 0, s>>>(h->ex.p, h->exv.p, (int)nx, (int)nz, (int)nu, (long)(nx * nz), tot);
+        h->launches++;
+    }
+    {
+        const int npair = (int)(nz * (nz + 1) / 2);
+        const long tot = (long)NM * npair;
+        bmpc::k_level_hess<<<(unsigned)((tot + TB - 1) / TB), TB, 0, s>>>(h->Ht.p, h->Hv.p, h->Hee.p, (int)n, (int)nz, (int)nu,
+                                                                         d.neps, h->nHp2, npair, tot);
+        bmpc::k_chol_serial<<<(unsigned)((NM + 63) / 64), 64, 0, s>>>(h->Hv.p, h->Lv.p, h->lv_ok.p, (int)nz, h->nHp2, (int)NM);
+        h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    h->have_predmat = true;
+    if (h->have_constraints) {  // Pd depends on Ev / exv
+        if (!h->pd_is_ev && h->rt.nDb > 0) {
+            const long tot = (long)NM * h->rt.nDb * nz;
+            bmpc::k_gather_pd<<<(unsigned)((tot + TB - 1) / TB), TB, 0, s>>>(h->Ev.p, term ? h->exv.p : nullptr, h->Pd.p, h->t_pdsrc.p,
+                                                                            (int)nY, (int)nx, (int)nz, h->rt.nDb, (long)h->nEv2, h->nPd2, tot);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    return BMPC_OK;
+}
+
+int bmpc_set_weights(bmpc_handle* h, const double* M, int32_t M_dense, const double* L_diag) {
+    if (!h || !M) return fail(BMPC_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->d.device));
+    const size_t NM = h->NM, nY = h->nY;
+    CK(up(h->Mw, M, NM * (M_dense ? nY * nY : nY), h->stream));
+    h->M_dense = M_dense != 0;
+    h->has_L = false;
+    if (L_diag) {
+        bool any = false;
+        for (size_t i = 0; i < NM * (size_t)h->nU && !any; ++i) any = L_diag[i] != 0.0;
+        if (any) {  // iszero_L_Hp short-circuit, construct.jl:86 / execute.jl:268
+            CK(up(h->Lw, L_diag, NM * h->nU, h->stream));
+            h->has_L = true;
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_weights = true;
+    return BMPC_OK;
+}
+
+int bmpc_set_oppoints(bmpc_handle* h, const double* uop, const double* yop) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->d.device));
+    const size_t NM = h->NM;
+    std::vector<double> z;
+    if (uop) {
+        CK(up(h->uop, uop, NM * h->d.nu, h->stream));
+    } else {
+        z.assign(NM * h->d.nu, 0.0);
+        CK(h->uop.upload(z, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (yop) {
+        CK(up(h->yop, yop, NM * h->d.ny, h->stream));
+    } else {
+        z.assign(NM * h->d.ny, 0.0);
+        CK(h->yop.upload(z, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return BMPC_OK;
+}
+
+int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0max, const double* DUmin,
+                         const double* DUmax, const double* Y0min, const double* Y0max, const double* x0min,
+                         const double* x0max, const bmpc_softness* soft) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    const bmpc_dims& d = h->d;
+    CK(cudaSetDevice(d.device));
+    const int N = d.N, nu = d.nu, nz = h->nz, nY = h->nY, nU = h->nU, nx = d.nxhat, neps = d.neps;
+    const double INF = INFINITY;
+    auto get = [&](const double* a, int len, int i, int k, double dflt) { return a ? a[(size_t)i * len + k] : dflt; };
+    auto softv = [&](const double* a, int k, double dflt) { return (neps && a) ? a[k] : (neps ? dflt : 0.0); };
+    const bmpc_softness S = soft ? *soft : bmpc_softness{};
+    // ---- finiteness pattern (shared by all instances) ----
+    const int plen = 2 * nU + 2 * nz + 2 * nY + 2 * nx;
+    std::vector<unsigned char> pat(plen, 0);
+    const double* arrs[8] = {U0min, U0max, DUmin, DUmax, Y0min, Y0max, x0min, x0max};
+    const int lens[8] = {nU, nU, nz, nz, nY, nY, nx, nx};
+    for (int i = 0; i < N; ++i) {
+        int o = 0;
+        for (int a = 0; a < 8; ++a) {
+            for (int k = 0; k < lens[a]; ++k, ++o) {
+                const double v = get(arrs[a], lens[a], i, k, (a & 1) ? INF : -INF);
+                if (std::isnan(v)) return fail(BMPC_ERR_ARG, "NaN bound");
+                const unsigned char fin = std::isfinite(v) ? 1 : 0;
+                if (i == 0)
+                    pat[o] = fin;
+                else if (pat[o] != fin)
+                    return fail(BMPC_ERR_ARG, "all instances of a handle must share the +-Inf pattern of their bounds");
+            }
+        }
+    }
+    if (h->stepped && pat != h->pattern)
+        return fail(BMPC_ERR_STATE, "Cannot modify +-Inf constraints after the first step (construct.jl:548-551)");
+    const bool any_x = std::any_of(pat.begin() + 2 * nU + 2 * nz + 2 * nY, pat.end(), [](unsigned char c) { return c; });
+    if (any_x && h->have_predmat && !h->has_terminal_mats)
+        return fail(BMPC_ERR_ARG, "terminal bounds need the terminal matrices (bmpc_set_predmat ex,kx,vx,bx)");
+    // ---- sparse (1-/2-variable) rows, merged by (i1, i2, side, softness, shift channel) ----
+    struct Src { int arr, k; };
+    typedef std::tuple<int, int, int, double, int> Key;
+    std::map<Key, int> groups;
+    std::vector<Key> gkeys;
+    std::vector<std::vector<Src>> gsrc;
+    auto add = [&](int i1, int i2, int side, double c, int ch, int arr, int k) {
+        Key key(i1, i2, side, c, ch);
+        auto it = groups.find(key);
+        int g;
+        if (it == groups.end()) {
+            g = (int)gkeys.size();
+            groups[key] = g;
+            gkeys.push_back(key);
+            gsrc.emplace_back();
+        } else {
+            g = it->second;
+        }
+        gsrc[g].push_back({arr, k});
+    };
+    for (int t = 0; t < d.Hp; ++t)
+        for (int ch = 0; ch < nu; ++ch) {
+            const int k = t * nu + ch, var = h->blk_of_t[t] * nu + ch;
+            if (pat[k]) add(var, -1, -1, softv(S.C_umin, k, 0.0), ch, 0, k);
+            if (pat[nU + k]) add(var, -1, +1, softv(S.C_umax, k, 0.0), ch, 1, k);
+        }
+    for (int k = 0; k < nz; ++k) {
+        const int i2 = k >= nu ? k - nu : -1;
+        if (pat[2 * nU + k]) add(k, i2, -1, softv(S.C_dumin, k, 0.0), -1, 2, k);
+        if (pat[2 * nU + nz + k]) add(k, i2, +1, softv(S.C_dumax, k, 0.0), -1, 3, k);
+    }
+    const int nS = (int)gkeys.size();
+    // ---- dense rows ----
+    std::vector<int> dr_base, dr_src, db_rmax, db_rmin, pd_src;
+    std::vector<double> sig, cc;
+    std::vector<int> s_i1(nS), s_i2(nS), s_ch(nS);
+    for (int g = 0; g < nS; ++g) {
+        s_i1[g] = std::get<0>(gkeys[g]);
+        s_i2[g] = std::get<1>(gkeys[g]);
+        sig.push_back((double)std::get<2>(gkeys[g]));
+        cc.push_back(std::get<3>(gkeys[g]));
+        s_ch[g] = std::get<4>(gkeys[g]);
+    }
+    struct DSrc { int arr, k; };
+    std::vector<DSrc> dsrc;
+    const int oY = 2 * nU + 2 * nz, oX = oY + 2 * nY;
+    auto add_dense = [&](int src, bool hasmin, bool hasmax, double cmin, double cmax, int arrmin, int arrmax, int k) {
+        if (!hasmin && !hasmax) return;
+        const int base = (int)pd_src.size();
+        pd_src.push_back(src);
+        db_rmax.push_back(-1);
+        db_rmin.push_back(-1);
+        if (hasmin) {
+            db_rmin[base] = nS + (int)dr_base.size();
+            dr_base.push_back(base);
+            dr_src.push_back(src);
+            sig.push_back(-1.0);
+            cc.push_back(cmin);
+            dsrc.push_back({arrmin, k});
+        }
+        if (hasmax) {
+            db_rmax[base] = nS + (int)dr_base.size();
+            dr_base.push_back(base);
+            dr_src.push_back(src);
+            sig.push_back(+1.0);
+            cc.push_back(cmax);
+            dsrc.push_back({arrmax, k});
+        }
+    };
+    for (int t = 0; t < nY; ++t)
+        add_dense(t, pat[oY + t], pat[oY + nY + t], softv(S.C_ymin, t, 1.0), softv(S.C_ymax, t, 1.0), 4, 5, t);
+    for (int i = 0; i < nx; ++i)
+        add_dense(nY + i, pat[oX + i], pat[oX + nx + i], softv(S.c_xmin, i, 1.0), softv(S.c_xmax, i, 1.0), 6, 7, i);
+    const int nDr = (int)dr_base.size(), nDb = (int)pd_src.size();
+    if (neps) {
+        sig.push_back(0.0);
+        cc.push_back(1.0);
+    }
+    const int m = nS + nDr + neps;
+    if (h->stepped && m != h->rt.m) return fail(BMPC_ERR_STATE, "constraint structure changed after the first step");
+    for (double c : cc)
+        if (c < 0) return fail(BMPC_ERR_ARG, "softness weights should be non-negative (construct.jl:456)");
+    // ---- CSR variable -> sparse rows ----
+    std::vector<int> var_ptr(nz + 1, 0), var_row, var_sgn;
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<int> cnt(nz, 0);
+        for (int g = 0; g < nS; ++g) {
+            const int a = s_i1[g], b = s_i2[g];
+            if (pass == 0) {
+                var_ptr[a + 1]++;
+                if (b >= 0) var_ptr[b + 1]++;
+            } else {
+                var_row[var_ptr[a] + cnt[a]] = g;
+                var_sgn[var_ptr[a] + cnt[a]++] = +1;
+                if (b >= 0) {
+                    var_row[var_ptr[b] + cnt[b]] = g;
+                    var_sgn[var_ptr[b] + cnt[b]++] = -1;
+                }
+            }
+        }
+        if (pass == 0) {
+            for (int j = 0; j < nz; ++j) var_ptr[j + 1] += var_ptr[j];
+            var_row.assign(var_ptr[nz], 0);
+            var_sgn.assign(var_ptr[nz], 0);
+        }
+    }
+    std::vector<short> pi, pj;
+    for (int i = 0; i < nz; ++i)
+        for (int j = 0; j <= i; ++j) {
+            pi.push_back((short)i);
+            pj.push_back((short)j);
+        }
+    // ---- per-instance numeric bounds ----
+    std::vector<double> sbase((size_t)N * std::max(nS, 1)), dbound((size_t)N * std::max(nDr, 1));
+    for (int i = 0; i < N; ++i) {
+        for (int g = 0; g < nS; ++g) {
+            const double sg = sig[g];
+            double best = INF;
+            for (const Src& s : gsrc[g]) best = std::min(best, sg * arrs[s.arr][(size_t)i * lens[s.arr] + s.k]);
+            sbase[(size_t)i * nS + g] = best;
+        }
+        for (int r = 0; r < nDr; ++r) dbound[(size_t)i * nDr + r] = arrs[dsrc[r].arr][(size_t)i * lens[dsrc[r].arr] + dsrc[r].k];
+    }
+    cudaStream_t s = h->stream;
+    CK(h->t_si1.upload(s_i1, s));
+    CK(h->t_si2.upload(s_i2, s));
+    CK(h->t_sch.upload(s_ch, s));
+    CK(h->t_sig.upload(sig, s));
+    CK(h->t_c.upload(cc, s));
+    CK(h->t_varptr.upload(var_ptr, s));
+    CK(h->t_varrow.upload(var_row, s));
+    CK(h->t_varsgn.upload(var_sgn, s));
+    CK(h->t_dbrmax.upload(db_rmax, s));
+    CK(h->t_dbrmin.upload(db_rmin, s));
+    CK(h->t_drbase.upload(dr_base, s));
+    CK(h->t_drsrc.upload(dr_src, s));
+    CK(h->t_pdsrc.upload(pd_src, s));
+    CK(h->t_pi.upload(pi, s));
+    CK(h->t_pj.upload(pj, s));
+    CK(h->sbase.upload(sbase, s));
+    CK(h->dbound.upload(dbound, s));
+    bmpc::RowTables& rt = h->rt;
+    rt.nS = nS;
+    rt.nDr = nDr;
+    rt.nDb = nDb;
+    rt.m = m;
+    rt.s_i1 = h->t_si1.p;
+    rt.s_i2 = h->t_si2.p;
+    rt.s_ch = h->t_sch.p;
+    rt.row_sig = h->t_sig.p;
+    rt.row_c = h->t_c.p;
+    rt.var_ptr = h->t_varptr.p;
+    rt.var_row = h->t_varrow.p;
+    rt.var_sgn = h->t_varsgn.p;
+    rt.db_rmax = h->t_dbrmax.p;
+    rt.db_rmin = h->t_dbrmin.p;
+    rt.dr_base = h->t_drbase.p;
+    rt.dr_src = h->t_drsrc.p;
+    rt.pair_i = h->t_pi.p;
+    rt.pair_j = h->t_pj.p;
+    h->has_terminal_rows = any_x;
+    h->pd_is_ev = (nDb == nY) && !any_x;  // dense base rows are exactly the rows of Ev, in order
+    h->nPd2 = even(nDb * nz);
+    if (!h->pd_is_ev && nDb > 0) {
+        CK(h->Pd.alloc((size_t)h->NM * h->nPd2));
+        CK(cudaMemsetAsync(h->Pd.p, 0, (size_t)h->NM * h->nPd2 * sizeof(double), s));
+        if (h->have_predmat) {
+            const long tot = (long)h->NM * nDb * nz;
+            bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->has_terminal_mats ? h->exv.p : nullptr, h->Pd.p,
+                                                                          h->t_pdsrc.p, nY, nx, nz, nDb, (long)h->nEv2, h->nPd2, tot);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    h->pattern = pat;
+    h->have_constraints = true;
+    int rc = configure_launch(h);
+    if (rc != BMPC_OK) return rc;
+    return BMPC_OK;
+}
+
+int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
+    if (!h || !io) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->have_predmat) return fail(BMPC_ERR_STATE, "bmpc_set_predmat / bmpc_set_model must be called before bmpc_step");
+    if (!h->have_weights) return fail(BMPC_ERR_STATE, "bmpc_set_weights must be called before bmpc_step");
+    const bmpc_dims& d = h->d;
+    CK(cudaSetDevice(d.device));
+    if (!h->have_constraints) {
+        int rc = bmpc_set_constraints(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc != BMPC_OK) return rc;
+    }
+    if (!h->uop.p) {
+        int rc = bmpc_set_oppoints(h, nullptr, nullptr);
+        if (rc != BMPC_OK) return rc;
+    }
+    if (!io->xhat0 || !io->lastu0 || (!io->ry && !io->Rhat_y) || !io->Ztilde || !io->u || !io->status || !io->iters)
+        return fail(BMPC_ERR_ARG, "xhat0, lastu0, ry|Rhat_y, Ztilde, u, status, iters are required");
+    if (d.nd > 0 && !io->d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
+    if (h->has_terminal_rows && !h->has_terminal_mats) return fail(BMPC_ERR_STATE, "terminal matrices missing");
+    cudaStream_t s = h->stream;
+    const size_t N = d.N, nx = d.nxhat, nu = d.nu, ny = d.ny, nd = d.nd, Hp = d.Hp, n = h->n, nY = h->nY, nU = h->nU;
+    bmpc::StepParams P{};
+    const bool dev = io->device_ptrs != 0;
+    auto in = [&](DevBuf<double>& buf, const double* src, size_t cnt, const double** dst) -> cudaError_t {
+        if (!src) { *dst = nullptr; return cudaSuccess; }
+        if (dev) { *dst = src; return cudaSuccess; }
+        cudaError_t e = buf.upload(src, cnt, s);
+        *dst = buf.p;
+        return e;
+    };
+    CK(in(h->xhat0, io->xhat0, N * nx, &P.xhat0));
+    CK(in(h->ry, io->ry, N * ny, &P.ry));
+    CK(in(h->Rhat_y, io->Rhat_y, N * nY, &P.Rhat_y));
+    CK(in(h->Rhat_u, io->Rhat_u, N * nU, &P.Rhat_u));
+    CK(in(h->d0, io->d0, N * nd, &P.d0));
+    CK(in(h->Dhat0, io->Dhat0, N * nd * Hp, &P.Dhat0));
+    if (dev) {
+        P.lastu0 = io->lastu0;
+        P.Z = io->Ztilde;
+        P.u = io->u;
+        P.J_out = io->J;
+        P.status = io->status;
+        P.iters = io->iters;
+    } else {
+        CK(cudaMemcpyAsync(h->lastu0.p, io->lastu0, N * nu * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->Z.p, io->Ztilde, N * n * 8, cudaMemcpyHostToDevice, s));
+        P.lastu0 = h->lastu0.p;
+        P.Z = h->Z.p;
+        P.u = h->u.p;
+        P.J_out = h->Jv.p;
+        P.status = h->status.p;
+        P.iters = h->iters.p;
+    }
+    P.N = d.N; P.nu = d.nu; P.ny = d.ny; P.nd = d.nd; P.nx = d.nxhat; P.Hp = d.Hp; P.Hc = d.Hc;
+    P.nz = h->nz; P.n = h->n; P.neps = d.neps; P.nY = h->nY; P.nU = h->nU;
+    P.max_iter = d.max_iter;
+    P.tol = d.tol;
+    P.tol_mu = d.tol * 1e-3;  // duality gap  s'lam <= tol_mu * (1+|q|)(1+|h|)
+    P.rt = h->rt;
+    P.sm = h->sm;
+    P.pd_in_smem = h->pd_in_smem; P.pd_is_ev = h->pd_is_ev; P.has_terminal = h->has_terminal_rows;
+    P.M_dense = h->M_dense; P.has_L = h->has_L;
+    const long sh = d.shared_model ? 0 : 1;
+    P.sEv = sh * h->nEv2; P.sH = sh * h->nHp2; P.sK = sh * nY * nx; P.sV = sh * nY * nu; P.sB = sh * nY;
+    P.sG = sh * nY * nd; P.sJ = sh * nY * nd * Hp; P.skx = sh * nx * nx; P.svx = sh * nx * nu; P.sbx = sh * nx;
+    P.sgx = sh * nx * nd; P.sjx = sh * nx * nd * Hp; P.sM = sh * (h->M_dense ? nY * nY : nY); P.sL = sh * nU;
+    P.suop = sh * nu; P.syop = sh * ny;
+    P.Ev = h->Ev.p; P.Hv = h->Hv.p; P.Lv = h->Lv.p; P.Hee = h->Hee.p; P.K = h->K.p; P.V = h->V.p; P.B = h->B.p;
+    P.G = h->G.p; P.J = h->J.p; P.kx = h->kx.p; P.vx = h->vx.p; P.bx = h->bx.p; P.gx = h->gx.p; P.jx = h->jx.p;
+    P.Mw = h->Mw.p; P.Lw = h->Lw.p; P.uop = h->uop.p; P.yop = h->yop.p; P.sbase = h->sbase.p; P.dbound = h->dbound.p;
+    P.lv_ok = h->lv_ok.p; P.blk_of_t = h->t_blk.p; P.blk_start = h->t_blkstart.p;
+    if (h->pd_is_ev) { P.Pd = h->Ev.p; P.sPd = P.sEv; } else { P.Pd = h->Pd.p; P.sPd = sh * h->nPd2; }
+    P.F_out = h->F.p; P.qt_out = h->qt.p; P.r_out = h->r.p; P.lastu_prev = h->lastu_prev.p;
+    P.counters = h->counters.p;
+    P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
+    cudaError_t le;
+    switch (h->team) {
+        case 8: le = launch_step<8>(h, P); break;
+        case 16: le = launch_step<16>(h, P); break;
+        case 32: le = launch_step<32>(h, P); break;
+        case 64: le = launch_step<64>(h, P); break;
+        case 128: le = launch_step<128>(h, P); break;
+        default: le = launch_step<256>(h, P); break;
+    }
+    if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(le));
+    h->launches++;
+    h->stepped = true;
+    h->last_Z = P.Z;
+    h->last_xhat0 = P.xhat0;
+    if (!dev) {
+        CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(io->u, h->u.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
+        if (io->J) CK(cudaMemcpyAsync(io->J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(io->status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (io->sync || !dev) CK(cudaStreamSynchronize(s));
+    return BMPC_OK;
+}
+
+int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
+    if (!h || !info) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->stepped) return fail(BMPC_ERR_STATE, "bmpc_getinfo needs a previous bmpc_step");
+    if (!h->E.p) return fail(BMPC_ERR_UNSUPPORTED, "bmpc_getinfo needs the reference-coordinate matrices (bmpc_set_predmat)");
+    const bmpc_dims& d = h->d;
+    CK(cudaSetDevice(d.device));
+    cudaStream_t s = h->stream;
+    const size_t N = d.N, nY = h->nY, nU = h->nU, nx = d.nxhat, n = h->n;
+    DevBuf<double> Y, U, X;
+    CK(Y.alloc(N * nY));
+    CK(U.alloc(N * nU));
+    CK(X.alloc(N * nx));
+    const long sh = d.shared_model ? 0 : 1;
+    bmpc::k_getinfo<<<(unsigned)N, 128, 0, s>>>(h->E.p, sh * (long)(nY * h->nz), h->has_terminal_mats ? h->ex.p : nullptr,
+                                              sh * (long)(nx * h->nz), h->kx.p, sh * (long)(nx * nx), h->vx.p,
+                                              sh * (long)(nx * d.nu), h->bx.p, sh * (long)nx, h->last_Z, h->F.p, h->last_xhat0,
+                                              h->lastu_prev.p, h->t_blk.p, Y.p, U.p, X.p, (int)nY, h->nz, (int)n, d.nu,
+                                              (int)nx, d.Hp);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (info->Yhat0) CK(cudaMemcpyAsync(info->Yhat0, Y.p, N * nY * 8, cudaMemcpyDeviceToHost, s));
+    if (info->U0) CK(cudaMemcpyAsync(info->U0, U.p, N * nU * 8, cudaMemcpyDeviceToHost, s));
+    if (info->xhat0end && h->has_terminal_mats) CK(cudaMemcpyAsync(info->xhat0end, X.p, N * nx * 8, cudaMemcpyDeviceToHost, s));
+    if (info->F) CK(cudaMemcpyAsync(info->F, h->F.p, N * nY * 8, cudaMemcpyDeviceToHost, s));
+    if (info->qtilde) CK(cudaMemcpyAsync(info->qtilde, h->qt.p, N * n * 8, cudaMemcpyDeviceToHost, s));
+    if (info->r) CK(cudaMemcpyAsync(info->r, h->r.p, N * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    Y.release();
+    U.release();
+    X.release();
+    return BMPC_OK;
+}
+
+int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
+    if (!h || !out) return fail(BMPC_ERR_ARG, "null argument");
+    out[0] = h->team;
+    out[1] = h->teams_per_cta;
+    out[2] = h->grid;
+    out[3] = h->smem_bytes;
+    out[4] = h->pd_in_smem;
+    out[5] = h->rt.m;
+    out[6] = h->rt.nS;
+    out[7] = h->rt.nDr;
+    return BMPC_OK;
+}
+
+int64_t bmpc_launch_count(bmpc_handle* h) { return h ? h->launches : 0; }
+
+int bmpc_set_model(bmpc_handle* h, const double*, const double*, const double*, const double*, const double*,
+                   const double*, const double*, const double*, const double*, double) {
+    (void)h;
+    return fail(BMPC_ERR_UNSUPPORTED, "bmpc_set_model: on-device init_predmat is not built yet (use bmpc_set_predmat)");
+}
+
+}  // extern "C"

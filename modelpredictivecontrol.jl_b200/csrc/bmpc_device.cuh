@@ -1,0 +1,788 @@
+// Device code of the batched LinMPC step (sm_100a).  See DESIGN.md for the algorithm and
+// include/bmpc.h for the reference functions each stage replaces.
+//
+// One TEAM of threads (8/16/32 lanes of a warp, or a whole CTA of 64..256 threads) owns one
+// controller instance at a time.  Per instance:
+//   stage 0  TMA bulk loads (cp.async.bulk + mbarrier) of the instance's dense constraint
+//            rows Pd, packed Hessian Hv and its Cholesky factor Lv from HBM into shared memory
+//   stage 1  initpred! + linconstraint!: F, q, r, fx, row right-hand sides h   (execute.jl:247-277,
+//            transcription.jl:811-848)
+//   stage 2  unconstrained exit: x = -Hv^-1 q with the cached factor; feasible -> done
+//            (ExplicitMPC, explicitmpc.jl:209)
+//   stage 3  Mehrotra predictor-corrector interior point; per iteration
+//            Phi = Hv + P' D P (dense rows by a pair loop, 1-/2-variable rows by a gather),
+//            packed Cholesky in shared memory, two triangular solve pairs
+//   stage 4  getinput!: Z = D x, u, lastu0, J, status               (execute.jl:536-546)
+// Coordinates: "input levels" x = [v; eps], v_l = sum_{i<=l} DU_i  (DESIGN.md section 3).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bmpc {
+
+constexpr int ST_OPTIMAL = 0, ST_ITERATION_LIMIT = 1, ST_INFEASIBLE = 2;  // = BMPC_STATUS_* in bmpc.h
+
+struct RowTables {
+    int nS, nDr, nDb, m;     // sparse rows, dense rows, dense base rows, total rows (incl. eps>=0)
+    const int* s_i1;         // [nS] variable with coefficient +sigma
+    const int* s_i2;         // [nS] variable with coefficient -sigma, or -1
+    const int* s_ch;         // [nS] input channel whose lastu0 shifts the bound, or -1
+    const double* row_sig;   // [m]  +1 (max side) / -1 (min side); eps row: 0
+    const double* row_c;     // [m]  softness c (coefficient of -eps); eps row: 1
+    const int* var_ptr;      // [nz+1] CSR variable -> sparse rows
+    const int* var_row;      //        row index
+    const int* var_sgn;      //        +1 if the variable is i1 of the row, -1 if i2
+    const int* db_rmax;      // [nDb] dense base row -> its max-side row index or -1
+    const int* db_rmin;      // [nDb] ... min-side row index or -1
+    const int* dr_base;      // [nDr] dense row -> base row k
+    const int* dr_src;       // [nDr] dense row -> source: t < nY (F[t]) or nY + i (fx[i])
+    const short* pair_i;     // [nz(nz+1)/2] row index of packed pair p
+    const short* pair_j;     //              col index
+};
+
+struct SmemLayout {  // offsets in doubles inside a team's slice
+    int Pd, Hv, Phi, x, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
+        xhat, lastu, dd, Dh, red, bar, total;
+};
+
+struct StepParams {
+    int N, nu, ny, nd, nx, Hp, Hc, nz, n, neps, nY, nU;
+    int max_iter;
+    double tol, tol_mu;
+    RowTables rt;
+    SmemLayout sm;
+    int pd_in_smem, pd_is_ev, has_terminal, M_dense, has_L;
+    long sPd, sEv, sH, sK, sV, sB, sG, sJ, skx, svx, sbx, sgx, sjx, sM, sL, suop, syop;
+    const double *Pd, *Ev, *Hv, *Lv, *Hee, *K, *V, *B, *G, *J, *kx, *vx, *bx, *gx, *jx, *Mw, *Lw,
+        *uop, *yop, *sbase, *dbound;
+    const int* lv_ok;
+    const int* blk_of_t;  // [Hp] move block of time step t
+    const int* blk_start; // [Hc+1] first time step of block l (j_l)
+    // per-step io (device pointers)
+    const double *xhat0, *ry, *Rhat_y, *Rhat_u, *d0, *Dhat0;
+    double *lastu0, *Z, *u, *J_out, *F_out, *qt_out, *r_out, *lastu_prev;
+    int *status, *iters;
+    unsigned int* counters;  // [2] work counter, finished-CTA counter
+    int nHp2, nPd2;          // padded (even) sizes in doubles of packed Hv and of Pd: TMA needs 16-byte multiples
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// Team: 8/16/32 lanes inside a warp (independent thread scheduling + masked sync), or a CTA.
+// ------------------------------------------------------------------------------------------
+template <int TEAM>
+struct Team {
+    static constexpr bool kSub = TEAM <= 32;
+    int tid;
+    unsigned mask;
+    double* red;  // CTA teams: 40 doubles of scratch
+    __device__ __forceinline__ void sync() const {
+        if (kSub)
+            __syncwarp(mask);
+        else
+            __syncthreads();
+    }
+    template <class Op>
+    __device__ __forceinline__ double reduce(double v, Op op, double ident) const {
+        if (kSub) {
+#pragma unroll
+            for (int o = TEAM / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(mask, v, o));
+            return v;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+            __syncthreads();
+            if ((tid & 31) == 0) red[tid >> 5] = v;
+            __syncthreads();
+            double r = ident;
+            for (int w = 0; w < TEAM / 32; ++w) r = op(r, red[w]);
+            return r;
+        }
+    }
+    __device__ __forceinline__ double sum(double v) const {
+        return reduce(v, [](double a, double b) { return a + b; }, 0.0);
+    }
+    __device__ __forceinline__ double max(double v) const {
+        return reduce(v, [](double a, double b) { return fmax(a, b); }, -1e300);
+    }
+    __device__ __forceinline__ double min(double v) const {
+        return reduce(v, [](double a, double b) { return fmin(a, b); }, 1e300);
+    }
+};
+
+__device__ __forceinline__ int pidx(int i, int j) { return (i * (i + 1)) / 2 + j; }  // i >= j
+
+// In-place packed (row-major lower) Cholesky, column-Crout with redundant diagonal; invd = 1/L_jj.
+// Returns number of guarded (non-positive) pivots (uniform across the team).
+template <int TEAM>
+__device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, double* invd, int n) {
+    int bad = 0;
+    for (int j = 0; j < n; ++j) {
+        const double* rj = A + pidx(j, 0);
+        double dj = rj[j];
+        for (int p = 0; p < j; ++p) dj = fma(-rj[p], rj[p], dj);
+        if (!(dj > 1e-280)) {
+            dj = 1e200;
+            ++bad;
+        }
+        const double ljj = sqrt(dj);
+        const double inv = 1.0 / ljj;
+        T.sync();  // everybody has read row j (incl. A[j][j]) before it is overwritten
+        for (int i = j + T.tid; i < n; i += TEAM) {
+            if (i == j) {
+                A[pidx(j, j)] = ljj;
+                invd[j] = inv;
+            } else {
+                double* ri = A + pidx(i, 0);
+                double a = ri[j];
+                for (int p = 0; p < j; ++p) a = fma(-ri[p], rj[p], a);
+                ri[j] = a * inv;
+            }
+        }
+        T.sync();
+    }
+    return bad;
+}
+
+// Solve L L' x = b in place (b -> x) with packed row-major L and invd.
+template <int TEAM>
+__device__ __forceinline__ void chol_solve(const Team<TEAM>& T, const double* L, const double* invd, double* b,
+                                           int n) {
+    for (int j = 0; j < n; ++j) {  // forward
+        T.sync();
+        const double yj = b[j] * invd[j];
+        for (int i = j + 1 + T.tid; i < n; i += TEAM) b[i] = fma(-L[pidx(i, j)], yj, b[i]);
+        T.sync();
+        if (T.tid == 0) b[j] = yj;
+    }
+    for (int j = n - 1; j >= 0; --j) {  // backward
+        T.sync();
+        const double xj = b[j] * invd[j];
+        const double* rj = L + pidx(j, 0);
+        for (int i = T.tid; i < j; i += TEAM) b[i] = fma(-rj[i], xj, b[i]);
+        T.sync();
+        if (T.tid == 0) b[j] = xj;
+    }
+    T.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// Structured row operators.  Row r:  g_r'x = sig_r * (p_r'v) - c_r * eps
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+    const StepParams* P;
+    const double* Pd;  // dense base rows [nDb x nz], column-major, ld = nDb (shared or global memory)
+    double *x, *q, *rd, *rhs, *dx, *invd, *F, *tY, *fx, *yb, *ybd, *wd, *s, *lam, *h, *rp, *t, *ds, *dl, *Hv, *Phi;
+};
+
+// yout[k] = sum_j Pd[k, j] * v[j]
+template <int TEAM>
+__device__ __forceinline__ void dense_apply(const Team<TEAM>& T, const Ctx& c, const double* v, double* yout) {
+    const int nDb = c.P->rt.nDb, nz = c.P->nz;
+    for (int k = T.tid; k < nDb; k += TEAM) {
+        double a0 = 0.0, a1 = 0.0;
+        int j = 0;
+        for (; j + 1 < nz; j += 2) {
+            a0 = fma(c.Pd[k + (long)nDb * j], v[j], a0);
+            a1 = fma(c.Pd[k + (long)nDb * (j + 1)], v[j + 1], a1);
+        }
+        if (j < nz) a0 = fma(c.Pd[k + (long)nDb * j], v[j], a0);
+        yout[k] = a0 + a1;
+    }
+}
+
+// value of g_r'vec for row r given the dense base products ybase = Pd * vec_v
+__device__ __forceinline__ double row_gx(const Ctx& c, int r, const double* vec, const double* ybase) {
+    const RowTables& rt = c.P->rt;
+    const double eps = c.P->neps ? vec[c.P->nz] : 0.0;
+    double base;
+    if (r < rt.nS) {
+        const int i2 = rt.s_i2[r];
+        base = vec[rt.s_i1[r]] - (i2 >= 0 ? vec[i2] : 0.0);
+    } else if (r < rt.nS + rt.nDr) {
+        base = ybase[rt.dr_base[r - rt.nS]];
+    } else {
+        base = 0.0;
+    }
+    return rt.row_sig[r] * base - rt.row_c[r] * eps;
+}
+
+// out[0..n) (+)= G' w  : out_v[j] = sum_r sig_r w_r p_r[j],  out_eps = -sum_r c_r w_r
+// scale: result = base[j] + alpha * (G'w)[j];  base may be nullptr (treated as 0)
+template <int TEAM>
+__device__ __forceinline__ void gt_apply(const Team<TEAM>& T, const Ctx& c, const double* w, double alpha,
+                                         const double* base, double* out) {
+    const RowTables& rt = c.P->rt;
+    const int nDb = rt.nDb, nz = c.P->nz;
+    for (int k = T.tid; k < nDb; k += TEAM) {
+        const int a = rt.db_rmax[k], b = rt.db_rmin[k];
+        c.wd[k] = (a >= 0 ? w[a] : 0.0) - (b >= 0 ? w[b] : 0.0);
+    }
+    double ce = 0.0;
+    if (c.P->neps)
+        for (int r = T.tid; r < rt.m; r += TEAM) ce = fma(rt.row_c[r], w[r], ce);
+    T.sync();
+    for (int j = T.tid; j < nz; j += TEAM) {
+        double a0 = 0.0, a1 = 0.0;
+        const double* col = c.Pd + (long)nDb * j;
+        int k = (nDb > 0) ? (j % nDb) : 0;  // skewed start: conflict-free shared-memory columns
+        int cnt = 0;
+        for (; cnt + 1 < nDb; cnt += 2) {
+            a0 = fma(col[k], c.wd[k], a0);
+            k = (k + 1 == nDb) ? 0 : k + 1;
+            a1 = fma(col[k], c.wd[k], a1);
+            k = (k + 1 == nDb) ? 0 : k + 1;
+        }
+        if (cnt < nDb) a0 = fma(col[k], c.wd[k], a0);
+        double acc = a0 + a1;
+        for (int e = rt.var_ptr[j]; e < rt.var_ptr[j + 1]; ++e) {
+            const int r = rt.var_row[e];
+            acc = fma((double)rt.var_sgn[e] * rt.row_sig[r], w[r], acc);
+        }
+        out[j] = (base ? base[j] : 0.0) + alpha * acc;
+    }
+    if (c.P->neps) {
+        ce = T.sum(ce);
+        if (T.tid == 0) out[nz] = (base ? base[nz] : 0.0) - alpha * ce;
+    }
+    T.sync();
+}
+
+// hx[i] = sum_j Hv(i,j) v[j] (+ Hee*eps on the slack row)
+template <int TEAM>
+__device__ __forceinline__ void hess_apply(const Team<TEAM>& T, const Ctx& c, double Hee, const double* v,
+                                           double* hx) {
+    const int nz = c.P->nz;
+    for (int i = T.tid; i < nz; i += TEAM) {
+        double a = 0.0;
+        const double* ri = c.Hv + pidx(i, 0);
+        for (int j = 0; j <= i; ++j) a = fma(ri[j], v[j], a);
+        for (int j = i + 1; j < nz; ++j) a = fma(c.Hv[pidx(j, i)], v[j], a);
+        hx[i] = a;
+    }
+    if (c.P->neps && T.tid == 0) hx[nz] = Hee * v[nz];
+}
+
+// Phi = H + G' diag(d) G   (packed lower, n = nz + neps), d in c.t
+template <int TEAM>
+__device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, double Hee, const double* d) {
+    const RowTables& rt = c.P->rt;
+    const int nDb = rt.nDb, nz = c.P->nz, neps = c.P->neps;
+    // dense weights: wd[k] = d_max + d_min ; ybd[k] = sig*c*d summed (for the slack border)
+    for (int k = T.tid; k < nDb; k += TEAM) {
+        const int a = rt.db_rmax[k], b = rt.db_rmin[k];
+        double w = 0.0, g = 0.0;
+        if (a >= 0) {
+            w += d[a];
+            g += d[a] * rt.row_c[a];
+        }
+        if (b >= 0) {
+            w += d[b];
+            g -= d[b] * rt.row_c[b];
+        }
+        c.wd[k] = w;
+        c.ybd[k] = g;
+    }
+    T.sync();
+    const int npair = nz * (nz + 1) / 2;
+    for (int p = T.tid; p < npair; p += TEAM) {
+        const int i = rt.pair_i[p], j = rt.pair_j[p];
+        const double* ci = c.Pd + (long)nDb * i;
+        const double* cj = c.Pd + (long)nDb * j;
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < nDb; k += 2) {
+            a0 = fma(ci[k] * c.wd[k], cj[k], a0);
+            a1 = fma(ci[k + 1] * c.wd[k + 1], cj[k + 1], a1);
+        }
+        if (k < nDb) a0 = fma(ci[k] * c.wd[k], cj[k], a0);
+        c.Phi[p] = c.Hv[p] + a0 + a1;
+    }
+    T.sync();
+    // 1-/2-variable rows: gather per variable (each packed entry has exactly one writer)
+    for (int j = T.tid; j < nz; j += TEAM) {
+        double dg = 0.0, be = 0.0;
+        for (int e = rt.var_ptr[j]; e < rt.var_ptr[j + 1]; ++e) {
+            const int r = rt.var_row[e];
+            const double dr = d[r];
+            dg += dr;
+            const double sg = (double)rt.var_sgn[e];
+            be = fma(sg * rt.row_sig[r] * rt.row_c[r], dr, be);
+            if (rt.var_sgn[e] > 0) {
+                const int i2 = rt.s_i2[r];
+                if (i2 >= 0) c.Phi[pidx(j, i2)] -= dr;  // j = i1 > i2
+            }
+        }
+        c.Phi[pidx(j, j)] += dg;
+        if (neps) {
+            // border: Phi[eps, j] = -sum_r d_r sig_r c_r p_r[j]
+            double a = 0.0;
+            const double* col = c.Pd + (long)nDb * j;
+            for (int k = 0; k < nDb; ++k) a = fma(col[k], c.ybd[k], a);
+            c.Phi[pidx(nz, j)] = -(a + be);
+        }
+    }
+    if (neps) {
+        double cc = 0.0;
+        for (int r = T.tid; r < rt.m; r += TEAM) cc = fma(rt.row_c[r] * rt.row_c[r], d[r], cc);
+        cc = T.sum(cc);
+        if (T.tid == 0) c.Phi[pidx(nz, nz)] = Hee + cc;
+    }
+    T.sync();
+}
+
+// max step in [0,1] keeping s + a ds > 0 and lam + a dl > 0
+template <int TEAM>
+__device__ __forceinline__ double max_step(const Team<TEAM>& T, const Ctx& c, int m) {
+    double a = 1.0;
+    for (int r = T.tid; r < m; r += TEAM) {
+        const double ds = c.ds[r], dl = c.dl[r];
+        if (ds < 0.0) a = fmin(a, -c.s[r] / ds);
+        if (dl < 0.0) a = fmin(a, -c.lam[r] / dl);
+    }
+    return T.min(a);
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
+    step_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) double smem[];
+    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    constexpr int TEAMS = CTA / TEAM;
+    const int team_id = threadIdx.x / TEAM;
+    Team<TEAM> T;
+    T.tid = threadIdx.x % TEAM;
+    if constexpr (TEAM < 32) {
+        const int lane = threadIdx.x & 31;
+        T.mask = ((1u << TEAM) - 1u) << (lane & ~(TEAM - 1));
+    } else {
+        T.mask = 0xffffffffu;
+    }
+    double* base = smem + (long)team_id * P.sm.total;
+    T.red = base + P.sm.red;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + P.sm.bar);
+    volatile int* slot = reinterpret_cast<volatile int*>(base + P.sm.bar + 1);
+
+    Ctx c;
+    c.P = &P;
+    c.x = base + P.sm.x;
+    c.q = base + P.sm.q;
+    c.rd = base + P.sm.rd;
+    c.rhs = base + P.sm.rhs;
+    c.dx = base + P.sm.dx;
+    c.invd = base + P.sm.invd;
+    c.F = base + P.sm.F;
+    c.tY = base + P.sm.tY;
+    c.fx = base + P.sm.fx;
+    c.yb = base + P.sm.yb;
+    c.ybd = base + P.sm.ybd;
+    c.wd = base + P.sm.wd;
+    c.s = base + P.sm.s;
+    c.lam = base + P.sm.lam;
+    c.h = base + P.sm.h;
+    c.rp = base + P.sm.rp;
+    c.t = base + P.sm.t;
+    c.ds = base + P.sm.ds;
+    c.dl = base + P.sm.dl;
+    c.Hv = base + P.sm.Hv;
+    c.Phi = base + P.sm.Phi;
+    double* sm_xhat = base + P.sm.xhat;
+    double* sm_lastu = base + P.sm.lastu;
+    double* sm_d0 = base + P.sm.dd;
+    double* sm_Dh = base + P.sm.Dh;
+    double* sm_Pd = base + P.sm.Pd;
+
+    const RowTables& rt = P.rt;
+    const int nz = P.nz, n = P.n, neps = P.neps, nY = P.nY, nu = P.nu, ny = P.ny, nx = P.nx, nd = P.nd;
+    const int m = rt.m, nS = rt.nS, nDr = rt.nDr, nDb = rt.nDb;
+
+    if (T.tid == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    T.sync();
+    uint32_t phase = 0;
+
+    for (;;) {
+        // ---- fetch the next instance (dynamic scheduling: iteration counts differ) ----
+        if (T.tid == 0) *slot = (int)atomicAdd(&P.counters[0], 1u);
+        T.sync();
+        const int inst = *slot;
+        T.sync();
+        if (inst >= P.N) break;
+
+        // ---- stage 0: TMA bulk loads ----
+        const double* gHv = P.Hv + (long)inst * P.sH;
+        const double* gLv = P.Lv + (long)inst * P.sH;
+        const double* gPd = P.Pd + (long)inst * P.sPd;
+        const int lv_ok = P.lv_ok[P.sH ? inst : 0];
+        if (T.tid == 0) {
+            fence_proxy_async();
+            uint32_t bytes = (uint32_t)P.nHp2 * 8u * 2u;
+            if (P.pd_in_smem) bytes += (uint32_t)P.nPd2 * 8u;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_bulk_g2s(c.Hv, gHv, (uint32_t)P.nHp2 * 8u, bar);
+            tma_bulk_g2s(c.Phi, gLv, (uint32_t)P.nHp2 * 8u, bar);
+            if (P.pd_in_smem) tma_bulk_g2s(sm_Pd, gPd, (uint32_t)P.nPd2 * 8u, bar);
+        }
+        c.Pd = P.pd_in_smem ? sm_Pd : gPd;
+
+        // ---- stage 1: initpred! ----
+        for (int k = T.tid; k < nx; k += TEAM) sm_xhat[k] = P.xhat0[(long)inst * nx + k];
+        for (int k = T.tid; k < nu; k += TEAM) sm_lastu[k] = P.lastu0[(long)inst * nu + k];
+        if (nd > 0) {
+            for (int k = T.tid; k < nd; k += TEAM) sm_d0[k] = P.d0[(long)inst * nd + k];
+            for (int k = T.tid; k < nd * P.Hp; k += TEAM)
+                sm_Dh[k] = P.Dhat0 ? P.Dhat0[(long)inst * nd * P.Hp + k] : P.d0[(long)inst * nd + (k % nd)];
+        }
+        T.sync();
+        const double* gK = P.K + (long)inst * P.sK;
+        const double* gV = P.V + (long)inst * P.sV;
+        const double* gB = P.B + (long)inst * P.sB;
+        const double* gyop = P.yop + (long)inst * P.syop;
+        const double* gM = P.Mw + (long)inst * P.sM;
+        double racc = 0.0;
+        for (int t = T.tid; t < nY; t += TEAM) {
+            double f = gB[t];
+            for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sm_xhat[k], f);
+            for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], sm_lastu[k], f);
+            if (nd > 0) {
+                const double* gG = P.G + (long)inst * P.sG;
+                const double* gJ = P.J + (long)inst * P.sJ;
+                for (int k = 0; k < nd; ++k) f = fma(gG[t + (long)nY * k], sm_d0[k], f);
+                for (int k = 0; k < nd * P.Hp; ++k) f = fma(gJ[t + (long)nY * k], sm_Dh[k], f);
+            }
+            c.F[t] = f;
+            const double ryt = P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)];
+            const double cy = f + gyop[t % ny] - ryt;
+            if (P.M_dense) {
+                c.tY[t] = cy;  // tY = M*Cy is formed below
+            } else {
+                const double ty = gM[t] * cy;
+                c.tY[t] = ty;
+                racc = fma(cy, ty, racc);
+            }
+            P.F_out[(long)inst * nY + t] = f;
+        }
+        if (P.M_dense) {
+            // tY = M * Cy (dense, symmetric, lower triangle authoritative)
+            T.sync();
+            double* cyv = c.dl;  // scratch: the layout reserves max(m, nY) doubles for dl
+            for (int t = T.tid; t < nY; t += TEAM) cyv[t] = c.tY[t];
+            T.sync();
+            for (int t = T.tid; t < nY; t += TEAM) {
+                double a = 0.0;
+                for (int k = 0; k < nY; ++k) {
+                    const double mk = (t >= k) ? gM[t + (long)nY * k] : gM[k + (long)nY * t];
+                    a = fma(mk, cyv[k], a);
+                }
+                c.tY[t] = a;
+                racc = fma(cyv[t], a, racc);
+            }
+        }
+        if (P.has_terminal) {
+            const double* gkx = P.kx + (long)inst * P.skx;
+            const double* gvx = P.vx + (long)inst * P.svx;
+            const double* gbx = P.bx + (long)inst * P.sbx;
+            for (int i = T.tid; i < nx; i += TEAM) {
+                double f = gbx[i];
+                for (int k = 0; k < nx; ++k) f = fma(gkx[i + (long)nx * k], sm_xhat[k], f);
+                for (int k = 0; k < nu; ++k) f = fma(gvx[i + (long)nx * k], sm_lastu[k], f);
+                if (nd > 0) {
+                    const double* ggx = P.gx + (long)inst * P.sgx;
+                    const double* gjx = P.jx + (long)inst * P.sjx;
+                    for (int k = 0; k < nd; ++k) f = fma(ggx[i + (long)nx * k], sm_d0[k], f);
+                    for (int k = 0; k < nd * P.Hp; ++k) f = fma(gjx[i + (long)nx * k], sm_Dh[k], f);
+                }
+                c.fx[i] = f;
+            }
+        }
+        T.sync();
+        // q_v = 2 Ev' tY (+ 2 sum_{t in block} L_t Cu_t);   Ev is Pd when pd_is_ev
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        const double* gEv = P.Ev + (long)inst * P.sEv;
+        const double* gL = P.has_L ? P.Lw + (long)inst * P.sL : nullptr;
+        const double* guop = P.uop + (long)inst * P.suop;
+        for (int j = T.tid; j < nz; j += TEAM) {
+            const double* col = (P.pd_is_ev && P.pd_in_smem) ? (sm_Pd + (long)nY * j) : (gEv + (long)nY * j);
+            double a0 = 0.0, a1 = 0.0;
+            int k = j % nY, cnt = 0;
+            for (; cnt + 1 < nY; cnt += 2) {
+                a0 = fma(col[k], c.tY[k], a0);
+                k = (k + 1 == nY) ? 0 : k + 1;
+                a1 = fma(col[k], c.tY[k], a1);
+                k = (k + 1 == nY) ? 0 : k + 1;
+            }
+            if (cnt < nY) a0 = fma(col[k], c.tY[k], a0);
+            double a = a0 + a1;
+            if (gL) {
+                const int l = j / nu, ch = j % nu;
+                for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) {
+                    const int idx = tt * nu + ch;
+                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
+                    const double cu = sm_lastu[ch] + guop[ch] - ru;
+                    a = fma(gL[idx], cu, a);
+                }
+            }
+            c.q[j] = 2.0 * a;
+        }
+        if (gL) {
+            for (int idx = T.tid; idx < P.nU; idx += TEAM) {
+                const int ch = idx % nu;
+                const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
+                const double cu = sm_lastu[ch] + guop[ch] - ru;
+                racc = fma(gL[idx] * cu, cu, racc);
+            }
+        }
+        if (neps && T.tid == 0) c.q[nz] = 0.0;
+        const double rconst = T.sum(racc);
+        // ---- linconstraint!: row right-hand sides ----
+        const double* gsb = P.sbase + (long)inst * nS;
+        const double* gdb = P.dbound + (long)inst * nDr;
+        double hmax = 0.0;
+        for (int r = T.tid; r < m; r += TEAM) {
+            double hv;
+            if (r < nS) {
+                const int ch = rt.s_ch[r];
+                hv = gsb[r] - (ch >= 0 ? rt.row_sig[r] * sm_lastu[ch] : 0.0);
+            } else if (r < nS + nDr) {
+                const int src = rt.dr_src[r - nS];
+                const double fsrc = src < nY ? c.F[src] : c.fx[src - nY];
+                hv = rt.row_sig[r] * (gdb[r - nS] - fsrc);
+            } else {
+                hv = 0.0;
+            }
+            c.h[r] = hv;
+            hmax = fmax(hmax, fabs(hv));
+        }
+        const double hscale = 1.0 + T.max(hmax);
+        double qmax = 0.0;
+        T.sync();
+        for (int j = T.tid; j < n; j += TEAM) qmax = fmax(qmax, fabs(c.q[j]));
+        const double qs = 1.0 + T.max(qmax);
+        const double Hee = neps ? P.Hee[P.sH ? inst : 0] : 0.0;
+
+        // ---- stage 2: unconstrained minimiser with the cached factor (Lv sits in Phi) ----
+        for (int j = T.tid; j < n; j += TEAM) c.x[j] = (j < nz && lv_ok) ? -c.q[j] : 0.0;
+        if (lv_ok) {
+            for (int j = T.tid; j < nz; j += TEAM) c.invd[j] = 1.0 / c.Phi[pidx(j, j)];
+            T.sync();
+            chol_solve(T, c.Phi, c.invd, c.x, nz);
+        }
+        T.sync();
+        dense_apply(T, c, c.x, c.yb);
+        T.sync();
+        double smin = 1e300;
+        for (int r = T.tid; r < m; r += TEAM) {
+            const double sl = c.h[r] - row_gx(c, r, c.x, c.yb);
+            c.s[r] = sl;
+            smin = fmin(smin, sl);
+        }
+        smin = (m > 0) ? T.min(smin) : 0.0;
+        int status = ST_OPTIMAL;
+        int iters = 0;
+        const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
+        if (!feasible) {
+            // ---- stage 3: Mehrotra predictor-corrector ----
+            const double mu0 = fmax(1e-2 * qs * hscale / (double)m, 1e-8);
+            for (int r = T.tid; r < m; r += TEAM) {
+                const double sv = fmax(c.s[r], 1e-2 * hscale);
+                c.s[r] = sv;
+                c.lam[r] = mu0 / sv;
+            }
+            T.sync();
+            status = ST_ITERATION_LIMIT;
+            double rp_inf = 0.0, best_merit = 1e300;
+            for (int it = 0; it <= P.max_iter; ++it) {
+                // residuals
+                hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
+                T.sync();
+                for (int j = T.tid; j < n; j += TEAM) c.rhs[j] += c.q[j];
+                T.sync();
+                gt_apply(T, c, c.lam, 1.0, c.rhs, c.rd);  // rd = Hx + q + G' lam
+                double e_d = 0.0, e_p = 0.0, musum = 0.0;
+                for (int j = T.tid; j < n; j += TEAM) e_d = fmax(e_d, fabs(c.rd[j]));
+                for (int r = T.tid; r < m; r += TEAM) {
+                    const double rpv = row_gx(c, r, c.x, c.yb) + c.s[r] - c.h[r];
+                    c.rp[r] = rpv;
+                    e_p = fmax(e_p, fabs(rpv));
+                    musum = fma(c.s[r], c.lam[r], musum);
+                }
+                e_d = T.max(e_d);
+                e_p = T.max(e_p);
+                const double mu = T.sum(musum) / (double)m;
+                rp_inf = e_p;
+                if (!(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250) {
+                    status = ST_INFEASIBLE;
+                    break;
+                }
+                // merit = worst of the three scaled KKT residuals (1.0 = exactly at tolerance)
+                const double merit = fmax(fmax(e_d / (P.tol * qs), e_p / (P.tol * hscale)),
+                                          mu * (double)m / (P.tol_mu * qs * hscale));
+                if (merit <= 1.0) {
+                    status = ST_OPTIMAL;
+                    break;
+                }
+                // fp64 floor: once inside the acceptable level (1e3 x tol, still far below the reference
+                // solver's eps = 1e-3) the first iteration that no longer improves the merit ends the solve:
+                // the normal equations lose accuracy as lam/s spreads over > 1e24 and the dual residual
+                // starts to grow again.
+                if (best_merit <= 1e3 && merit >= best_merit) {
+                    status = ST_OPTIMAL;
+                    break;
+                }
+                best_merit = fmin(best_merit, merit);
+                if (it == P.max_iter) {
+                    if (merit <= 1e3) status = ST_OPTIMAL;
+                    break;
+                }
+                iters = it + 1;
+                // Phi = H + G' D G, factor
+                for (int r = T.tid; r < m; r += TEAM) c.t[r] = c.lam[r] / c.s[r];
+                T.sync();
+                build_phi(T, c, Hee, c.t);
+                chol_packed(T, c.Phi, c.invd, n);
+                // predictor: rhs = -rd - G'(d*rp - lam)
+                for (int r = T.tid; r < m; r += TEAM) c.dl[r] = c.t[r] * c.rp[r] - c.lam[r];
+                T.sync();
+                gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
+                for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+                chol_solve(T, c.Phi, c.invd, c.dx, n);
+                dense_apply(T, c, c.dx, c.ybd);
+                T.sync();
+                for (int r = T.tid; r < m; r += TEAM) {
+                    const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
+                    c.ds[r] = dsv;
+                    c.dl[r] = -c.lam[r] - c.t[r] * dsv;
+                }
+                T.sync();
+                const double a_aff = max_step(T, c, m);
+                double mua = 0.0;
+                for (int r = T.tid; r < m; r += TEAM)
+                    mua = fma(c.s[r] + a_aff * c.ds[r], c.lam[r] + a_aff * c.dl[r], mua);
+                mua = T.sum(mua) / (double)m;
+                double sig = mua / mu;
+                sig = sig * sig * sig;
+                // corrector: rc = s*lam + ds*dl - sig*mu ; rhs = -rd - G'((lam*rp - rc)/s)
+                for (int r = T.tid; r < m; r += TEAM) {
+                    const double rc = c.s[r] * c.lam[r] + c.ds[r] * c.dl[r] - sig * mu;
+                    c.ds[r] = rc;  // keep rc
+                    c.dl[r] = (c.lam[r] * c.rp[r] - rc) / c.s[r];
+                }
+                T.sync();
+                gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
+                for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+                chol_solve(T, c.Phi, c.invd, c.dx, n);
+                dense_apply(T, c, c.dx, c.ybd);
+                T.sync();
+                for (int r = T.tid; r < m; r += TEAM) {
+                    const double rc = c.ds[r];
+                    const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
+                    c.ds[r] = dsv;
+                    c.dl[r] = -(rc + c.lam[r] * dsv) / c.s[r];
+                }
+                T.sync();
+                const double a = fmin(1.0, 0.99 * max_step(T, c, m));
+                for (int j = T.tid; j < n; j += TEAM) c.x[j] = fma(a, c.dx[j], c.x[j]);
+                for (int k = T.tid; k < nDb; k += TEAM) c.yb[k] = fma(a, c.ybd[k], c.yb[k]);
+                for (int r = T.tid; r < m; r += TEAM) {
+                    c.s[r] = fma(a, c.ds[r], c.s[r]);
+                    c.lam[r] = fma(a, c.dl[r], c.lam[r]);
+                }
+                T.sync();
+            }
+            if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+        }
+        // ---- stage 4: getinput! ----
+        double* gZ = P.Z + (long)inst * n;
+        T.sync();
+        if (status == ST_INFEASIBLE) {
+            // shifted previous solution Z̃s (set_warmstart_mpc!, transcription.jl:997-1007), in level coordinates
+            for (int j = T.tid; j < nz; j += TEAM) c.dx[j] = (j + nu < nz) ? gZ[j + nu] : 0.0;
+            if (neps && T.tid == 0) c.x[nz] = gZ[nz];
+            T.sync();
+            for (int j = T.tid; j < nz; j += TEAM) {
+                double a = 0.0;
+                for (int l = j % nu; l <= j; l += nu) a += c.dx[l];
+                c.x[j] = a;
+            }
+            T.sync();
+        }
+        // J = 1/2 x'Hx + q'x + r
+        hess_apply(T, c, Hee, c.x, c.rhs);
+        T.sync();
+        double jacc = 0.0;
+        for (int j = T.tid; j < n; j += TEAM) jacc += c.x[j] * (0.5 * c.rhs[j] + c.q[j]);
+        jacc = T.sum(jacc) + rconst;
+        for (int j = T.tid; j < nz; j += TEAM) gZ[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
+        if (neps && T.tid == 0) gZ[nz] = c.x[nz];
+        // q̃ in reference coordinates: q̃[j] = sum_{l' >= l(j)} q_v[l' nu + ch]
+        for (int j = T.tid; j < nz; j += TEAM) {
+            double a = 0.0;
+            for (int l = j; l < nz; l += nu) a += c.q[l];
+            P.qt_out[(long)inst * n + j] = a;
+        }
+        for (int k = T.tid; k < nu; k += TEAM) {
+            const double du = c.x[k];  // DU_0 = v_0
+            const double lu = sm_lastu[k];
+            P.lastu_prev[(long)inst * nu + k] = lu;
+            P.lastu0[(long)inst * nu + k] = lu + du;
+            P.u[(long)inst * nu + k] = lu + du + guop[k];
+        }
+        if (T.tid == 0) {
+            if (neps) P.qt_out[(long)inst * n + nz] = 0.0;
+            P.r_out[inst] = rconst;
+            if (P.J_out) P.J_out[inst] = jacc;
+            P.status[inst] = status;
+            P.iters[inst] = iters;
+        }
+        fence_proxy_async();  // generic-proxy writes to Hv/Phi/Pd slices precede the next TMA overwrite
+        T.sync();
+    }
+    // ---- reset the work counters for the next launch (last CTA out) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&P.counters[1], 1u);
+        if (done == gridDim.x - 1) {
+            P.counters[0] = 0u;
+            P.counters[1] = 0u;
+            __threadfence();
+        }
+    }
+    (void)TEAMS;
+}
+
+}  // namespace bmpc

@@ -1,0 +1,129 @@
+// One-off / on-demand kernels around the step: change of coordinates of the host-supplied
+// prediction matrices (route B of bmpc.h), cached Cholesky of the Hessian, gather of the
+// dense constraint rows, and the getinfo predictions.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bmpc {
+
+// out[:, j] = in[:, j] - in[:, j+nu]   (X_v = X * D,  DU_l = v_l - v_{l-1});  column-major [rows x nz]
+// in has per-instance stride rows*nz, out has stride ostride (even, TMA alignment).
+__global__ void k_level_cols(const double* __restrict__ in, double* __restrict__ out, int rows, int nz, int nu,
+                             long ostride, long tot) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tot) return;
+    const long per = (long)rows * nz;
+    const long inst = e / per;
+    const int rem = (int)(e - inst * per);
+    const int j = rem / rows;
+    const double nxt = (j + nu < nz) ? in[e + (long)rows * nu] : 0.0;
+    out[inst * ostride + rem] = in[e] - nxt;
+}
+
+// Hv = D' H̃[0:nz,0:nz] D, packed row-major lower (p = i(i+1)/2 + j); Hee = H̃[n-1,n-1] when neps.
+// H̃ is column-major n x n with the LOWER triangle authoritative (Hermitian(:L), construct.jl:842).
+__global__ void k_level_hess(const double* __restrict__ Ht, double* __restrict__ Hv, double* __restrict__ Hee, int n,
+                             int nz, int nu, int neps, int nHp2, int npair, long tot) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tot) return;
+    const long inst = e / npair;
+    const int p = (int)(e - inst * npair);
+    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    while (i * (i + 1) / 2 > p) --i;
+    const int j = p - i * (i + 1) / 2;
+    const double* H = Ht + inst * (long)n * n;
+    auto hs = [&](int a, int b) -> double {
+        if (a >= nz || b >= nz) return 0.0;
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        return H[hi + (long)n * lo];
+    };
+    Hv[inst * nHp2 + p] = hs(i, j) - hs(i + nu, j) - hs(i, j + nu) + hs(i + nu, j + nu);
+    if (p == 0) Hee[inst] = neps ? H[(long)(n - 1) + (long)n * (n - 1)] : 0.0;
+}
+
+// Lv = chol(Hv), one thread per instance (one-off); ok = 0 if Hv is not safely positive definite.
+__global__ void k_chol_serial(const double* __restrict__ Hv, double* __restrict__ Lv, int* __restrict__ ok, int nz,
+                              int nHp2, int NM) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= NM) return;
+    const double* A = Hv + (long)inst * nHp2;
+    double* L = Lv + (long)inst * nHp2;
+    double dmax = 0.0;
+    for (int i = 0; i < nz; ++i) dmax = fmax(dmax, fabs(A[i * (i + 1) / 2 + i]));
+    int good = 1;
+    for (int i = 0; i < nz; ++i) {
+        double* ri = L + i * (i + 1) / 2;
+        const double* ai = A + i * (i + 1) / 2;
+        for (int j = 0; j <= i; ++j) {
+            const double* rj = L + j * (j + 1) / 2;
+            double a = ai[j];
+            for (int p = 0; p < j; ++p) a = fma(-ri[p], rj[p], a);
+            if (j == i) {
+                if (!(a > 1e-13 * dmax)) {
+                    good = 0;
+                    a = 1.0;
+                }
+                ri[j] = sqrt(a);
+            } else {
+                ri[j] = a / rj[j];
+            }
+        }
+    }
+    ok[inst] = good;
+}
+
+// Pd[k, j] = (src_k < nY ? Ev[src_k, j] : exv[src_k - nY, j])
+__global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restrict__ exv, double* __restrict__ Pd,
+                            const int* __restrict__ pd_src, int nY, int nx, int nz, int nDb, long sEv, int nPd2,
+                            long tot) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tot) return;
+    const long per = (long)nDb * nz;
+    const long inst = e / per;
+    const int rem = (int)(e - inst * per);
+    const int j = rem / nDb, k = rem - j * nDb;
+    const int src = pd_src[k];
+    const double v = src < nY ? Ev[inst * sEv + src + (long)nY * j] : exv[inst * (long)nx * nz + (src - nY) + (long)nx * j];
+    Pd[inst * nPd2 + rem] = v;
+}
+
+// getinfo predictions in reference coordinates (predict!, transcription.jl:1136-1145; getU0!, :1115).
+// One CTA per instance.  Measured-disturbance terms of fx̂ are not included (nd = 0 scope).
+__global__ void k_getinfo(const double* __restrict__ E, long sE, const double* __restrict__ ex, long sex,
+                          const double* __restrict__ kx, long skx, const double* __restrict__ vx, long svx,
+                          const double* __restrict__ bx, long sbx, const double* __restrict__ Z,
+                          const double* __restrict__ F, const double* __restrict__ xhat0,
+                          const double* __restrict__ lastu_prev, const int* __restrict__ blk_of_t,
+                          double* __restrict__ Yhat0, double* __restrict__ U0, double* __restrict__ xend, int nY, int nz,
+                          int n, int nu, int nx, int Hp) {
+    const int inst = blockIdx.x;
+    const double* z = Z + (long)inst * n;
+    const double* e = E + inst * sE;
+    for (int t = threadIdx.x; t < nY; t += blockDim.x) {
+        double a = F[(long)inst * nY + t];
+        for (int j = 0; j < nz; ++j) a = fma(e[t + (long)nY * j], z[j], a);
+        Yhat0[(long)inst * nY + t] = a;
+    }
+    for (int k = threadIdx.x; k < nu * Hp; k += blockDim.x) {
+        const int t = k / nu, ch = k % nu;
+        double a = lastu_prev[(long)inst * nu + ch];
+        for (int l = 0; l <= blk_of_t[t]; ++l) a += z[l * nu + ch];
+        U0[(long)inst * nu * Hp + k] = a;
+    }
+    if (ex) {
+        const double* exi = ex + inst * sex;
+        const double* kxi = kx + inst * skx;
+        const double* vxi = vx + inst * svx;
+        const double* bxi = bx + inst * sbx;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+            double a = bxi[i];
+            for (int k = 0; k < nx; ++k) a = fma(kxi[i + (long)nx * k], xhat0[(long)inst * nx + k], a);
+            for (int k = 0; k < nu; ++k) a = fma(vxi[i + (long)nx * k], lastu_prev[(long)inst * nu + k], a);
+            for (int j = 0; j < nz; ++j) a = fma(exi[i + (long)nx * j], z[j], a);
+            xend[(long)inst * nx + i] = a;
+        }
+    }
+}
+
+}  // namespace bmpc
