@@ -6,7 +6,10 @@ this package is only the host-side mirror of the reference interface for that pa
 from . import _lib
 from ._lib import (BmpcError, STATUS_INFEASIBLE, STATUS_ITERATION_LIMIT, STATUS_OPTIMAL)
 from .batch import BatchLinMPC
-from .host import move_blocking
+from .host import LinModel, ManualEstimator, SteadyKalmanFilter, move_blocking
+from .linmpc import LinMPC, sim
+from . import workloads
 
-__all__ = ["BatchLinMPC", "BmpcError", "move_blocking", "STATUS_OPTIMAL", "STATUS_ITERATION_LIMIT",
+__all__ = ["BatchLinMPC", "LinMPC", "LinModel", "SteadyKalmanFilter", "ManualEstimator", "sim", "workloads",
+           "BmpcError", "move_blocking", "STATUS_OPTIMAL", "STATUS_ITERATION_LIMIT",
            "STATUS_INFEASIBLE"]

@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -21,6 +22,7 @@
 
 #include "bmpc_device.cuh"
 #include "bmpc_setup.cuh"
+#include "bmpc_model.cuh"
 
 namespace {
 
@@ -112,6 +114,7 @@ namespace {
 
 int choose_team(const bmpc_handle* h) {
     if (h->d.team) return h->d.team;
+    if (const char* e = getenv("BMPC_TEAM")) return atoi(e);  // tuning override
     const int n = h->n;
     if (n <= 16) return 16;
     if (n <= 48) return 32;
@@ -390,6 +393,9 @@ int bmpc_set_predmat(bmpc_handle* h, const double* E, const double* K, const dou
         }
     }
     CK(cudaStreamSynchronize(s));
+    h->E.release();  // only the level-coordinate copies are kept
+    h->ex.release();
+    h->Ht.release();
     return BMPC_OK;
 }
 
@@ -755,7 +761,6 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
 int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
     if (!h || !info) return fail(BMPC_ERR_ARG, "null argument");
     if (!h->stepped) return fail(BMPC_ERR_STATE, "bmpc_getinfo needs a previous bmpc_step");
-    if (!h->E.p) return fail(BMPC_ERR_UNSUPPORTED, "bmpc_getinfo needs the reference-coordinate matrices (bmpc_set_predmat)");
     const bmpc_dims& d = h->d;
     CK(cudaSetDevice(d.device));
     cudaStream_t s = h->stream;
@@ -765,11 +770,10 @@ int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
     CK(U.alloc(N * nU));
     CK(X.alloc(N * nx));
     const long sh = d.shared_model ? 0 : 1;
-    bmpc::k_getinfo<<<(unsigned)N, 128, 0, s>>>(h->E.p, sh * (long)(nY * h->nz), h->has_terminal_mats ? h->ex.p : nullptr,
-                                              sh * (long)(nx * h->nz), h->kx.p, sh * (long)(nx * nx), h->vx.p,
-                                              sh * (long)(nx * d.nu), h->bx.p, sh * (long)nx, h->last_Z, h->F.p, h->last_xhat0,
-                                              h->lastu_prev.p, h->t_blk.p, Y.p, U.p, X.p, (int)nY, h->nz, (int)n, d.nu,
-                                              (int)nx, d.Hp);
+    bmpc::k_getinfo<<<(unsigned)N, 128, h->nz * sizeof(double), s>>>(
+        h->Ev.p, sh * (long)h->nEv2, h->has_terminal_mats ? h->exv.p : nullptr, sh * (long)(nx * h->nz), h->kx.p,
+        sh * (long)(nx * nx), h->vx.p, sh * (long)(nx * d.nu), h->bx.p, sh * (long)nx, h->last_Z, h->F.p, h->last_xhat0,
+        h->lastu_prev.p, h->t_blk.p, Y.p, U.p, X.p, (int)nY, h->nz, (int)n, d.nu, (int)nx, d.Hp);
     h->launches++;
     CK(cudaGetLastError());
     if (info->Yhat0) CK(cudaMemcpyAsync(info->Yhat0, Y.p, N * nY * 8, cudaMemcpyDeviceToHost, s));
@@ -800,10 +804,94 @@ int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
 
 int64_t bmpc_launch_count(bmpc_handle* h) { return h ? h->launches : 0; }
 
-int bmpc_set_model(bmpc_handle* h, const double*, const double*, const double*, const double*, const double*,
-                   const double*, const double*, const double*, const double*, double) {
-    (void)h;
-    return fail(BMPC_ERR_UNSUPPORTED, "bmpc_set_model: on-device init_predmat is not built yet (use bmpc_set_predmat)");
+int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, const double* Chat, const double* Bdhat,
+                   const double* Ddhat, const double* fop_minus_xop, const double* M_diag, const double* N_diag,
+                   const double* L_diag, double Cwt) {
+    if (!h || !Ahat || !Buhat || !Chat || !M_diag || !N_diag) return fail(BMPC_ERR_ARG, "null argument");
+    const bmpc_dims& d = h->d;
+    if (d.nd > 0 && (!Bdhat || !Ddhat)) return fail(BMPC_ERR_ARG, "Bdhat and Ddhat are required when nd > 0");
+    if (d.neps && !(Cwt >= 0 && std::isfinite(Cwt))) return fail(BMPC_ERR_ARG, "Cwt must be finite and >= 0 when neps = 1");
+    CK(cudaSetDevice(d.device));
+    cudaStream_t s = h->stream;
+    const size_t NM = h->NM, nY = h->nY, nz = h->nz, nx = d.nxhat, nu = d.nu, ny = d.ny, nd = d.nd, Hp = d.Hp, nU = h->nU;
+    DevBuf<double> A, Bu, C, Bd, Dd, f, Nd;
+    std::vector<double> zeros;
+    CK(A.upload(Ahat, NM * nx * nx, s));
+    CK(Bu.upload(Buhat, NM * nx * nu, s));
+    CK(C.upload(Chat, NM * ny * nx, s));
+    if (nd) {
+        CK(Bd.upload(Bdhat, NM * nx * nd, s));
+        CK(Dd.upload(Ddhat, NM * ny * nd, s));
+    }
+    if (fop_minus_xop) {
+        CK(f.upload(fop_minus_xop, NM * nx, s));
+    } else {
+        zeros.assign(NM * nx, 0.0);
+        CK(f.upload(zeros, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(up(h->Mw, M_diag, NM * nY, s));
+    CK(Nd.upload(N_diag, NM * nz, s));
+    std::vector<double> Lz;
+    const double* Lsrc = L_diag;
+    h->has_L = false;
+    if (L_diag) {
+        for (size_t i = 0; i < NM * nU && !h->has_L; ++i) h->has_L = L_diag[i] != 0.0;
+    } else {
+        Lz.assign(NM * nU, 0.0);
+        Lsrc = Lz.data();
+    }
+    CK(up(h->Lw, Lsrc, NM * nU, s));
+    h->M_dense = false;
+    CK(h->K.alloc(NM * nY * nx));
+    CK(h->V.alloc(NM * nY * nu));
+    CK(h->B.alloc(NM * nY));
+    if (nd) {
+        CK(h->G.alloc(NM * nY * nd));
+        CK(h->J.alloc(NM * nY * nd * Hp));
+        CK(h->gx.alloc(NM * nx * nd));
+        CK(h->jx.alloc(NM * nx * nd * Hp));
+    }
+    CK(h->kx.alloc(NM * nx * nx));
+    CK(h->vx.alloc(NM * nx * nu));
+    CK(h->bx.alloc(NM * nx));
+    CK(h->Ev.alloc(NM * h->nEv2));
+    CK(h->exv.alloc(NM * nx * nz));
+    CK(h->Hv.alloc(NM * h->nHp2));
+    CK(h->Lv.alloc(NM * h->nHp2));
+    CK(h->Hee.alloc(NM));
+    CK(h->lv_ok.alloc(NM));
+    CK(cudaMemsetAsync(h->Ev.p, 0, NM * h->nEv2 * sizeof(double), s));
+    CK(cudaMemsetAsync(h->Hv.p, 0, NM * h->nHp2 * sizeof(double), s));
+    CK(cudaMemsetAsync(h->Lv.p, 0, NM * h->nHp2 * sizeof(double), s));
+    bmpc::ModelParams P{};
+    P.nu = d.nu; P.ny = d.ny; P.nd = d.nd; P.nx = d.nxhat; P.Hp = d.Hp; P.Hc = d.Hc; P.nz = h->nz; P.nY = h->nY;
+    P.nU = h->nU; P.neps = d.neps; P.nHp2 = h->nHp2; P.nEv2 = h->nEv2; P.Cwt = Cwt;
+    P.A = A.p; P.Bu = Bu.p; P.C = C.p; P.Bd = Bd.p; P.Dd = Dd.p; P.f = f.p; P.Mdiag = h->Mw.p; P.Ndiag = Nd.p;
+    P.Ldiag = h->Lw.p;
+    P.K = h->K.p; P.V = h->V.p; P.B = h->B.p; P.G = h->G.p; P.J = h->J.p; P.kx = h->kx.p; P.vx = h->vx.p;
+    P.bx = h->bx.p; P.gx = h->gx.p; P.jx = h->jx.p; P.Ev = h->Ev.p; P.exv = h->exv.p; P.Hv = h->Hv.p;
+    P.Hee = h->Hee.p; P.blk_start = h->t_blkstart.p;
+    const size_t smem = (3 * nx * nx + 3 * ny * nx + 3 * nx * nu + 5 * nx + 2 * nx * nd + 8) * sizeof(double);
+    if (smem > 200 * 1024) return fail(BMPC_ERR_UNSUPPORTED, "model too large for the on-device builder (use bmpc_set_predmat)");
+    CK(cudaFuncSetAttribute(bmpc::k_build_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bmpc::k_build_model<<<(unsigned)NM, 128, smem, s>>>(P);
+    bmpc::k_chol_serial<<<(unsigned)((NM + 63) / 64), 64, 0, s>>>(h->Hv.p, h->Lv.p, h->lv_ok.p, (int)nz, h->nHp2, (int)NM);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    h->has_terminal_mats = true;
+    h->have_predmat = true;
+    h->have_weights = true;
+    if (h->have_constraints && !h->pd_is_ev && h->rt.nDb > 0) {
+        const long tot = (long)NM * h->rt.nDb * nz;
+        bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->exv.p, h->Pd.p, h->t_pdsrc.p, (int)nY, (int)nx,
+                                                                      (int)nz, h->rt.nDb, (long)h->nEv2, h->nPd2, tot);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));
+    A.release(); Bu.release(); C.release(); Bd.release(); Dd.release(); f.release(); Nd.release();
+    return BMPC_OK;
 }
 
 }  // extern "C"

@@ -88,31 +88,37 @@ __global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restr
     Pd[inst * nPd2 + rem] = v;
 }
 
-// getinfo predictions in reference coordinates (predict!, transcription.jl:1136-1145; getU0!, :1115).
+// getinfo predictions (predict!, transcription.jl:1136-1145; getU0!, :1115) evaluated in level
+// coordinates: v = cumsum(ΔU) per input, Ŷ0 = Ev v + F, U0 = v[block(t)] + lastu0, x̂0end = exv v + fx̂.
 // One CTA per instance.  Measured-disturbance terms of fx̂ are not included (nd = 0 scope).
-__global__ void k_getinfo(const double* __restrict__ E, long sE, const double* __restrict__ ex, long sex,
+__global__ void k_getinfo(const double* __restrict__ Ev, long sE, const double* __restrict__ exv, long sex,
                           const double* __restrict__ kx, long skx, const double* __restrict__ vx, long svx,
                           const double* __restrict__ bx, long sbx, const double* __restrict__ Z,
                           const double* __restrict__ F, const double* __restrict__ xhat0,
                           const double* __restrict__ lastu_prev, const int* __restrict__ blk_of_t,
                           double* __restrict__ Yhat0, double* __restrict__ U0, double* __restrict__ xend, int nY, int nz,
                           int n, int nu, int nx, int Hp) {
+    extern __shared__ double v[];
     const int inst = blockIdx.x;
     const double* z = Z + (long)inst * n;
-    const double* e = E + inst * sE;
+    for (int j = threadIdx.x; j < nz; j += blockDim.x) {
+        double a = 0.0;
+        for (int l = j % nu; l <= j; l += nu) a += z[l];
+        v[j] = a;
+    }
+    __syncthreads();
+    const double* e = Ev + inst * sE;
     for (int t = threadIdx.x; t < nY; t += blockDim.x) {
         double a = F[(long)inst * nY + t];
-        for (int j = 0; j < nz; ++j) a = fma(e[t + (long)nY * j], z[j], a);
+        for (int j = 0; j < nz; ++j) a = fma(e[t + (long)nY * j], v[j], a);
         Yhat0[(long)inst * nY + t] = a;
     }
     for (int k = threadIdx.x; k < nu * Hp; k += blockDim.x) {
         const int t = k / nu, ch = k % nu;
-        double a = lastu_prev[(long)inst * nu + ch];
-        for (int l = 0; l <= blk_of_t[t]; ++l) a += z[l * nu + ch];
-        U0[(long)inst * nu * Hp + k] = a;
+        U0[(long)inst * nu * Hp + k] = lastu_prev[(long)inst * nu + ch] + v[blk_of_t[t] * nu + ch];
     }
-    if (ex) {
-        const double* exi = ex + inst * sex;
+    if (exv) {
+        const double* exi = exv + inst * sex;
         const double* kxi = kx + inst * skx;
         const double* vxi = vx + inst * svx;
         const double* bxi = bx + inst * sbx;
@@ -120,7 +126,7 @@ __global__ void k_getinfo(const double* __restrict__ E, long sE, const double* _
             double a = bxi[i];
             for (int k = 0; k < nx; ++k) a = fma(kxi[i + (long)nx * k], xhat0[(long)inst * nx + k], a);
             for (int k = 0; k < nu; ++k) a = fma(vxi[i + (long)nx * k], lastu_prev[(long)inst * nu + k], a);
-            for (int j = 0; j < nz; ++j) a = fma(exi[i + (long)nx * j], z[j], a);
+            for (int j = 0; j < nz; ++j) a = fma(exi[i + (long)nx * j], v[j], a);
             xend[(long)inst * nx + i] = a;
         }
     }

@@ -24,3 +24,198 @@ def move_blocking(Hp, Hc):
         if sum(nb) > Hp:
             nb[-1] = Hp - sum(nb[:-1])
     return nb
+
+
+# ----------------------------------------------------------------------------------------------
+# Batched host-side constructors (numpy, leading axis = instance).  They mirror the reference's
+# one-off setup code; nothing here runs per control period except the tiny estimator updates.
+# ----------------------------------------------------------------------------------------------
+def _b(a, N, shape):
+    """Broadcast a per-model array to (N, *shape)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == len(shape):
+        a = np.broadcast_to(a, (N,) + tuple(shape))
+    if a.shape != (N,) + tuple(shape):
+        raise ValueError(f"expected shape {(N,) + tuple(shape)}, got {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+class LinModel:
+    """Batch of N linear plants ``x0(k+1) = A x0 + Bu u0 + Bd d0 + fop - xop``, ``y0 = C x0 + Dd d0``
+    (reference src/model/linmodel.jl:1-66, direct-matrix constructor :252-253; operating points
+    as set by ``setop!`` src/sim_model.jl:101-126).  Matrices are (N, rows, cols) or 2-D (shared)."""
+
+    def __init__(self, A, Bu, C, Bd=None, Dd=None, Ts=1.0, N=None, uop=None, yop=None, dop=None, xop=None, fop=None):
+        A = np.asarray(A, dtype=np.float64)
+        if N is None:
+            N = A.shape[0] if A.ndim == 3 else 1
+        self.N = N
+        nx = A.shape[-1]
+        Bu = np.asarray(Bu, dtype=np.float64)
+        C = np.asarray(C, dtype=np.float64)
+        nu, ny = Bu.shape[-1], C.shape[-2]
+        nd = 0 if Bd is None else np.asarray(Bd).shape[-1]
+        self.nx, self.nu, self.ny, self.nd, self.Ts = nx, nu, ny, nd, Ts
+        self.A, self.Bu, self.C = _b(A, N, (nx, nx)), _b(Bu, N, (nx, nu)), _b(C, N, (ny, nx))
+        self.Bd = _b(np.zeros((nx, 0)) if Bd is None else Bd, N, (nx, nd))
+        self.Dd = _b(np.zeros((ny, nd)) if Dd is None else Dd, N, (ny, nd))
+        z = lambda v, n: _b(np.zeros(n) if v is None else v, N, (n,))
+        self.uop, self.yop, self.dop, self.xop, self.fop = z(uop, nu), z(yop, ny), z(dop, nd), z(xop, nx), z(fop, nx)
+        self.x0 = np.zeros((N, nx))
+
+    def setstate(self, x):
+        self.x0 = _b(x, self.N, (self.nx,)) - self.xop
+
+    def evaloutput(self, d=None):
+        d0 = (np.zeros((self.N, 0)) if d is None else _b(d, self.N, (self.nd,))) - self.dop
+        return np.einsum("nij,nj->ni", self.C, self.x0) + np.einsum("nij,nj->ni", self.Dd, d0) + self.yop
+
+    def updatestate(self, u, d=None):
+        u0 = _b(u, self.N, (self.nu,)) - self.uop
+        d0 = (np.zeros((self.N, 0)) if d is None else _b(d, self.N, (self.nd,))) - self.dop
+        self.x0 = (np.einsum("nij,nj->ni", self.A, self.x0) + np.einsum("nij,nj->ni", self.Bu, u0)
+                   + np.einsum("nij,nj->ni", self.Bd, d0) + self.fop - self.xop)
+        return self.x0 + self.xop
+
+
+def init_integrators(nint, ny):
+    """reference src/estimator/construct.jl:226-251."""
+    nint = np.zeros(ny, int) if np.isscalar(nint) and nint == 0 else np.asarray(nint, int).reshape(-1)
+    if nint.size != ny or (nint < 0).any():
+        raise ValueError("nint must have one non-negative entry per output")
+    nxs = int(nint.sum())
+    A, C = np.zeros((nxs, nxs)), np.zeros((ny, nxs))
+    i0 = 0
+    for i, k in enumerate(nint):
+        if k:
+            A[i0:i0 + k, i0:i0 + k] = np.eye(k) + np.eye(k, k=-1)
+            C[i, i0 + k - 1] = 1.0
+            i0 += k
+    return A, C, nint
+
+
+def augment_model(model, nint_u=0, nint_ym=None, i_ym=None):
+    """init_estimstoch + augment_model (reference src/estimator/construct.jl:172-185, 305-323), batched.
+    The default ``nint_ym`` is one integrator per measured output (default_nint :365-376 additionally drops
+    integrators that break observability; that check is left to the caller for synthetic plants)."""
+    N, nx, nu, ny, nd = model.N, model.nx, model.nu, model.ny, model.nd
+    i_ym = list(range(ny)) if i_ym is None else list(i_ym)
+    if nint_ym is None:
+        nint_ym = [1] * len(i_ym)
+    As_u, Cs_u, _ = init_integrators(nint_u, nu)
+    As_ym, Cs_ym, _ = init_integrators(nint_ym, len(i_ym))
+    Cs_y = np.zeros((ny, Cs_ym.shape[1]))
+    Cs_y[i_ym] = Cs_ym
+    nsu, nsy = As_u.shape[0], As_ym.shape[0]
+    nxs = nsu + nsy
+    As = np.zeros((nxs, nxs))
+    As[:nsu, :nsu], As[nsu:, nsu:] = As_u, As_ym
+    Cs_u = np.hstack([Cs_u, np.zeros((nu, nsy))])
+    Cs_y = np.hstack([np.zeros((ny, nsu)), Cs_y])
+    nxh = nx + nxs
+    Ahat = np.zeros((N, nxh, nxh))
+    Ahat[:, :nx, :nx] = model.A
+    Ahat[:, :nx, nx:] = model.Bu @ Cs_u
+    Ahat[:, nx:, nx:] = As
+    Buhat = np.concatenate([model.Bu, np.zeros((N, nxs, nu))], axis=1)
+    Chat = np.concatenate([model.C, np.broadcast_to(Cs_y, (N, ny, nxs))], axis=2)
+    Bdhat = np.concatenate([model.Bd, np.zeros((N, nxs, nd))], axis=1)
+    xop = np.concatenate([model.xop, np.zeros((N, nxs))], axis=1)
+    fop = np.concatenate([model.fop, np.zeros((N, nxs))], axis=1)
+    return dict(Ahat=Ahat, Buhat=Buhat, Chat=Chat, Bdhat=Bdhat, Ddhat=model.Dd.copy(), xophat=xop, fophat=fop,
+                nxhat=nxh, nxs=nxs, i_ym=i_ym, nint_ym=list(nint_ym))
+
+
+def dare_filter_sda(A, C, Q, R, iters=60, tol=1e-13):
+    """Batched filter Riccati  P = A P A' - A P C'(C P C' + R)^-1 C P A' + Q  by the structure-preserving
+    doubling algorithm (quadratic convergence); A (N,n,n), C (N,m,n), Q (n,n) or (N,n,n), R (m,m) or (N,m,m).
+    Stands in for ControlSystemsBase.kalman (third-party) used by init_skf, reference
+    src/estimator/kalman.jl:204-227."""
+    N, n = A.shape[0], A.shape[-1]
+    Q = np.broadcast_to(Q, (N, n, n))
+    R = np.broadcast_to(R, (N,) + R.shape[-2:])
+    Ak = np.swapaxes(A, 1, 2).copy()                       # dual system: A -> A', B -> C'
+    Gk = np.swapaxes(C, 1, 2) @ np.linalg.solve(R, C)       # C' R^-1 C
+    Hk = Q.copy()
+    I = np.eye(n)
+    for _ in range(iters):
+        W = np.linalg.inv(I + Gk @ Hk)
+        AW = Ak @ W
+        Gn = Gk + AW @ Gk @ np.swapaxes(Ak, 1, 2)
+        Hn = Hk + np.swapaxes(Ak, 1, 2) @ Hk @ W @ Ak
+        An = AW @ Ak
+        done = np.abs(Hn - Hk).max() <= tol * (1 + np.abs(Hn).max())
+        Ak, Gk, Hk = An, Gn, Hn
+        if done:
+            break
+    return 0.5 * (Hk + np.swapaxes(Hk, 1, 2))
+
+
+class SteadyKalmanFilter:
+    """Batched ``SteadyKalmanFilter`` (reference src/estimator/kalman.jl:163-227, 284-309): constant gain
+    K̂ = P Ĉm'(Ĉm P Ĉm' + R̂)^-1 (direct=true).  ``preparestate`` / ``updatestate`` are the reference's
+    correct_estimate_obsv! / predict_estimate_obsv!."""
+
+    direct = True
+
+    def __init__(self, model, nint_u=0, nint_ym=None, i_ym=None, sigmaQ=None, sigmaR=None, sigmaQint_u=None,
+                 sigmaQint_ym=None):
+        self.model = model
+        aug = augment_model(model, nint_u, nint_ym, i_ym)
+        self.__dict__.update(aug)
+        N, nx = model.N, model.nx
+        nym = len(self.i_ym)
+        sQ = np.full(nx, 1.0 / nx) if sigmaQ is None else np.asarray(sigmaQ, float)
+        sR = np.ones(nym) if sigmaR is None else np.asarray(sigmaR, float)
+        nsu = int(np.sum(nint_u)) if not np.isscalar(nint_u) else int(nint_u) * 0
+        sQu = np.ones(nsu) if sigmaQint_u is None else np.asarray(sigmaQint_u, float)
+        sQy = np.ones(self.nxs - nsu) if sigmaQint_ym is None else np.asarray(sigmaQint_ym, float)
+        self.Qhat = np.diag(np.concatenate([sQ, sQu, sQy]) ** 2)
+        self.Rhat = np.diag(sR ** 2)
+        self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]
+        P = dare_filter_sda(self.Ahat, self.Cmhat, self.Qhat, self.Rhat)
+        S = self.Cmhat @ P @ np.swapaxes(self.Cmhat, 1, 2) + self.Rhat
+        self.Khat = np.swapaxes(np.linalg.solve(np.swapaxes(S, 1, 2), self.Cmhat @ np.swapaxes(P, 1, 2)), 1, 2)
+        self.Phat = P
+        self.xhat0 = np.zeros((N, self.nxhat))
+
+    def _d0(self, d):
+        return (np.zeros((self.model.N, 0)) if d is None else _b(d, self.model.N, (self.model.nd,))) - self.model.dop
+
+    def setstate(self, xhat):
+        self.xhat0 = _b(xhat, self.model.N, (self.nxhat,)) - self.xophat
+
+    def preparestate(self, ym, d=None):
+        y0m = _b(ym, self.model.N, (len(self.i_ym),)) - self.model.yop[:, self.i_ym]
+        d0 = self._d0(d)
+        v = y0m - (np.einsum("nij,nj->ni", self.Cmhat, self.xhat0) + np.einsum("nij,nj->ni", self.Ddmhat, d0))
+        self.xhat0 = self.xhat0 + np.einsum("nij,nj->ni", self.Khat, v)
+        return self.xhat0 + self.xophat
+
+    def updatestate(self, u, ym, d=None):
+        u0 = _b(u, self.model.N, (self.model.nu,)) - self.model.uop
+        d0 = self._d0(d)
+        self.xhat0 = (np.einsum("nij,nj->ni", self.Ahat, self.xhat0) + np.einsum("nij,nj->ni", self.Buhat, u0)
+                      + np.einsum("nij,nj->ni", self.Bdhat, d0) + self.fophat - self.xophat)
+        return self.xhat0 + self.xophat
+
+    def evaloutput(self, d=None):
+        d0 = self._d0(d)
+        return (np.einsum("nij,nj->ni", self.Chat, self.xhat0) + np.einsum("nij,nj->ni", self.Ddhat, d0)
+                + self.model.yop)
+
+
+class ManualEstimator(SteadyKalmanFilter):
+    """``ManualEstimator`` (reference src/estimator/manual.jl:60-64,150-154): the caller sets x̂ with
+    ``setstate``; prepare/update do nothing."""
+
+    def __init__(self, model, nint_u=0, nint_ym=None, i_ym=None):
+        self.model = model
+        self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
+        self.xhat0 = np.zeros((model.N, self.nxhat))
+
+    def preparestate(self, ym, d=None):
+        return self.xhat0 + self.xophat
+
+    def updatestate(self, u, ym, d=None):
+        return self.xhat0 + self.xophat

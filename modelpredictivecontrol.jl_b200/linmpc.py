@@ -1,0 +1,155 @@
+"""``LinMPC``: host-side mirror of the reference controller API for a BATCH of controllers.
+
+Same names and argument meaning as the reference (src/controller/linmpc.jl:229-316,
+``setconstraint!`` construct.jl:324-559, ``moveinput!`` execute.jl:59-80, ``getinfo`` :145-198,
+``preparestate!/updatestate!`` :523-555), with a leading batch axis on every array.  The per-period
+work is one call into libbmpc.so; there is no Python/CPU implementation of the step.
+"""
+import numpy as np
+
+from .batch import BatchLinMPC
+from .host import LinModel, ManualEstimator, SteadyKalmanFilter, _b, move_blocking
+
+DEFAULT_HP0, DEFAULT_HC, DEFAULT_MWT, DEFAULT_NWT, DEFAULT_LWT, DEFAULT_CWT = 10, 2, 1.0, 0.1, 0.0, 1e5
+
+
+class LinMPC:
+    def __init__(self, model_or_estim, Hp=None, Hc=DEFAULT_HC, Mwt=None, Nwt=None, Lwt=None, Cwt=DEFAULT_CWT,
+                 device=0, team=0, max_iter=0, tol=0.0, **estim_kwargs):
+        estim = model_or_estim if hasattr(model_or_estim, "Ahat") else SteadyKalmanFilter(model_or_estim, **estim_kwargs)
+        model = estim.model
+        self.estim, self.model = estim, model
+        N, nu, ny, nd = model.N, model.nu, model.ny, model.nd
+        if Hp is None:
+            Hp = DEFAULT_HP0  # default_Hp adds the estimated delays (construct.jl:569-591); batch plants: none assumed
+        self.nb = move_blocking(Hp, Hc)
+        self.Hp, self.Hc = Hp, len(self.nb)
+        w = lambda v, dflt, n: np.full(n, dflt) if v is None else np.asarray(v, dtype=np.float64).reshape(n)
+        self.Mwt, self.Nwt, self.Lwt = w(Mwt, DEFAULT_MWT, ny), w(Nwt, DEFAULT_NWT, nu), w(Lwt, DEFAULT_LWT, nu)
+        if (self.Mwt < 0).any() or (self.Nwt < 0).any() or (self.Lwt < 0).any():
+            raise ValueError("weights should be nonnegative")
+        self.Cwt = float(Cwt)
+        self.batch = BatchLinMPC(N, nu, ny, estim.nxhat, Hp, self.nb, nd=nd, Cwt=Cwt, device=device, team=team,
+                                 max_iter=max_iter, tol=tol)
+        b = self.batch
+        b.set_model(estim.Ahat, estim.Buhat, estim.Chat, estim.Bdhat if nd else None, estim.Ddhat if nd else None,
+                    estim.fophat - estim.xophat, np.tile(self.Mwt, Hp), np.tile(self.Nwt, self.Hc),
+                    np.tile(self.Lwt, Hp))
+        b.set_oppoints(model.uop, model.yop)
+        self.Uop, self.Yop = np.tile(model.uop, (1, Hp)), np.tile(model.yop, (1, Hp))
+        inf = np.inf
+        self.con = dict(U0min=np.full((N, nu * Hp), -inf), U0max=np.full((N, nu * Hp), inf),
+                        DUmin=np.full((N, nu * self.Hc), -inf), DUmax=np.full((N, nu * self.Hc), inf),
+                        Y0min=np.full((N, ny * Hp), -inf), Y0max=np.full((N, ny * Hp), inf),
+                        xhat0min=np.full((N, estim.nxhat), -inf), xhat0max=np.full((N, estim.nxhat), inf))
+        self.soft = dict(C_umin=np.zeros(nu * Hp), C_umax=np.zeros(nu * Hp), C_dumin=np.zeros(nu * self.Hc),
+                         C_dumax=np.zeros(nu * self.Hc), C_ymin=np.ones(ny * Hp), C_ymax=np.ones(ny * Hp),
+                         c_xmin=np.ones(estim.nxhat), c_xmax=np.ones(estim.nxhat))
+        self._solved = False
+        self._push()
+
+    @property
+    def Ztilde(self):
+        return self.batch.Ztilde
+
+    @property
+    def lastu0(self):
+        return self.batch.lastu0
+
+    def _push(self):
+        c = self.con
+        self.batch.set_constraints(c["U0min"], c["U0max"], c["DUmin"], c["DUmax"], c["Y0min"], c["Y0max"],
+                                   c["xhat0min"], c["xhat0max"], self.soft if self.batch.neps else None)
+
+    def setconstraint(self, umin=None, umax=None, dumin=None, dumax=None, ymin=None, ymax=None, xhatmin=None,
+                      xhatmax=None, Umin=None, Umax=None, DUmin=None, DUmax=None, Ymin=None, Ymax=None,
+                      c_umin=None, c_umax=None, c_dumin=None, c_dumax=None, c_ymin=None, c_ymax=None,
+                      c_xhatmin=None, c_xhatmax=None):
+        """``setconstraint!``: bounds are per instance ((N, len) or (len,)), softness is shared."""
+        N, Hp, Hc = self.model.N, self.Hp, self.Hc
+        nu, ny, nx = self.model.nu, self.model.ny, self.estim.nxhat
+        c = self.con
+        rep = lambda v, n, k: np.tile(_b(v, N, (n,)), (1, k))
+        if Umin is None and umin is not None: c["U0min"] = rep(umin, nu, Hp) - self.Uop
+        elif Umin is not None: c["U0min"] = _b(Umin, N, (nu * Hp,)) - self.Uop
+        if Umax is None and umax is not None: c["U0max"] = rep(umax, nu, Hp) - self.Uop
+        elif Umax is not None: c["U0max"] = _b(Umax, N, (nu * Hp,)) - self.Uop
+        if DUmin is None and dumin is not None: c["DUmin"] = rep(dumin, nu, Hc)
+        elif DUmin is not None: c["DUmin"] = _b(DUmin, N, (nu * Hc,)).copy()
+        if DUmax is None and dumax is not None: c["DUmax"] = rep(dumax, nu, Hc)
+        elif DUmax is not None: c["DUmax"] = _b(DUmax, N, (nu * Hc,)).copy()
+        if Ymin is None and ymin is not None: c["Y0min"] = rep(ymin, ny, Hp) - self.Yop
+        elif Ymin is not None: c["Y0min"] = _b(Ymin, N, (ny * Hp,)) - self.Yop
+        if Ymax is None and ymax is not None: c["Y0max"] = rep(ymax, ny, Hp) - self.Yop
+        elif Ymax is not None: c["Y0max"] = _b(Ymax, N, (ny * Hp,)) - self.Yop
+        if xhatmin is not None: c["xhat0min"] = _b(xhatmin, N, (nx,)) - self.estim.xophat
+        if xhatmax is not None: c["xhat0max"] = _b(xhatmax, N, (nx,)) - self.estim.xophat
+        ecr = dict(C_umin=(c_umin, nu, Hp), C_umax=(c_umax, nu, Hp), C_dumin=(c_dumin, nu, Hc),
+                   C_dumax=(c_dumax, nu, Hc), C_ymin=(c_ymin, ny, Hp), C_ymax=(c_ymax, ny, Hp),
+                   c_xmin=(c_xhatmin, nx, 1), c_xmax=(c_xhatmax, nx, 1))
+        if any(v[0] is not None for v in ecr.values()):
+            if not self.batch.neps:
+                raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
+            if self._solved:
+                raise RuntimeError("Cannot set softness parameters after calling moveinput!")
+            for k, (v, n, reps) in ecr.items():
+                if v is not None:
+                    v = np.asarray(v, dtype=np.float64).reshape(n)
+                    if (v < 0).any():
+                        raise ValueError(f"{k} weights should be non-negative")
+                    self.soft[k] = np.tile(v, reps)
+        self._push()
+        return self
+
+    # ---- estimator pass-throughs ----
+    def preparestate(self, ym, d=None):
+        return self.estim.preparestate(ym, d)
+
+    def updatestate(self, u, ym, d=None):
+        return self.estim.updatestate(u, ym, d)
+
+    def setstate(self, xhat):
+        self.estim.setstate(xhat)
+        return self
+
+    # ---- the hot path ----
+    def moveinput(self, ry=None, d=None, lastu=None, Dhat=None, Rhat_y=None, Rhat_u=None):
+        m = self.model
+        N = m.N
+        ry = m.yop if ry is None else _b(ry, N, (m.ny,))
+        if lastu is not None:
+            self.batch.lastu0[:] = _b(lastu, N, (m.nu,)) - m.uop
+        d0 = Dh0 = None
+        if m.nd:
+            d0 = _b(d, N, (m.nd,)) - m.dop
+            if Dhat is not None:
+                Dh0 = _b(Dhat, N, (m.nd * self.Hp,)) - np.tile(m.dop, (1, self.Hp))
+        self._solved = True
+        return self.batch.step(self.estim.xhat0, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0).copy()
+
+    def getinfo(self):
+        i = self.batch.getinfo()
+        out = dict(DU=i["DU"], eps=i["eps"], J=i["J"], U=i["U0"] + self.Uop, Yhat=i["Yhat0"] + self.Yop,
+                   xhatend=i["xhat0end"] + self.estim.xophat, status=i["status"], iters=i["iters"])
+        out["u"] = out["U"][:, :self.model.nu]
+        return out
+
+
+def sim(mpc, steps, ry, plant=None, y_noise=None):
+    """Batched ``sim!`` closed loop (reference src/plot_sim.jl:253-319): per period
+    y = plant(); preparestate!; u = moveinput!(ry); updatestate! on plant and estimator."""
+    plant = plant or LinModel(mpc.model.A, mpc.model.Bu, mpc.model.C, N=mpc.model.N, uop=mpc.model.uop,
+                              yop=mpc.model.yop, xop=mpc.model.xop, fop=mpc.model.fop)
+    N = mpc.model.N
+    Y, U = np.zeros((steps, N, mpc.model.ny)), np.zeros((steps, N, mpc.model.nu))
+    for k in range(steps):
+        r = ry(k) if callable(ry) else ry
+        y = plant.evaloutput()
+        if y_noise is not None:
+            y = y + y_noise[k]
+        mpc.preparestate(y)
+        u = mpc.moveinput(r)
+        Y[k], U[k] = y, u
+        plant.updatestate(u)
+        mpc.updatestate(u, y)
+    return dict(Y=Y, U=U)

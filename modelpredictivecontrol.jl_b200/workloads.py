@@ -1,0 +1,29 @@
+"""Synthetic workloads of BASELINE.json's configs: seeded random stable plants."""
+import numpy as np
+
+from .host import LinModel
+
+CONFIGS = {
+    # name: (N, nx, nu, ny, Hp, Hc, seed)
+    "C1": (4096, 4, 2, 2, 20, 5, 1),
+    "C2": (65536, 8, 4, 4, 30, 10, 2),
+    "C4": (16384, 16, 8, 8, 50, 20, 4),
+}
+
+
+def random_plants(N, nx, nu, ny, seed, rho=(0.5, 0.95)):
+    """A ~ N(0,1) scaled to spectral radius U(0.5, 0.95); Bu, C ~ N(0,1)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((N, nx, nx))
+    rad = np.abs(np.linalg.eigvals(A)).max(axis=1)
+    A *= (rng.uniform(rho[0], rho[1], N) / rad)[:, None, None]
+    Bu = rng.standard_normal((N, nx, nu))
+    C = rng.standard_normal((N, ny, nx))
+    return LinModel(A, Bu, C, N=N), rng
+
+
+def setpoints(rng, N, ny, steps, period=25):
+    """Setpoint steps ry in {-1,+1}^ny switching every ``period`` control periods: (steps, N, ny)."""
+    nseg = (steps + period - 1) // period
+    seg = rng.choice([-1.0, 1.0], (nseg, N, ny))
+    return np.repeat(seg, period, axis=0)[:steps]

