@@ -23,6 +23,7 @@
 #include "bmpc_device.cuh"
 #include "bmpc_setup.cuh"
 #include "bmpc_model.cuh"
+#include "bmpc_small_registry.h"
 
 namespace {
 
@@ -106,6 +107,10 @@ struct bmpc_handle {
     DevBuf<unsigned int> counters;
     // launch geometry
     int team = 0, teams_per_cta = 0, grid = 0, smem_bytes = 0;
+    bool dirty = true;      // launch geometry / derived arrays must be rebuilt before the next step
+    const bmpc::SmallEntry* small = nullptr;  // chosen small-kernel specialisation, or null (general kernel)
+    bmpc::SmallParams sp{};
+    DevBuf<double> PdR, HvS, LvS;
     bmpc::SmemLayout sm{};
     int64_t launches = 0;
 };
@@ -190,7 +195,113 @@ int configure(bmpc_handle* h) {
     return BMPC_OK;
 }
 
+const std::vector<bmpc::SmallEntry>& small_registry() {
+    static std::vector<bmpc::SmallEntry> reg = [] {
+        std::vector<bmpc::SmallEntry> v;
+        bmpc::small_register_02(v);
+        bmpc::small_register_04(v);
+        bmpc::small_register_06(v);
+        bmpc::small_register_08(v);
+        bmpc::small_register_10(v);
+        bmpc::small_register_12(v);
+        bmpc::small_register_15(v);
+        return v;
+    }();
+    return reg;
+}
+
+int configure_small(bmpc_handle* h, const bmpc::SmallEntry& E) {
+    const int nzt = E.nzt, nt = E.nzt + E.neps, DS = E.ds, SS = E.ss;
+    const int nz = h->nz, nDb = h->rt.nDb, nY = h->nY, nx = h->d.nxhat;
+    const int nsr = h->rt.nS + h->d.neps;
+    const int ldp = (nzt + 1) & ~1, ldn = nt | 1;
+    bmpc::SmallLayout& L = h->sp.L;
+    L.nDbp = even(nDb);
+    L.nPdR = L.nDbp * ldp;
+    L.nHS = even(nzt * ldp);
+    int o = 0;
+    auto take = [&](int cnt) { int at = o; o += even(std::max(cnt, 1)); return at; };
+    L.Pd = take(L.nPdR);
+    L.Hv = take(L.nHS);
+    L.Lb = take(std::max(L.nHS, even(nt * ldn)));
+    L.vbuf = take(16);
+    L.wd = take(16 * DS);
+    L.wp = take(32 * DS);
+    L.ws = take(16 * SS);
+    L.bb = take(16);
+    L.F = take(nY);
+    L.tY = take(nY);
+    L.fx = take(nx);
+    L.xh = take(nx);
+    L.lu = take(h->d.nu);
+    L.dd = take(h->d.nd);
+    L.Dh = take(h->d.nd * h->d.Hp);
+    L.bar = take(2);
+    L.team_total = o;
+    o = 0;
+    L.t_sigd = take(nDb); L.t_cd = take(nDb); L.t_srcd = take((nDb + 1) / 2);
+    L.t_sigs = take(nsr); L.t_cs = take(nsr); L.t_i1 = take((nsr + 1) / 2); L.t_i2 = take((nsr + 1) / 2);
+    L.t_ch = take((nsr + 1) / 2); L.t_vptr = take((nzt + 2) / 2);
+    const int nnz = 2 * h->rt.nS;
+    L.t_vrow = take((nnz + 1) / 2); L.t_vsgn = take((nnz + 1) / 2);
+    L.tab_total = o;
+    const int teams = 4;  // 64 threads
+    h->smem_bytes = (L.team_total * teams + L.tab_total) * 8;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
+    if (h->smem_bytes > max_optin) return BMPC_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(E.func, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, E.func, 64, h->smem_bytes));
+    if (occ < 1) return BMPC_ERR_UNSUPPORTED;
+    h->team = 16;
+    h->teams_per_cta = teams;
+    const int need = (h->d.N + teams - 1) / teams;
+    h->grid = std::max(1, std::min(need, occ * h->num_sms));
+    h->small = &E;
+    h->pd_in_smem = true;
+    h->sp.nsr = nsr;
+    // row-major padded copies (TMA sources)
+    const long NM = h->NM;
+    h->sp.sPdR = h->d.shared_model ? 0 : L.nPdR;
+    h->sp.sHS = h->d.shared_model ? 0 : L.nHS;
+    CK(h->PdR.alloc((size_t)NM * std::max(L.nPdR, 2)));
+    CK(h->HvS.alloc((size_t)NM * L.nHS));
+    CK(h->LvS.alloc((size_t)NM * L.nHS));
+    CK(cudaMemsetAsync(h->PdR.p, 0, (size_t)NM * std::max(L.nPdR, 2) * 8, h->stream));
+    CK(cudaMemsetAsync(h->HvS.p, 0, (size_t)NM * L.nHS * 8, h->stream));
+    CK(cudaMemsetAsync(h->LvS.p, 0, (size_t)NM * L.nHS * 8, h->stream));
+    const double* pdsrc = h->pd_is_ev ? h->Ev.p : h->Pd.p;
+    const long spd = h->pd_is_ev ? h->nEv2 : h->nPd2;
+    bmpc::k_make_small<<<(unsigned)NM, 128, 0, h->stream>>>(pdsrc, spd, nDb, h->Hv.p, h->Lv.p, h->nHp2, h->PdR.p, (long)L.nPdR,
+                                                          h->HvS.p, h->LvS.p, (long)L.nHS, nz, nzt, ldp);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->sp.PdR = h->PdR.p;
+    h->sp.HvS = h->HvS.p;
+    h->sp.LvS = h->LvS.p;
+    return BMPC_OK;
+}
+
 int configure_launch(bmpc_handle* h) {
+    h->small = nullptr;
+    const int forced = h->d.team ? h->d.team : (getenv("BMPC_TEAM") ? atoi(getenv("BMPC_TEAM")) : 0);
+    const int nsr = h->rt.nS + h->d.neps;
+    const bool one_sided = h->rt.nDr == h->rt.nDb;
+    if (forced == 0 && h->n <= 16 && one_sided && !h->M_dense && h->have_predmat) {
+        // smallest specialisation that holds the controller (padding with dummy variables is exact)
+        const bmpc::SmallEntry* best = nullptr;
+        for (const bmpc::SmallEntry& E : small_registry()) {
+            if (E.neps != h->d.neps || E.nzt < h->nz || h->rt.nDb > 16 * E.ds || nsr > 16 * E.ss) continue;
+            if (!best || E.nzt < best->nzt || (E.nzt == best->nzt && E.ds < best->ds)) best = &E;
+        }
+        if (best) {
+            int rc = configure_small(h, *best);
+            if (rc == BMPC_OK) return rc;
+            if (rc != BMPC_ERR_UNSUPPORTED) return rc;
+            h->small = nullptr;
+        }
+    }
     switch (choose_team(h)) {
         case 8: return configure<8>(h);
         case 16: return configure<16>(h);
@@ -200,6 +311,24 @@ int configure_launch(bmpc_handle* h) {
         case 256: return configure<256>(h);
         default: return fail(BMPC_ERR_ARG, "team must be one of 0,8,16,32,64,128,256");
     }
+}
+
+// (re)build everything that depends on model + weights + constraints together
+int finalize(bmpc_handle* h) {
+    cudaStream_t s = h->stream;
+    if (!h->pd_is_ev && h->rt.nDb > 0) {
+        const long tot = (long)h->NM * h->rt.nDb * h->nz;
+        bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->has_terminal_mats ? h->exv.p : nullptr, h->Pd.p,
+                                                                      h->t_pdsrc.p, h->nY, h->d.nxhat, h->nz, h->rt.nDb,
+                                                                      (long)h->nEv2, h->nPd2, tot);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    int rc = configure_launch(h);
+    if (rc != BMPC_OK) return rc;
+    CK(cudaStreamSynchronize(s));
+    h->dirty = false;
+    return BMPC_OK;
 }
 
 template <int TEAM>
@@ -383,15 +512,7 @@ int bmpc_set_predmat(bmpc_handle* h, const double* E, const double* K, const dou
     }
     CK(cudaGetLastError());
     h->have_predmat = true;
-    if (h->have_constraints) {  // Pd depends on Ev / exv
-        if (!h->pd_is_ev && h->rt.nDb > 0) {
-            const long tot = (long)NM * h->rt.nDb * nz;
-            bmpc::k_gather_pd<<<(unsigned)((tot + TB - 1) / TB), TB, 0, s>>>(h->Ev.p, term ? h->exv.p : nullptr, h->Pd.p, h->t_pdsrc.p,
-                                                                            (int)nY, (int)nx, (int)nz, h->rt.nDb, (long)h->nEv2, h->nPd2, tot);
-            h->launches++;
-            CK(cudaGetLastError());
-        }
-    }
+    h->dirty = true;
     CK(cudaStreamSynchronize(s));
     h->E.release();  // only the level-coordinate copies are kept
     h->ex.release();
@@ -416,6 +537,7 @@ int bmpc_set_weights(bmpc_handle* h, const double* M, int32_t M_dense, const dou
     }
     CK(cudaStreamSynchronize(h->stream));
     h->have_weights = true;
+    h->dirty = true;
     return BMPC_OK;
 }
 
@@ -637,24 +759,19 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     rt.pair_i = h->t_pi.p;
     rt.pair_j = h->t_pj.p;
     h->has_terminal_rows = any_x;
+    h->sp.has_pair_rows = 0;
+    for (int g = 0; g < nS; ++g)
+        if (s_i2[g] >= 0) h->sp.has_pair_rows = 1;
     h->pd_is_ev = (nDb == nY) && !any_x;  // dense base rows are exactly the rows of Ev, in order
     h->nPd2 = even(nDb * nz);
     if (!h->pd_is_ev && nDb > 0) {
         CK(h->Pd.alloc((size_t)h->NM * h->nPd2));
         CK(cudaMemsetAsync(h->Pd.p, 0, (size_t)h->NM * h->nPd2 * sizeof(double), s));
-        if (h->have_predmat) {
-            const long tot = (long)h->NM * nDb * nz;
-            bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->has_terminal_mats ? h->exv.p : nullptr, h->Pd.p,
-                                                                          h->t_pdsrc.p, nY, nx, nz, nDb, (long)h->nEv2, h->nPd2, tot);
-            h->launches++;
-            CK(cudaGetLastError());
-        }
     }
     CK(cudaStreamSynchronize(s));
     h->pattern = pat;
     h->have_constraints = true;
-    int rc = configure_launch(h);
-    if (rc != BMPC_OK) return rc;
+    h->dirty = true;
     return BMPC_OK;
 }
 
@@ -676,6 +793,10 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         return fail(BMPC_ERR_ARG, "xhat0, lastu0, ry|Rhat_y, Ztilde, u, status, iters are required");
     if (d.nd > 0 && !io->d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
     if (h->has_terminal_rows && !h->has_terminal_mats) return fail(BMPC_ERR_STATE, "terminal matrices missing");
+    if (h->dirty) {
+        int rc = finalize(h);
+        if (rc != BMPC_OK) return rc;
+    }
     cudaStream_t s = h->stream;
     const size_t N = d.N, nx = d.nxhat, nu = d.nu, ny = d.ny, nd = d.nd, Hp = d.Hp, n = h->n, nY = h->nY, nU = h->nU;
     bmpc::StepParams P{};
@@ -733,6 +854,9 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.counters = h->counters.p;
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     cudaError_t le;
+    if (h->small) {
+        le = h->small->launch(P, h->sp, h->grid, h->smem_bytes, h->stream);
+    } else
     switch (h->team) {
         case 8: le = launch_step<8>(h, P); break;
         case 16: le = launch_step<16>(h, P); break;
@@ -795,7 +919,7 @@ int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
     out[1] = h->teams_per_cta;
     out[2] = h->grid;
     out[3] = h->smem_bytes;
-    out[4] = h->pd_in_smem;
+    out[4] = h->small ? 100 + h->small->nzt : (int)h->pd_in_smem;  // >= 100: small kernel, NZT = value - 100
     out[5] = h->rt.m;
     out[6] = h->rt.nS;
     out[7] = h->rt.nDr;
@@ -882,13 +1006,7 @@ int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, cons
     h->has_terminal_mats = true;
     h->have_predmat = true;
     h->have_weights = true;
-    if (h->have_constraints && !h->pd_is_ev && h->rt.nDb > 0) {
-        const long tot = (long)NM * h->rt.nDb * nz;
-        bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->exv.p, h->Pd.p, h->t_pdsrc.p, (int)nY, (int)nx,
-                                                                      (int)nz, h->rt.nDb, (long)h->nEv2, h->nPd2, tot);
-        h->launches++;
-        CK(cudaGetLastError());
-    }
+    h->dirty = true;
     CK(cudaStreamSynchronize(s));
     A.release(); Bu.release(); C.release(); Bd.release(); Dd.release(); f.release(); Nd.release();
     return BMPC_OK;

@@ -1,0 +1,9 @@
+// step_small specialisations for NZT = 6 move variables (see bmpc_small_registry.h).
+#include "bmpc_small_registry.h"
+
+namespace bmpc {
+void small_register_06(std::vector<SmallEntry>& v) {
+    v.push_back(small_entry<6, 0, 3, 2>());
+    v.push_back(small_entry<6, 1, 3, 2>());
+}
+}  // namespace bmpc
