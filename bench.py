@@ -78,13 +78,13 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def build_workload(rank, total_periods):
+def build_workload(rank, total_periods, device=0):
     """C1 batch on this rank + recorded closed-loop trajectory (untimed)."""
     import mpc_b200
     from mpc_b200 import workloads
     N, nx, nu, ny, Hp, Hc, seed = workloads.CONFIGS[WORKLOAD]
     model, rng = workloads.random_plants(N, nx, nu, ny, seed + 1000 * rank)
-    mpc = mpc_b200.LinMPC(model, Hp=Hp, Hc=Hc, Cwt=1e5)
+    mpc = mpc_b200.LinMPC(model, Hp=Hp, Hc=Hc, Cwt=1e5, device=device)
     mpc.setconstraint(umin=[-1.0] * nu, umax=[1.0] * nu, ymax=[0.8] * ny)
     ry = workloads.setpoints(rng, N, ny, total_periods, period=25)
     plant = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N)
@@ -180,7 +180,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import mpc_b200
-    mpc, model, rec = build_workload(rank, total)
+    mpc, model, rec = build_workload(rank, total, device=local_rank)
     b = mpc.batch
     n = b.n
     dev = torch.device("cuda", local_rank)
