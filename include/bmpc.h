@@ -162,6 +162,53 @@ int bmpc_launch_info(bmpc_handle *h, int32_t out[8]);
 /* Number of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t bmpc_launch_count(bmpc_handle *h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Linear MovingHorizonEstimator (LinModel + SingleShooting, direct = true), batched.
+ * Replaces preparestate!/correct_estimate! and updatestate!/update_estimate! of the reference
+ * (src/estimator/mhe/execute.jl:44-84): the handle owns the data windows, the arrival state and
+ * the arrival covariance of every instance (estim.Y0m/U0/D0/X̂0_old/x̂0arr_old/P̂arr_old/invP̄, Nk).
+ * Z̃ = [ε; x̂0(k-Nk); Ŵ] (slack FIRST, src/estimator/mhe/construct.jl:1174-1178).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct bmhe_handle bmhe_handle;
+
+typedef struct {
+    int32_t N;            /* estimator instances                                                   */
+    int32_t nu, nym, nd;  /* inputs, measured outputs, measured disturbances                       */
+    int32_t nxhat;        /* augmented state size (<= 32)                                          */
+    int32_t He;           /* estimation horizon                                                    */
+    int32_t neps;         /* 1 if Cwt finite                                                       */
+    int32_t direct;       /* must be 1 (current form, the reference default)                       */
+    int32_t shared_model; /* 1: matrices given once                                                */
+    int32_t max_iter;     /* 0 -> 50                                                               */
+    int32_t device;
+    int32_t reserved;
+    double tol;           /* 0 -> 1e-11                                                            */
+} bmhe_dims;
+
+int bmhe_create(bmhe_handle **out, const bmhe_dims *dims);
+int bmhe_destroy(bmhe_handle *h);
+/* estim.Ẽ (without the slack column: nym*He x nxhat*(He+1)), .G, .J, .B and con.ẼX̂ (same), GX̂, JX̂, BX̂
+ * (init_predmat_mhe, src/estimator/mhe/transcription.jl:151-260), column-major, NM copies. */
+int bmhe_set_predmat(bmhe_handle *h, const double *E, const double *G, const double *J, const double *B,
+                     const double *EX, const double *GX, const double *JX, const double *BX);
+/* estim.Â, Ĉm and the covariances P̂_0, Q̂, R̂ (R̂ diagonal) of cov (estimator/construct.jl:60-119); resets. */
+int bmhe_set_cov(bmhe_handle *h, const double *Ahat, const double *Cmhat, const double *P0, const double *Qhat,
+                 const double *Rhat, double Cwt);
+/* setconstraint!(mhe; x̂min, x̂max, ŵmin, ŵmax, v̂min, v̂max) in deviation form, N x len (NULL = none);
+ * softness c_x (2*nxhat: min then max), c_w (2*nxhat), c_v (2*nym), shared, NULL = hard (the default). */
+int bmhe_set_constraints(bmhe_handle *h, const double *xmin, const double *xmax, const double *wmin,
+                         const double *wmax, const double *vmin, const double *vmax, const double *c_x,
+                         const double *c_w, const double *c_v);
+/* init_estimate_cov!: empty windows, Nk = 0, P̄ = P̂_0, x̂0 = 0 (execute.jl:2-37). */
+int bmhe_reset(bmhe_handle *h);
+/* preparestate!: add y0m(k), d0(k) (and the stored u0(k-1)) to the windows, correct P̄ when the window
+ * moves, rebuild H̃/q̃, solve, return x̂0(k) (N x nxhat).  Optional outputs may be NULL. */
+int bmhe_correct(bmhe_handle *h, const double *y0m, const double *d0, double *xhat0, double *Ztilde, double *J,
+                 int32_t *status, int32_t *iters, double *Vhat, double *X0);
+/* updatestate!: store u0(k); when the window is full, P̄ <- Â P̄ Â' + Q̂ (update_cov!). */
+int bmhe_update(bmhe_handle *h, const double *u0);
+int64_t bmhe_launch_count(bmhe_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,10 @@ from ._lib import (BmpcError, STATUS_INFEASIBLE, STATUS_ITERATION_LIMIT, STATUS_
 from .batch import BatchLinMPC
 from .host import LinModel, ManualEstimator, SteadyKalmanFilter, move_blocking
 from .linmpc import LinMPC, sim
+from .mhe import MovingHorizonEstimator
 from . import workloads
 from .shard import gather_moves, shard_range
 
-__all__ = ["BatchLinMPC", "LinMPC", "LinModel", "SteadyKalmanFilter", "ManualEstimator", "sim", "workloads", "shard_range", "gather_moves",
+__all__ = ["BatchLinMPC", "LinMPC", "MovingHorizonEstimator", "LinModel", "SteadyKalmanFilter", "ManualEstimator", "sim", "workloads", "shard_range", "gather_moves",
            "BmpcError", "move_blocking", "STATUS_OPTIMAL", "STATUS_ITERATION_LIMIT",
            "STATUS_INFEASIBLE"]

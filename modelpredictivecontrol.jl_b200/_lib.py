@@ -35,6 +35,11 @@ class StepIO(C.Structure):
                  ("device_ptrs", C.c_int32), ("sync", C.c_int32)])
 
 
+class MheDims(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("N", "nu", "nym", "nd", "nxhat", "He", "neps", "direct", "shared_model",
+                                         "max_iter", "device", "reserved")] + [("tol", C.c_double)]
+
+
 class Info(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("Yhat0", "U0", "xhat0end", "F", "qtilde", "r")]
 
@@ -50,7 +55,9 @@ _lib = None
 # every symbol include/bmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bmpc_set_stream", "bmpc_set_model",
            "bmpc_set_predmat", "bmpc_set_weights", "bmpc_set_oppoints", "bmpc_set_constraints", "bmpc_step",
-           "bmpc_getinfo", "bmpc_launch_info", "bmpc_launch_count"]
+           "bmpc_getinfo", "bmpc_launch_info", "bmpc_launch_count",
+           "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
+           "bmhe_correct", "bmhe_update", "bmhe_launch_count"]
 
 
 def lib():
@@ -78,6 +85,17 @@ def lib():
     L.bmpc_launch_info.argtypes = [C.c_void_p, c_int32_p]
     L.bmpc_launch_count.argtypes = [C.c_void_p]
     L.bmpc_launch_count.restype = C.c_int64
+    L.bmhe_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(MheDims)]
+    L.bmhe_destroy.argtypes = [C.c_void_p]
+    L.bmhe_set_predmat.argtypes = [C.c_void_p] + [c_double_p] * 8
+    L.bmhe_set_cov.argtypes = [C.c_void_p] + [c_double_p] * 5 + [C.c_double]
+    L.bmhe_set_constraints.argtypes = [C.c_void_p] + [c_double_p] * 9
+    L.bmhe_reset.argtypes = [C.c_void_p]
+    L.bmhe_correct.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p,
+                               c_int32_p, c_double_p, c_double_p]
+    L.bmhe_update.argtypes = [C.c_void_p, c_double_p]
+    L.bmhe_launch_count.argtypes = [C.c_void_p]
+    L.bmhe_launch_count.restype = C.c_int64
     _lib = L
     return L
 

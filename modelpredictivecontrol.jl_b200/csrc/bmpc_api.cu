@@ -5,7 +5,7 @@
 //    coordinates,
 //  - launches the step kernel (bmpc_device.cuh).
 // No CPU fallback exists: without a CUDA device bmpc_create fails with BMPC_ERR_CUDA.
-#include "../../include/bmpc.h"
+#include "bmpc_host_util.h"
 
 #include <cuda_runtime.h>
 
@@ -25,58 +25,16 @@
 #include "bmpc_model.cuh"
 #include "bmpc_small_registry.h"
 
-namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
+namespace bmpc_host {
+std::string& last_error() {
+    thread_local std::string err;
+    return err;
 }
+}  // namespace bmpc_host
 
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(BMPC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                        __FILE__, __LINE__);                                                  \
-    } while (0)
-
-inline int even(int v) { return (v + 1) & ~1; }
-
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    cudaError_t alloc(size_t count) {
-        if (count <= n && p) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-        if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
-        cudaError_t e = alloc(count);
-        if (e != cudaSuccess || count == 0) return e;
-        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
-    }
-    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) { return upload(v.data(), v.size(), s); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-};
-
-}  // namespace
+using bmpc_host::DevBuf;
+using bmpc_host::even;
+using bmpc_host::fail;
 
 struct bmpc_handle {
     bmpc_dims d;
@@ -345,7 +303,7 @@ cudaError_t up(DevBuf<double>& buf, const double* src, size_t count, cudaStream_
 
 extern "C" {
 
-const char* bmpc_last_error(void) { return g_err.c_str(); }
+const char* bmpc_last_error(void) { return bmpc_host::last_error().c_str(); }
 int bmpc_version(void) { return 100; }
 
 int bmpc_create(bmpc_handle** out, const bmpc_dims* dims, const int32_t* nb) {

@@ -376,6 +376,129 @@ __device__ __forceinline__ double max_step(const Team<TEAM>& T, const Ctx& c, in
     return T.min(a);
 }
 
+// Mehrotra predictor-corrector on  min 1/2 x'Hx + q'x  s.t. Gx + s = h  (structured rows, see RowTables).
+// In: c.x = starting point, c.yb = Pd*x_v, c.s = h - Gx (raw slacks), c.q, c.h, c.Hv; out: c.x, status, iters.
+template <int TEAM>
+__device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, const StepParams& P, double Hee, double qs,
+                                          double hscale, int& status, int& iters) {
+    const RowTables& rt = P.rt;
+    const int n = P.n, m = rt.m, nDb = rt.nDb;
+    const double mu0 = fmax(1e-2 * qs * hscale / (double)m, 1e-8);
+    for (int r = T.tid; r < m; r += TEAM) {
+        const double sv = fmax(c.s[r], 1e-2 * hscale);
+        c.s[r] = sv;
+        c.lam[r] = mu0 / sv;
+    }
+    T.sync();
+    status = ST_ITERATION_LIMIT;
+    double rp_inf = 0.0, best_merit = 1e300;
+    for (int it = 0; it <= P.max_iter; ++it) {
+        // residuals
+        hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
+        T.sync();
+        for (int j = T.tid; j < n; j += TEAM) c.rhs[j] += c.q[j];
+        T.sync();
+        gt_apply(T, c, c.lam, 1.0, c.rhs, c.rd);  // rd = Hx + q + G' lam
+        double e_d = 0.0, e_p = 0.0, musum = 0.0, dsc = 0.0;
+        for (int j = T.tid; j < n; j += TEAM) {
+            e_d = fmax(e_d, fabs(c.rd[j]));
+            dsc = fmax(dsc, fmax(fabs(c.rhs[j]), fabs(c.rd[j] - c.rhs[j])));  // |Hx + q|, |G'lam|
+        }
+        for (int r = T.tid; r < m; r += TEAM) {
+            const double rpv = row_gx(c, r, c.x, c.yb) + c.s[r] - c.h[r];
+            c.rp[r] = rpv;
+            e_p = fmax(e_p, fabs(rpv));
+            musum = fma(c.s[r], c.lam[r], musum);
+        }
+        e_d = T.max(e_d);
+        e_p = T.max(e_p);
+        // the dual residual is a difference of terms that can be far larger than q (slack weight 2*Cwt,
+        // large multipliers): it is judged relative to the largest of them, as in OSQP's eps_rel test
+        const double qd = qs + T.max(dsc);
+        const double mu = T.sum(musum) / (double)m;
+        rp_inf = e_p;
+        if (!(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250) {
+            status = ST_INFEASIBLE;
+            break;
+        }
+        // merit = worst of the three scaled KKT residuals (1.0 = exactly at tolerance)
+        const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
+                                  mu * (double)m / (P.tol_mu * qs * hscale));
+        if (merit <= 1.0) {
+            status = ST_OPTIMAL;
+            break;
+        }
+        // fp64 floor: once inside the acceptable level (1e3 x tol, still far below the reference
+        // solver's eps = 1e-3) the first iteration that no longer improves the merit ends the solve:
+        // the normal equations lose accuracy as lam/s spreads over > 1e24 and the dual residual
+        // starts to grow again.
+        if (best_merit <= 1e3 && merit >= best_merit) {
+            status = ST_OPTIMAL;
+            break;
+        }
+        best_merit = fmin(best_merit, merit);
+        if (it == P.max_iter) {
+            if (merit <= 1e3) status = ST_OPTIMAL;
+            break;
+        }
+        iters = it + 1;
+        // Phi = H + G' D G, factor
+        for (int r = T.tid; r < m; r += TEAM) c.t[r] = c.lam[r] / c.s[r];
+        T.sync();
+        build_phi(T, c, Hee, c.t);
+        chol_packed(T, c.Phi, c.invd, n);
+        // predictor: rhs = -rd - G'(d*rp - lam)
+        for (int r = T.tid; r < m; r += TEAM) c.dl[r] = c.t[r] * c.rp[r] - c.lam[r];
+        T.sync();
+        gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
+        for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+        chol_solve(T, c.Phi, c.invd, c.dx, n);
+        dense_apply(T, c, c.dx, c.ybd);
+        T.sync();
+        for (int r = T.tid; r < m; r += TEAM) {
+            const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
+            c.ds[r] = dsv;
+            c.dl[r] = -c.lam[r] - c.t[r] * dsv;
+        }
+        T.sync();
+        const double a_aff = max_step(T, c, m);
+        double mua = 0.0;
+        for (int r = T.tid; r < m; r += TEAM)
+            mua = fma(c.s[r] + a_aff * c.ds[r], c.lam[r] + a_aff * c.dl[r], mua);
+        mua = T.sum(mua) / (double)m;
+        double sig = mua / mu;
+        sig = sig * sig * sig;
+        // corrector: rc = s*lam + ds*dl - sig*mu ; rhs = -rd - G'((lam*rp - rc)/s)
+        for (int r = T.tid; r < m; r += TEAM) {
+            const double rc = c.s[r] * c.lam[r] + c.ds[r] * c.dl[r] - sig * mu;
+            c.ds[r] = rc;  // keep rc
+            c.dl[r] = (c.lam[r] * c.rp[r] - rc) / c.s[r];
+        }
+        T.sync();
+        gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
+        for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+        chol_solve(T, c.Phi, c.invd, c.dx, n);
+        dense_apply(T, c, c.dx, c.ybd);
+        T.sync();
+        for (int r = T.tid; r < m; r += TEAM) {
+            const double rc = c.ds[r];
+            const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
+            c.ds[r] = dsv;
+            c.dl[r] = -(rc + c.lam[r] * dsv) / c.s[r];
+        }
+        T.sync();
+        const double a = fmin(1.0, 0.99 * max_step(T, c, m));
+        for (int j = T.tid; j < n; j += TEAM) c.x[j] = fma(a, c.dx[j], c.x[j]);
+        for (int k = T.tid; k < nDb; k += TEAM) c.yb[k] = fma(a, c.ybd[k], c.yb[k]);
+        for (int r = T.tid; r < m; r += TEAM) {
+            c.s[r] = fma(a, c.ds[r], c.s[r]);
+            c.lam[r] = fma(a, c.dl[r], c.lam[r]);
+        }
+        T.sync();
+    }
+    if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+}
+
 template <int TEAM>
 __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
     step_kernel(const __grid_constant__ StepParams P) {
@@ -616,114 +739,7 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
         const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
         if (!feasible) {
             // ---- stage 3: Mehrotra predictor-corrector ----
-            const double mu0 = fmax(1e-2 * qs * hscale / (double)m, 1e-8);
-            for (int r = T.tid; r < m; r += TEAM) {
-                const double sv = fmax(c.s[r], 1e-2 * hscale);
-                c.s[r] = sv;
-                c.lam[r] = mu0 / sv;
-            }
-            T.sync();
-            status = ST_ITERATION_LIMIT;
-            double rp_inf = 0.0, best_merit = 1e300;
-            for (int it = 0; it <= P.max_iter; ++it) {
-                // residuals
-                hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
-                T.sync();
-                for (int j = T.tid; j < n; j += TEAM) c.rhs[j] += c.q[j];
-                T.sync();
-                gt_apply(T, c, c.lam, 1.0, c.rhs, c.rd);  // rd = Hx + q + G' lam
-                double e_d = 0.0, e_p = 0.0, musum = 0.0;
-                for (int j = T.tid; j < n; j += TEAM) e_d = fmax(e_d, fabs(c.rd[j]));
-                for (int r = T.tid; r < m; r += TEAM) {
-                    const double rpv = row_gx(c, r, c.x, c.yb) + c.s[r] - c.h[r];
-                    c.rp[r] = rpv;
-                    e_p = fmax(e_p, fabs(rpv));
-                    musum = fma(c.s[r], c.lam[r], musum);
-                }
-                e_d = T.max(e_d);
-                e_p = T.max(e_p);
-                const double mu = T.sum(musum) / (double)m;
-                rp_inf = e_p;
-                if (!(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250) {
-                    status = ST_INFEASIBLE;
-                    break;
-                }
-                // merit = worst of the three scaled KKT residuals (1.0 = exactly at tolerance)
-                const double merit = fmax(fmax(e_d / (P.tol * qs), e_p / (P.tol * hscale)),
-                                          mu * (double)m / (P.tol_mu * qs * hscale));
-                if (merit <= 1.0) {
-                    status = ST_OPTIMAL;
-                    break;
-                }
-                // fp64 floor: once inside the acceptable level (1e3 x tol, still far below the reference
-                // solver's eps = 1e-3) the first iteration that no longer improves the merit ends the solve:
-                // the normal equations lose accuracy as lam/s spreads over > 1e24 and the dual residual
-                // starts to grow again.
-                if (best_merit <= 1e3 && merit >= best_merit) {
-                    status = ST_OPTIMAL;
-                    break;
-                }
-                best_merit = fmin(best_merit, merit);
-                if (it == P.max_iter) {
-                    if (merit <= 1e3) status = ST_OPTIMAL;
-                    break;
-                }
-                iters = it + 1;
-                // Phi = H + G' D G, factor
-                for (int r = T.tid; r < m; r += TEAM) c.t[r] = c.lam[r] / c.s[r];
-                T.sync();
-                build_phi(T, c, Hee, c.t);
-                chol_packed(T, c.Phi, c.invd, n);
-                // predictor: rhs = -rd - G'(d*rp - lam)
-                for (int r = T.tid; r < m; r += TEAM) c.dl[r] = c.t[r] * c.rp[r] - c.lam[r];
-                T.sync();
-                gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
-                for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
-                chol_solve(T, c.Phi, c.invd, c.dx, n);
-                dense_apply(T, c, c.dx, c.ybd);
-                T.sync();
-                for (int r = T.tid; r < m; r += TEAM) {
-                    const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
-                    c.ds[r] = dsv;
-                    c.dl[r] = -c.lam[r] - c.t[r] * dsv;
-                }
-                T.sync();
-                const double a_aff = max_step(T, c, m);
-                double mua = 0.0;
-                for (int r = T.tid; r < m; r += TEAM)
-                    mua = fma(c.s[r] + a_aff * c.ds[r], c.lam[r] + a_aff * c.dl[r], mua);
-                mua = T.sum(mua) / (double)m;
-                double sig = mua / mu;
-                sig = sig * sig * sig;
-                // corrector: rc = s*lam + ds*dl - sig*mu ; rhs = -rd - G'((lam*rp - rc)/s)
-                for (int r = T.tid; r < m; r += TEAM) {
-                    const double rc = c.s[r] * c.lam[r] + c.ds[r] * c.dl[r] - sig * mu;
-                    c.ds[r] = rc;  // keep rc
-                    c.dl[r] = (c.lam[r] * c.rp[r] - rc) / c.s[r];
-                }
-                T.sync();
-                gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
-                for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
-                chol_solve(T, c.Phi, c.invd, c.dx, n);
-                dense_apply(T, c, c.dx, c.ybd);
-                T.sync();
-                for (int r = T.tid; r < m; r += TEAM) {
-                    const double rc = c.ds[r];
-                    const double dsv = -c.rp[r] - row_gx(c, r, c.dx, c.ybd);
-                    c.ds[r] = dsv;
-                    c.dl[r] = -(rc + c.lam[r] * dsv) / c.s[r];
-                }
-                T.sync();
-                const double a = fmin(1.0, 0.99 * max_step(T, c, m));
-                for (int j = T.tid; j < n; j += TEAM) c.x[j] = fma(a, c.dx[j], c.x[j]);
-                for (int k = T.tid; k < nDb; k += TEAM) c.yb[k] = fma(a, c.ybd[k], c.yb[k]);
-                for (int r = T.tid; r < m; r += TEAM) {
-                    c.s[r] = fma(a, c.ds[r], c.s[r]);
-                    c.lam[r] = fma(a, c.dl[r], c.lam[r]);
-                }
-                T.sync();
-            }
-            if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+            ipm_solve(T, c, P, Hee, qs, hscale, status, iters);
         }
         // ---- stage 4: getinput! ----
         double* gZ = P.Z + (long)inst * n;

@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(64, 7)
                     musum = fma(sSp[t], lamS[t], musum);
                 }
                 const double e_d = half_max(fabs(rd));
+                const double qd = qs + half_max(fmax(fabs(Hx + q), fabs(Gtl)));  // scale of the dual residual's terms
                 e_p = half_max(e_p);
                 const double mu = half_sum(musum) * minv;
                 if (active) {
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(64, 7)
                         status = ST_INFEASIBLE;
                         active = false;
                     } else {
-                        const double merit = fmax(fmax(e_d / (P.tol * qs), e_p / (P.tol * hscale)),
+                        const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
                                                   mu * (double)m / (P.tol_mu * qs * hscale));
                         if (merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) ||
                             (it == P.max_iter && merit <= 1e3)) {

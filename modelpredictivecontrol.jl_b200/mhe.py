@@ -1,0 +1,156 @@
+"""``MovingHorizonEstimator``: host-side mirror of the reference's linear MHE for a BATCH of estimators
+(src/estimator/mhe/construct.jl:528-630, ``setconstraint!`` :858-1046, ``preparestate!/updatestate!``
+src/estimator/execute.jl:334-386).  LinModel + SingleShooting, ``direct=true`` (the reference default).
+The per-period work (windows, arrival covariance, Hessian rebuild, QP) runs in libbmpc.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, colmajor, dptr
+from .host import _b, augment_model
+
+
+def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He):
+    """Batched init_predmat_mhe for p = 0 (direct = true), src/estimator/mhe/transcription.jl:151-260.
+    Block (i, j) formulas (i = 0-based step, j = block column; column 0 = arrival state):
+      E[i, arr] = -Cm A^(i+1),  E[i, w_j] = -Cm A^(i-j),  G[i, u_j] = -Cm A^(i-j) Bu   (j <= i),
+      J[i, d_j] = -Cm A^(i-j) Bd (j <= i),  J[i, d_(i+1)] = -Ddm,  B[i] = -Cm S(i) f,
+      EX[i, arr] = A^(i+1),  EX[i, w_j] = A^(i-j),  GX[i, u_j] = A^(i-j) Bu,  JX[i, d_j] = A^(i-j) Bd,  BX[i] = S(i) f."""
+    N, nx = A.shape[0], A.shape[1]
+    nu, nym, nd = Bu.shape[2], Cm.shape[1], Bd.shape[2]
+    Ap = [np.broadcast_to(np.eye(nx), (N, nx, nx)).copy()]
+    for _ in range(He):
+        Ap.append(Ap[-1] @ A)
+    S = np.cumsum(np.array(Ap), axis=0)
+    nZ = nx * (1 + He)
+    E, EX = np.zeros((N, nym * He, nZ)), np.zeros((N, nx * He, nZ))
+    G, GX = np.zeros((N, nym * He, nu * He)), np.zeros((N, nx * He, nu * He))
+    J, JX = np.zeros((N, nym * He, nd * (He + 1))), np.zeros((N, nx * He, nd * (He + 1)))
+    B, BX = np.zeros((N, nym * He)), np.zeros((N, nx * He))
+    for i in range(He):
+        ry, rx = slice(i * nym, (i + 1) * nym), slice(i * nx, (i + 1) * nx)
+        E[:, ry, :nx] = -Cm @ Ap[i + 1]
+        EX[:, rx, :nx] = Ap[i + 1]
+        B[:, ry] = -np.einsum("nij,nj->ni", Cm @ S[i], f)
+        BX[:, rx] = np.einsum("nij,nj->ni", S[i], f)
+        if nd:
+            J[:, ry, (i + 1) * nd:(i + 2) * nd] = -Ddm
+        for j in range(i + 1):
+            E[:, ry, nx + j * nx:nx + (j + 1) * nx] = -Cm @ Ap[i - j]
+            EX[:, rx, nx + j * nx:nx + (j + 1) * nx] = Ap[i - j]
+            G[:, ry, j * nu:(j + 1) * nu] = -Cm @ Ap[i - j] @ Bu
+            GX[:, rx, j * nu:(j + 1) * nu] = Ap[i - j] @ Bu
+            if nd:
+                J[:, ry, j * nd:(j + 1) * nd] = -Cm @ Ap[i - j] @ Bd
+                JX[:, rx, j * nd:(j + 1) * nd] = Ap[i - j] @ Bd
+    return E, G, J, B, EX, GX, JX, BX
+
+
+class MovingHorizonEstimator:
+    direct = True
+
+    def __init__(self, model, He, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None, nint_u=0, nint_ym=None,
+                 sigmaPint_ym_0=None, sigmaQint_ym=None, Cwt=np.inf, shared_model=False, device=0, max_iter=0,
+                 tol=0.0):
+        self.model, self.He = model, int(He)
+        self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
+        N, nx, nxh = model.N, model.nx, self.nxhat
+        self.nym = len(self.i_ym)
+        nsy = self.nxs
+        one = lambda v, n, d: np.full(n, d) if v is None else np.asarray(v, float).reshape(n)
+        sP = np.concatenate([one(sigmaP_0, nx, 1 / nx), one(sigmaPint_ym_0, nsy, 1.0)])
+        sQ = np.concatenate([one(sigmaQ, nx, 1 / nx), one(sigmaQint_ym, nsy, 1.0)])
+        sR = one(sigmaR, self.nym, 1.0)
+        self.P0hat, self.Qhat, self.Rhat = np.diag(sP ** 2), np.diag(sQ ** 2), np.diag(sR ** 2)
+        self.Cwt = float(Cwt)
+        self.neps = 0 if np.isinf(self.Cwt) else 1
+        self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]
+        self.shared_model = bool(shared_model)
+        NM = 1 if shared_model else N
+        sl = slice(0, NM)
+        E, G, J, B, EX, GX, JX, BX = init_predmat_mhe(self.Ahat[sl], self.Buhat[sl], self.Cmhat[sl], self.Bdhat[sl],
+                                                      self.Ddmhat[sl], (self.fophat - self.xophat)[sl], self.He)
+        self._h = C.c_void_p()
+        dims = _lib.MheDims(N=N, nu=model.nu, nym=self.nym, nd=model.nd, nxhat=nxh, He=self.He, neps=self.neps,
+                            direct=1, shared_model=int(shared_model), max_iter=max_iter, device=device, tol=tol)
+        L = _lib.lib()
+        check(L.bmhe_create(C.byref(self._h), C.byref(dims)))
+        nd = model.nd
+        args = [colmajor(E), colmajor(G), colmajor(J) if nd else None, np.ascontiguousarray(B), colmajor(EX),
+                colmajor(GX), colmajor(JX) if nd else None, np.ascontiguousarray(BX)]
+        check(L.bmhe_set_predmat(self._h, *[dptr(a) for a in args]))
+        rep = lambda M: np.ascontiguousarray(np.broadcast_to(M, (NM,) + M.shape))
+        covs = [colmajor(self.Ahat[sl]), colmajor(self.Cmhat[sl]), rep(self.P0hat), rep(self.Qhat), rep(self.Rhat)]
+        check(L.bmhe_set_cov(self._h, *[dptr(a) for a in covs], C.c_double(0.0 if np.isinf(self.Cwt) else self.Cwt)))
+        inf = np.inf
+        self.con = dict(xmin=np.full((N, nxh), -inf), xmax=np.full((N, nxh), inf), wmin=np.full((N, nxh), -inf),
+                        wmax=np.full((N, nxh), inf), vmin=np.full((N, self.nym), -inf), vmax=np.full((N, self.nym), inf))
+        self.soft = dict(c_x=np.zeros(2 * nxh), c_w=np.zeros(2 * nxh), c_v=np.zeros(2 * self.nym))
+        self.xhat0 = np.zeros((N, nxh))
+        self.Ztilde = np.zeros((N, self.neps + nxh * (1 + self.He)))
+        self.J = np.zeros(N)
+        self.status = np.zeros(N, dtype=np.int32)
+        self.iters = np.zeros(N, dtype=np.int32)
+        self.Vhat = np.zeros((N, self.nym * self.He))
+        self.X0 = np.zeros((N, nxh * self.He))
+        self._solved = False
+
+    def close(self):
+        if self._h:
+            _lib.lib().bmhe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setconstraint(self, xhatmin=None, xhatmax=None, whatmin=None, whatmax=None, vhatmin=None, vhatmax=None,
+                      c_xhatmin=None, c_xhatmax=None, c_whatmin=None, c_whatmax=None, c_vhatmin=None, c_vhatmax=None):
+        N, nxh, nym = self.model.N, self.nxhat, self.nym
+        c = self.con
+        if xhatmin is not None: c["xmin"] = _b(xhatmin, N, (nxh,)) - self.xophat
+        if xhatmax is not None: c["xmax"] = _b(xhatmax, N, (nxh,)) - self.xophat
+        if whatmin is not None: c["wmin"] = _b(whatmin, N, (nxh,)).copy()
+        if whatmax is not None: c["wmax"] = _b(whatmax, N, (nxh,)).copy()
+        if vhatmin is not None: c["vmin"] = _b(vhatmin, N, (nym,)).copy()
+        if vhatmax is not None: c["vmax"] = _b(vhatmax, N, (nym,)).copy()
+        ecr = [c_xhatmin, c_xhatmax, c_whatmin, c_whatmax, c_vhatmin, c_vhatmax]
+        if any(e is not None for e in ecr):
+            if not self.neps:
+                raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
+            if self._solved:
+                raise RuntimeError("Cannot set softness parameters after calling updatestate!")
+            s = self.soft
+            if c_xhatmin is not None: s["c_x"][:nxh] = c_xhatmin
+            if c_xhatmax is not None: s["c_x"][nxh:] = c_xhatmax
+            if c_whatmin is not None: s["c_w"][:nxh] = c_whatmin
+            if c_whatmax is not None: s["c_w"][nxh:] = c_whatmax
+            if c_vhatmin is not None: s["c_v"][:nym] = c_vhatmin
+            if c_vhatmax is not None: s["c_v"][nym:] = c_vhatmax
+        a = [np.ascontiguousarray(c[k]) for k in ("xmin", "xmax", "wmin", "wmax", "vmin", "vmax")]
+        sv = [np.ascontiguousarray(self.soft[k]) for k in ("c_x", "c_w", "c_v")]
+        check(_lib.lib().bmhe_set_constraints(self._h, *[dptr(x) for x in a], *[dptr(x) for x in sv]))
+        return self
+
+    def preparestate(self, ym, d=None):
+        m, N = self.model, self.model.N
+        y0m = np.ascontiguousarray(_b(ym, N, (self.nym,)) - m.yop[:, self.i_ym])
+        d0 = np.ascontiguousarray(_b(d, N, (m.nd,)) - m.dop) if m.nd else None
+        p32 = lambda a: a.ctypes.data_as(_lib.c_int32_p)
+        check(_lib.lib().bmhe_correct(self._h, dptr(y0m), dptr(d0) if d0 is not None else None, dptr(self.xhat0),
+                                      dptr(self.Ztilde), dptr(self.J), p32(self.status), p32(self.iters),
+                                      dptr(self.Vhat), dptr(self.X0)))
+        self._solved = True
+        return self.xhat0 + self.xophat
+
+    def updatestate(self, u, ym=None, d=None):
+        u0 = np.ascontiguousarray(_b(u, self.model.N, (self.model.nu,)) - self.model.uop)
+        check(_lib.lib().bmhe_update(self._h, dptr(u0)))
+        return self.xhat0 + self.xophat
+
+    def reset(self):
+        check(_lib.lib().bmhe_reset(self._h))
+        self.xhat0[:] = 0

@@ -16,13 +16,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "bmpc.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(bmpc_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(bm(?:pc|he)_[a-z_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported():
     L = _lib.lib()
     syms = declared_symbols()
-    assert len(syms) >= 14
+    assert len(syms) >= 23
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/bmpc.h but not exported by libbmpc.so"
     assert sorted(_lib.SYMBOLS) == syms
@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.StepIO) == 12 * 8 + 8
     assert C.sizeof(_lib.Info) == 6 * 8
     assert C.sizeof(_lib.Softness) == 8 * 8
+    assert C.sizeof(_lib.MheDims) == 12 * 4 + 8
 
 
 def test_no_cpu_fallback():

@@ -138,7 +138,8 @@ def ipm_device_model(H, q, G, h, max_iter=60, tol=1e-9, neps=1, verbose=False, t
         mu = s @ lam / m
         if verbose:
             print(it, np.abs(rd).max(), np.abs(rp).max(), mu)
-        if np.abs(rd).max() <= tol * qs and np.abs(rp).max() <= tol * hscale and mu * m <= tol_mu * qs * hscale:
+        qd = qs + max(np.abs(H @ x + q).max(), np.abs(G.T @ lam).max())
+        if np.abs(rd).max() <= tol * qd and np.abs(rp).max() <= tol * hscale and mu * m <= tol_mu * qs * hscale:
             status = 0
             it -= 1
             break
