@@ -68,7 +68,9 @@ struct bmpc_handle {
     bool dirty = true;      // launch geometry / derived arrays must be rebuilt before the next step
     const bmpc::SmallEntry* small = nullptr;  // chosen small-kernel specialisation, or null (general kernel)
     bmpc::SmallParams sp{};
-    DevBuf<double> PdR, HvS, LvS;
+    DevBuf<double> PdR, HvS, LvS, lam_ws;
+    DevBuf<int> ws_flag;
+    int warm_start = 1;
     bmpc::SmemLayout sm{};
     int64_t launches = 0;
 };
@@ -235,6 +237,10 @@ int configure_small(bmpc_handle* h, const bmpc::SmallEntry& E) {
                                                           h->HvS.p, h->LvS.p, (long)L.nHS, nz, nzt, ldp);
     h->launches++;
     CK(cudaGetLastError());
+    CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(h->rt.m, 1))));
+    CK(h->ws_flag.alloc((size_t)h->d.N));
+    CK(cudaMemsetAsync(h->ws_flag.p, 0, (size_t)h->d.N * sizeof(int), h->stream));
+    if (const char* e = getenv("BMPC_WARM")) h->warm_start = atoi(e);
     h->sp.PdR = h->PdR.p;
     h->sp.HvS = h->HvS.p;
     h->sp.LvS = h->LvS.p;
@@ -811,6 +817,8 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.F_out = h->F.p; P.qt_out = h->qt.p; P.r_out = h->r.p; P.lastu_prev = h->lastu_prev.p;
     P.counters = h->counters.p;
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
+    P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
+    P.use_ws = (h->small && h->warm_start && h->lam_ws.p) ? 1 : 0;
     cudaError_t le;
     if (h->small) {
         le = h->small->launch(P, h->sp, h->grid, h->smem_bytes, h->stream);

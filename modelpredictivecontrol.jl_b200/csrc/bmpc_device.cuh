@@ -63,6 +63,9 @@ struct StepParams {
     double *lastu0, *Z, *u, *J_out, *F_out, *qt_out, *r_out, *lastu_prev;
     int *status, *iters;
     unsigned int* counters;  // [2] work counter, finished-CTA counter
+    double* lam_ws;          // [N x ws_stride] multipliers of the previous period (IPM warm start), small kernel
+    int* ws_flag;            // [N] 1 if lam_ws holds a converged IPM solution of the previous period
+    int ws_stride, use_ws;
     int nHp2, nPd2;          // padded (even) sizes in doubles of packed Hv and of Pd: TMA needs 16-byte multiples
 };
 

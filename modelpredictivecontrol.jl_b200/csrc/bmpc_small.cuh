@@ -411,6 +411,47 @@ __global__ void __launch_bounds__(64, 7)
                 sSp[t] = fmax(sSp[t], 1e-2 * hscale);
                 lamS[t] = (l16 + 16 * t < nsr) ? mu0 / sSp[t] : 0.0;
             }
+            // ---- warm start (set_warmstart_mpc! analogue): previous period's Z̃ and multipliers ----
+            const bool warm = P.use_ws && active && P.ws_flag[inst] != 0;
+            if (__any_sync(FULL, warm)) {
+                double xw = x;
+                if (warm) {
+                    const double* gZp = P.Z + (long)inst * nr;
+                    double a = 0.0;
+                    if (isreal)
+                        for (int l = l16 % nu; l <= l16; l += nu) a += gZp[l];
+                    xw = isreal ? a : ((iseps && NEPS) ? gZp[nzr] : 0.0);
+                }
+                __syncwarp();
+                vbuf[l16] = xw;
+                __syncwarp();
+                double ybw[DS], gsw[SS];
+                row_products(ybw, gsw);
+                const double epsw = NEPS ? bcast(xw, NZT) : 0.0;
+                if (warm) {
+                    const double* glw = P.lam_ws + (long)inst * P.ws_stride;
+                    const double lmin = 1e-4 * qs / hscale;
+                    x = xw;
+                    eps = epsw;
+#pragma unroll
+                    for (int t = 0; t < DS; ++t) {
+                        const int k = l16 + 16 * t;
+                        yb[t] = ybw[t];
+                        sD[t] = fmax(hD[t] - (sigD[t] * ybw[t] - cD[t] * epsw), 1e-2 * hscale);
+                        lamD[t] = (k < nDb) ? fmax(glw[k], lmin) : 0.0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < SS; ++t) {
+                        const int r = l16 + 16 * t;
+                        gs[t] = gsw[t];
+                        sSp[t] = fmax(hS[t] - gSf(t, gsw[t], epsw), 1e-2 * hscale);
+                        lamS[t] = (r < nsr) ? fmax(glw[nDb + r], lmin) : 0.0;
+                    }
+                }
+                __syncwarp();
+                vbuf[l16] = x;
+                __syncwarp();
+            }
             if (active) status = ST_ITERATION_LIMIT;
             double best_merit = 1e300, rp_inf = 0.0;
             // primal residual r_p = Gx + s - h.  Because ds = -r_p - G dx is formed from the COMPUTED dx, the
@@ -692,6 +733,20 @@ __global__ void __launch_bounds__(64, 7)
                 P.lastu_prev[(long)inst * nu + l16] = lu;
                 P.lastu0[(long)inst * nu + l16] = lu + du;
                 P.u[(long)inst * nu + l16] = lu + du + guop[l16];
+            }
+            if (P.use_ws) {
+                // multipliers for the next period's warm start (valid only after a converged IPM solve)
+                const bool keep = status == ST_OPTIMAL && iters > 0;
+                double* glw = P.lam_ws + (long)inst * P.ws_stride;
+                if (keep) {
+#pragma unroll
+                    for (int t = 0; t < DS; ++t)
+                        if (l16 + 16 * t < nDb) glw[l16 + 16 * t] = lamD[t];
+#pragma unroll
+                    for (int t = 0; t < SS; ++t)
+                        if (l16 + 16 * t < nsr) glw[nDb + l16 + 16 * t] = lamS[t];
+                }
+                if (l16 == 0) P.ws_flag[inst] = keep ? 1 : 0;
             }
             if (l16 == 0) {
                 P.r_out[inst] = rconst;
