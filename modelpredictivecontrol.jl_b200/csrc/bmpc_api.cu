@@ -24,6 +24,7 @@
 #include "bmpc_setup.cuh"
 #include "bmpc_model.cuh"
 #include "bmpc_small_registry.h"
+#include "bmpc_warp_registry.h"
 
 namespace bmpc_host {
 std::string& last_error() {
@@ -70,6 +71,14 @@ struct bmpc_handle {
     bmpc::SmallParams sp{};
     DevBuf<double> PdR, HvS, LvS, lam_ws;
     DevBuf<int> ws_flag;
+    // warp-per-controller kernel (bmpc_warp.cuh)
+    const bmpc::WarpEntry* warp = nullptr;
+    bmpc::WarpParams wp{};
+    DevBuf<double> Gw, HLw;
+    DevBuf<int> order[2];
+    DevBuf<unsigned int> ocnt;
+    int order_cur = 0;       // order[order_cur] drives the next launch
+    bool order_valid = false;
     int warm_start = 1;
     bmpc::SmemLayout sm{};
     int64_t launches = 0;
@@ -247,11 +256,109 @@ int configure_small(bmpc_handle* h, const bmpc::SmallEntry& E) {
     return BMPC_OK;
 }
 
+const std::vector<bmpc::WarpEntry>& warp_registry() {
+    static std::vector<bmpc::WarpEntry> reg = [] {
+        std::vector<bmpc::WarpEntry> v;
+        bmpc::warp_register_03(v);
+        bmpc::warp_register_05(v);
+        bmpc::warp_register_07(v);
+        bmpc::warp_register_09(v);
+        bmpc::warp_register_11(v);
+        bmpc::warp_register_13(v);
+        bmpc::warp_register_16(v);
+        return v;
+    }();
+    return reg;
+}
+
+// warp-per-controller kernel: all rows dense, one TMA copy per instance, DMMA Hessian build
+int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
+    const int NT = E.nt, MP = 32 * E.rpl, nY = h->nY, nx = h->d.nxhat;
+    const int m = h->rt.nS + h->rt.nDr;  // without the (redundant) eps >= 0 row
+    bmpc::WarpLayout& L = h->wp.L;
+    int o = 0;
+    auto take = [&](int cnt) { int at = o; o += even(std::max(cnt, 1)); return at; };
+    L.G = take(MP * E.ldg);
+    L.H = take(NT * E.ldh);
+    L.L = take(NT * E.ldh);
+    L.phi = take(std::max(8 * ((NT + 7) / 8) * E.ldp, NT * E.ldn));
+    L.vx = take(16);
+    L.w1 = take(MP);
+    L.w2 = take(MP);
+    L.wd = take(MP);
+    L.F = take(nY);
+    L.tY = take(nY);
+    L.fx = take(nx);
+    L.xh = take(nx);
+    L.lu = take(h->d.nu);
+    L.dd = take(h->d.nd);
+    L.Dh = take(h->d.nd * h->d.Hp);
+    L.bar = take(2);
+    L.total = o;
+    if (L.H + NT * E.ldh != L.L) return BMPC_ERR_UNSUPPORTED;  // H and its factor are one TMA copy
+    h->smem_bytes = L.total * 8;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
+    if (h->smem_bytes > max_optin) return BMPC_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(E.func, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, E.func, 32, h->smem_bytes));
+    if (occ < 1) return BMPC_ERR_UNSUPPORTED;
+    h->team = 32;
+    h->teams_per_cta = 1;
+    h->grid = std::max(1, std::min(h->d.N, occ * h->num_sms));
+    h->warp = &E;
+    h->pd_in_smem = true;
+    const long NM = h->NM;
+    const long sG = (long)MP * E.ldg, sHL = 2L * NT * E.ldh;
+    CK(h->Gw.alloc((size_t)NM * sG));
+    CK(h->HLw.alloc((size_t)NM * sHL));
+    const double* pdsrc = h->pd_is_ev ? h->Ev.p : h->Pd.p;
+    const long spd = h->pd_is_ev ? h->nEv2 : h->nPd2;
+    bmpc::k_make_warp<<<(unsigned)NM, 128, 0, h->stream>>>(pdsrc, spd, h->rt.nDb, h->Hv.p, h->Lv.p, h->nHp2, h->Hee.p, h->rt, m,
+                                                         h->nz, h->d.neps, NT, E.ldg, E.ldh, MP, h->Gw.p, sG, h->HLw.p, sHL);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(h->rt.m, 1))));
+    CK(h->ws_flag.alloc((size_t)h->d.N));
+    CK(cudaMemsetAsync(h->ws_flag.p, 0, (size_t)h->d.N * sizeof(int), h->stream));
+    CK(h->order[0].alloc((size_t)h->d.N));
+    CK(h->order[1].alloc((size_t)h->d.N));
+    CK(h->ocnt.alloc(2));
+    CK(cudaMemsetAsync(h->ocnt.p, 0, 2 * sizeof(unsigned int), h->stream));
+    h->order_valid = false;
+    if (const char* e = getenv("BMPC_WARM")) h->warm_start = atoi(e);
+    h->wp.Gw = h->Gw.p;
+    h->wp.sGw = h->d.shared_model ? 0 : sG;
+    h->wp.HL = h->HLw.p;
+    h->wp.sHL = h->d.shared_model ? 0 : sHL;
+    h->wp.m = m;
+    h->wp.long_thresh = 9;
+    if (const char* e = getenv("BMPC_LONG")) h->wp.long_thresh = atoi(e);
+    return BMPC_OK;
+}
+
 int configure_launch(bmpc_handle* h) {
     h->small = nullptr;
+    h->warp = nullptr;
     const int forced = h->d.team ? h->d.team : (getenv("BMPC_TEAM") ? atoi(getenv("BMPC_TEAM")) : 0);
     const int nsr = h->rt.nS + h->d.neps;
     const bool one_sided = h->rt.nDr == h->rt.nDb;
+    const int m_rows = h->rt.nS + h->rt.nDr;
+    if (forced == 0 && h->n <= 16 && m_rows <= 128 && !h->M_dense && h->have_predmat &&
+        !(getenv("BMPC_NO_WARP") && atoi(getenv("BMPC_NO_WARP")))) {
+        const bmpc::WarpEntry* best = nullptr;
+        for (const bmpc::WarpEntry& E : warp_registry()) {
+            if (E.nt < h->n || 32 * E.rpl < m_rows) continue;
+            if (!best || E.nt < best->nt || (E.nt == best->nt && E.rpl < best->rpl)) best = &E;
+        }
+        if (best) {
+            int rc = configure_warp(h, *best);
+            if (rc == BMPC_OK) return rc;
+            if (rc != BMPC_ERR_UNSUPPORTED) return rc;
+            h->warp = nullptr;
+        }
+    }
     if (forced == 0 && h->n <= 16 && one_sided && !h->M_dense && h->have_predmat) {
         // smallest specialisation that holds the controller (padding with dummy variables is exact)
         const bmpc::SmallEntry* best = nullptr;
@@ -818,9 +925,17 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.counters = h->counters.p;
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
-    P.use_ws = (h->small && h->warm_start && h->lam_ws.p) ? 1 : 0;
+    P.use_ws = ((h->small || h->warp) && h->warm_start && h->lam_ws.p) ? 1 : 0;
     cudaError_t le;
-    if (h->small) {
+    if (h->warp) {
+        bmpc::WarpParams Q = h->wp;
+        Q.order = h->order_valid ? h->order[h->order_cur].p : nullptr;
+        Q.order_next = h->order[h->order_cur ^ 1].p;
+        Q.ocnt = h->ocnt.p;
+        le = h->warp->launch(P, Q, h->grid, h->smem_bytes, h->stream);
+        h->order_cur ^= 1;
+        h->order_valid = true;
+    } else if (h->small) {
         le = h->small->launch(P, h->sp, h->grid, h->smem_bytes, h->stream);
     } else
     switch (h->team) {
@@ -885,7 +1000,8 @@ int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
     out[1] = h->teams_per_cta;
     out[2] = h->grid;
     out[3] = h->smem_bytes;
-    out[4] = h->small ? 100 + h->small->nzt : (int)h->pd_in_smem;  // >= 100: small kernel, NZT = value - 100
+    // >= 200: warp-per-controller kernel, NT = value - 200; >= 100: 16-lane small kernel, NZT = value - 100
+    out[4] = h->warp ? 200 + h->warp->nt : (h->small ? 100 + h->small->nzt : (int)h->pd_in_smem);
     out[5] = h->rt.m;
     out[6] = h->rt.nS;
     out[7] = h->rt.nDr;

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "bmpc_device.cuh"
+
 namespace bmpc {
 
 // out[:, j] = in[:, j] - in[:, j+nu]   (X_v = X * D,  DU_l = v_l - v_{l-1});  column-major [rows x nz]
@@ -156,6 +158,54 @@ __global__ void k_make_small(const double* __restrict__ Pd, long sPd, int nDb, c
         }
         HvS[inst * sHS + (long)i * ldp + j] = h;
         LvS[inst * sHS + (long)i * ldp + j] = l;
+    }
+}
+
+// Setup: dense row matrix Gt and extended Hessian / factor for the warp kernel (one CTA per instance).
+//   Gt[r, :] = [sigma_r * p_r, -c_r]:  sparse rows p_r = e_i1 - e_i2, dense rows p_r = Pd[base_r, :]
+//   H_ext = blockdiag(Hv, Hee, I_dummy);  L_ext = its Cholesky factor with 1/L_ii on the diagonal
+__global__ void k_make_warp(const double* __restrict__ Pd, long sPd, int nDb, const double* __restrict__ Hv,
+                            const double* __restrict__ Lv, int nHp2, const double* __restrict__ Hee, RowTables rt, int m,
+                            int nz, int neps, int NT, int LDG, int LDH, int MP, double* __restrict__ Gw, long sGw,
+                            double* __restrict__ HL, long sHL) {
+    const long inst = blockIdx.x;
+    double* G = Gw + inst * sGw;
+    for (int e = threadIdx.x; e < MP * LDG; e += blockDim.x) {
+        const int r = e / LDG, j = e % LDG;
+        double v = 0.0;
+        if (r < m) {
+            const double sg = rt.row_sig[r], c = rt.row_c[r];
+            if (j < nz) {
+                if (r < rt.nS)
+                    v = (j == rt.s_i1[r]) ? sg : ((j == rt.s_i2[r]) ? -sg : 0.0);
+                else
+                    v = sg * Pd[inst * sPd + rt.dr_base[r - rt.nS] + (long)nDb * j];
+            } else if (neps && j == nz) {
+                v = -c;
+            }
+        }
+        G[e] = v;
+    }
+    double* H = HL + inst * sHL;
+    double* L = H + NT * LDH;
+    const int n = nz + neps;
+    for (int e = threadIdx.x; e < NT * LDH; e += blockDim.x) {
+        const int i = e / LDH, j = e % LDH;
+        double h = 0.0, l = 0.0;
+        if (j < NT) {
+            if (i < nz && j < nz) {
+                const int hi = i > j ? i : j, lo = i > j ? j : i;
+                h = Hv[inst * nHp2 + hi * (hi + 1) / 2 + lo];
+                if (j < i) l = Lv[inst * nHp2 + i * (i + 1) / 2 + j];
+                if (j == i) l = 1.0 / Lv[inst * nHp2 + i * (i + 1) / 2 + i];
+            } else if (i == j) {
+                const double hee = (i < n) ? Hee[inst] : 1.0;
+                h = hee;
+                l = hee > 0.0 ? rsqrt(hee) : 1.0;
+            }
+        }
+        H[e] = h;
+        L[e] = l;
     }
 }
 

@@ -1,0 +1,693 @@
+// Warp-per-controller step kernel for SMALL problems (n = nu*Hc + neps <= 16, m <= 128 rows): the
+// shape of BASELINE.json's headline config (C1: n = 11, 60 rows).
+//
+// One warp owns one controller instance for the whole moveinput!:
+//   * ALL inequality rows are kept as one dense matrix Gt = [sigma*p_r, -c_r] (m x n, row-major, zero
+//     padded), loaded per instance by ONE TMA bulk copy (cp.async.bulk + mbarrier) together with the
+//     Hessian and its cached Cholesky factor;
+//   * lane l owns rows l, l+32, ... (s, lambda, h, r_p in registers) and, for l < n, decision variable l
+//     (row l of Phi = H + Gt' D Gt and then of its Cholesky factor in registers);
+//   * Phi is formed on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) tiles A = Gt' (8 variables x 4
+//     rows), B = D*Gt, accumulators initialised with H; only the lower block-triangle is computed;
+//   * Cholesky and both triangular solves run on registers + warp shuffles; G'w products read Gt
+//     columns from shared memory with the row range split between the two half-warps;
+//   * the redundant  eps >= 0  row of the reference QP is NOT part of Gt: every softness weight is
+//     non-negative (construct.jl:456-506), so any point with eps < 0 is dominated by the same point with
+//     eps = 0 and the optimum is unchanged -- while the row's vanishing multiplier (no strict
+//     complementarity whenever no soft constraint is active) is what slows interior-point convergence.
+// Algorithm, tolerances, status policy and outputs are those of the general kernel (bmpc_device.cuh),
+// with two refinements: the step-to-boundary fraction tends to 1 as the affine step closes the gap
+// (tau = max(0.99, 1 - mu_aff/mu)), and work is handed out longest-expected-first (the previous period's
+// slow instances start first) so that the few 20-iteration solves do not start late in a launch.
+#pragma once
+#include "bmpc_device.cuh"
+
+namespace bmpc {
+
+struct WarpLayout {  // per-warp shared-memory offsets (doubles)
+    int G, H, L, phi, vx, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, total;
+};
+
+struct WarpParams {
+    WarpLayout L;
+    const double* Gw;  // [MP x LDG] per instance: all rows, zero padded
+    long sGw;
+    const double* HL;  // [2 x NT x LDH] per instance: extended Hessian, then its factor (1/L_ii on the diagonal)
+    long sHL;
+    const int* order;   // processing order of this launch (nullptr: 0..N-1)
+    int* order_next;    // written by this launch: slow instances first
+    unsigned int* ocnt; // [2] fill counters of order_next (front, back)
+    int long_thresh;    // iterations from which an instance counts as slow
+    int m;              // inequality rows (without the eps >= 0 row)
+};
+
+template <int NT>
+struct WarpDims {
+    static constexpr int NB = (NT + 7) / 8;            // 8-wide variable blocks (DMMA tiles)
+    static constexpr int LDG = NT <= 12 ? 12 : 20;     // == 4 (mod 8): conflict-free DMMA fragment loads
+    static constexpr int LDH = (NT + 1) & ~1;
+    static constexpr int LDN = NT | 1;
+    static constexpr int LDP = 8 * NB + 2;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr unsigned WFULL = 0xffffffffu;
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(WFULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(WFULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(WFULL, v, o));
+    return v;
+}
+// three maxima and one sum in ONE butterfly (the shuffles of the four values overlap)
+__device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, double& s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(WFULL, a, o), tb = __shfl_xor_sync(WFULL, b, o);
+        const double tc = __shfl_xor_sync(WFULL, c, o), ts = __shfl_xor_sync(WFULL, s, o);
+        a = fmax(a, ta);
+        b = fmax(b, tb);
+        c = fmax(c, tc);
+        s += ts;
+    }
+}
+
+template <int NT, int RPL>
+__global__ void __launch_bounds__(32, 16)
+    step_warp(const __grid_constant__ StepParams P, const __grid_constant__ WarpParams Q) {
+    using D = WarpDims<NT>;
+    constexpr int NB = D::NB, LDG = D::LDG, LDH = D::LDH, LDN = D::LDN, LDP = D::LDP;
+    constexpr int MP = 32 * RPL, NV2 = LDH / 2;
+    extern __shared__ __align__(128) double smem[];
+    const WarpLayout& L = Q.L;
+    const RowTables& rt = P.rt;
+    const int lane = threadIdx.x;
+    const int fg = lane >> 2, ft = lane & 3;  // DMMA fragment coordinates
+    const int half = lane >> 4, i16 = lane & 15;
+    const int nz = P.nz, nr = P.n;  // real sizes: move variables, move variables + slack
+    const int nY = P.nY, nu = P.nu, ny = P.ny, nx = P.nx, nd = P.nd;
+    const int nS = rt.nS, nDr = rt.nDr, m = Q.m;
+    double* sG = smem + L.G;
+    double* sH = smem + L.H;
+    double* sL = smem + L.L;
+    double* sPhi = smem + L.phi;  // C tiles of Phi, then the rows of its factor (stride LDN)
+    double* vx = smem + L.vx;
+    double* w1 = smem + L.w1;
+    double* w2 = smem + L.w2;
+    double* wd = smem + L.wd;
+    double* sF = smem + L.F;
+    double* stY = smem + L.tY;
+    double* sfx = smem + L.fx;
+    double* sxh = smem + L.xh;
+    double* slu = smem + L.lu;
+    double* sd0 = smem + L.dd;
+    double* sDh = smem + L.Dh;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane < 16) vx[lane] = 0.0;
+    __syncwarp();
+    uint32_t phase = 0;
+    const bool isvar = lane < NT;   // lane owns a (real or dummy) variable
+    const bool isreal = lane < nz;  // ... a real move variable
+    const bool iseps = P.neps && lane == nz;
+    const int iv = isvar ? lane : 0;
+    const double2* vx2 = reinterpret_cast<const double2*>(vx);
+    const double2* hrow = reinterpret_cast<const double2*>(sH + iv * LDH);
+    const int mh = ((m + 1) / 2 + 3) & ~3;  // rows per half-warp in the G'w products (multiple of 4)
+    const int KS = (m + 3) / 4;             // DMMA k-steps
+    const double minv = 1.0 / (double)max(m, 1);
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = (int)atomicAdd(&P.counters[0], 1u);
+        slot = __shfl_sync(WFULL, slot, 0);
+        if (slot >= P.N) break;
+        const int inst = Q.order ? Q.order[slot] : slot;
+
+        // ---- stage 0: TMA bulk loads of this instance's matrices ----
+        const int lv_ok = P.lv_ok[P.sH ? inst : 0];
+        if (lane == 0) {
+            fence_proxy_async();
+            const uint32_t bG = (uint32_t)(MP * LDG) * 8u, bH = (uint32_t)(2 * NT * LDH) * 8u;
+            mbar_arrive_expect_tx(bar, bG + bH);
+            tma_bulk_g2s(sH, Q.HL + (long)inst * Q.sHL, bH, bar);
+            tma_bulk_g2s(sG, Q.Gw + (long)inst * Q.sGw, bG, bar);
+        }
+        // ---- stage 1: initpred!  (execute.jl:247-277) ----
+        for (int k = lane; k < nx; k += 32) sxh[k] = P.xhat0[(long)inst * nx + k];
+        for (int k = lane; k < nu; k += 32) slu[k] = P.lastu0[(long)inst * nu + k];
+        if (nd > 0) {
+            for (int k = lane; k < nd; k += 32) sd0[k] = P.d0[(long)inst * nd + k];
+            for (int k = lane; k < nd * P.Hp; k += 32)
+                sDh[k] = P.Dhat0 ? P.Dhat0[(long)inst * nd * P.Hp + k] : P.d0[(long)inst * nd + (k % nd)];
+        }
+        __syncwarp();
+        const double* gK = P.K + (long)inst * P.sK;
+        const double* gV = P.V + (long)inst * P.sV;
+        const double* gB = P.B + (long)inst * P.sB;
+        const double* gyop = P.yop + (long)inst * P.syop;
+        const double* guop = P.uop + (long)inst * P.suop;
+        const double* gM = P.Mw + (long)inst * P.sM;
+        double racc = 0.0;
+        for (int t = lane; t < nY; t += 32) {
+            double f = gB[t];
+            for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
+            for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
+            if (nd > 0) {
+                const double* gG = P.G + (long)inst * P.sG;
+                const double* gJ = P.J + (long)inst * P.sJ;
+                for (int k = 0; k < nd; ++k) f = fma(gG[t + (long)nY * k], sd0[k], f);
+                for (int k = 0; k < nd * P.Hp; ++k) f = fma(gJ[t + (long)nY * k], sDh[k], f);
+            }
+            sF[t] = f;
+            const double ryt = P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)];
+            const double cy = f + gyop[t % ny] - ryt;
+            const double ty = gM[t] * cy;
+            stY[t] = ty;
+            racc = fma(cy, ty, racc);
+            P.F_out[(long)inst * nY + t] = f;
+        }
+        if (P.has_terminal) {
+            const double* gkx = P.kx + (long)inst * P.skx;
+            const double* gvx = P.vx + (long)inst * P.svx;
+            const double* gbx = P.bx + (long)inst * P.sbx;
+            for (int i = lane; i < nx; i += 32) {
+                double f = gbx[i];
+                for (int k = 0; k < nx; ++k) f = fma(gkx[i + (long)nx * k], sxh[k], f);
+                for (int k = 0; k < nu; ++k) f = fma(gvx[i + (long)nx * k], slu[k], f);
+                if (nd > 0) {
+                    const double* ggx = P.gx + (long)inst * P.sgx;
+                    const double* gjx = P.jx + (long)inst * P.sjx;
+                    for (int k = 0; k < nd; ++k) f = fma(ggx[i + (long)nx * k], sd0[k], f);
+                    for (int k = 0; k < nd * P.Hp; ++k) f = fma(gjx[i + (long)nx * k], sDh[k], f);
+                }
+                sfx[i] = f;
+            }
+        }
+        __syncwarp();
+        // q_i = 2 sum_t Ev[t,i] tY[t] (+ input-setpoint term): column i of Ev from HBM, t range split by half-warp
+        double q = 0.0;
+        {
+            const int ir = i16 < nz ? i16 : 0;
+            const double* col = P.Ev + (long)inst * P.sEv + (long)nY * ir;
+            const int th = (nY + 1) >> 1;
+            const int t0 = half ? th : 0, t1 = half ? nY : th;
+            double a0 = 0.0, a1 = 0.0;
+            int t = t0;
+            for (; t + 1 < t1; t += 2) {
+                a0 = fma(col[t], stY[t], a0);
+                a1 = fma(col[t + 1], stY[t + 1], a1);
+            }
+            if (t < t1) a0 = fma(col[t], stY[t], a0);
+            double a = a0 + a1;
+            a += __shfl_xor_sync(WFULL, a, 16);
+            if (P.has_L) {
+                const double* gL = P.Lw + (long)inst * P.sL;
+                const int l = ir / nu, ch = ir % nu;
+                for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) {
+                    const int idx = tt * nu + ch;
+                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
+                    a = fma(gL[idx], slu[ch] + guop[ch] - ru, a);
+                }
+                for (int idx = lane; idx < P.nU; idx += 32) {
+                    const int c2 = idx % nu;
+                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[c2];
+                    const double cu = slu[c2] + guop[c2] - ru;
+                    racc = fma(gL[idx] * cu, cu, racc);
+                }
+            }
+            q = isreal ? 2.0 * a : 0.0;
+        }
+        const double rconst = wsum(racc);
+        // ---- linconstraint!  (transcription.jl:811-848): right-hand sides of this lane's rows ----
+        double hR[RPL], sR[RPL], lamR[RPL];
+        bool okR[RPL];
+        double hmax = 0.0;
+        const double* gdb = P.dbound + (long)inst * nDr;
+        const double* gsb = P.sbase + (long)inst * nS;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int r = lane + 32 * t;
+            okR[t] = r < m;
+            double hv = 0.0;
+            if (r < nS) {
+                const int ch = rt.s_ch[r];
+                hv = gsb[r] - (ch >= 0 ? rt.row_sig[r] * slu[ch] : 0.0);
+            } else if (r < m) {
+                const int src = rt.dr_src[r - nS];
+                const double fsrc = src < nY ? sF[src] : sfx[src - nY];
+                hv = rt.row_sig[r] * (gdb[r - nS] - fsrc);
+            }
+            hR[t] = hv;
+            hmax = fmax(hmax, fabs(hv));
+        }
+        double qabs = fabs(q);
+        {
+            double z0 = 0.0, z1 = 0.0;
+            wred_mmms(hmax, qabs, z0, z1);
+        }
+        const double hscale = 1.0 + hmax;
+        const double qs = 1.0 + qabs;
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        // helpers -------------------------------------------------------------------------
+        // out[t] = Gt[r,:] . v   for this lane's rows, v in vx
+        auto row_products = [&](double (&out)[RPL]) {
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const double2* row = reinterpret_cast<const double2*>(sG + (lane + 32 * t) * LDG);
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < NV2; ++jj) {
+                    const double2 g2 = row[jj];
+                    const double2 v2 = vx2[jj];
+                    a = fma(g2.x, v2.x, a);
+                    b = fma(g2.y, v2.y, b);
+                }
+                out[t] = a + b;
+            }
+        };
+        // (Gt' w)_i for lane i < NT; w in shared memory (zero on padding rows)
+        const double* gcol = sG + (long)half * mh * LDG + (i16 < NT ? i16 : 0);
+        auto gt_apply1 = [&](const double* w) -> double {
+            const double2* wv = reinterpret_cast<const double2*>(w + half * mh);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+            for (int r = 0; r < mh; r += 4) {
+                const double2 wa = wv[r >> 1], wb = wv[(r >> 1) + 1];
+                a0 = fma(gcol[r * LDG], wa.x, a0);
+                a1 = fma(gcol[(r + 1) * LDG], wa.y, a1);
+                a2 = fma(gcol[(r + 2) * LDG], wb.x, a2);
+                a3 = fma(gcol[(r + 3) * LDG], wb.y, a3);
+            }
+            double a = (a0 + a1) + (a2 + a3);
+            a += __shfl_xor_sync(WFULL, a, 16);
+            return a;
+        };
+        auto gt_apply2 = [&](const double* wa_, const double* wb_, double& outa, double& outb) {
+            const double2* wva = reinterpret_cast<const double2*>(wa_ + half * mh);
+            const double2* wvb = reinterpret_cast<const double2*>(wb_ + half * mh);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 2
+            for (int r = 0; r < mh; r += 2) {
+                const double2 wa = wva[r >> 1], wb = wvb[r >> 1];
+                const double g0 = gcol[r * LDG], g1 = gcol[(r + 1) * LDG];
+                a0 = fma(g0, wa.x, a0);
+                a1 = fma(g1, wa.y, a1);
+                b0 = fma(g0, wb.x, b0);
+                b1 = fma(g1, wb.y, b1);
+            }
+            double a = a0 + a1, b = b0 + b1;
+            a += __shfl_xor_sync(WFULL, a, 16);
+            b += __shfl_xor_sync(WFULL, b, 16);
+            outa = a;
+            outb = b;
+        };
+        // (H x)_i with x in vx
+        auto hess_apply = [&]() -> double {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < NV2; ++jj) {
+                const double2 h2 = hrow[jj];
+                const double2 v2 = vx2[jj];
+                a = fma(h2.x, v2.x, a);
+                b = fma(h2.y, v2.y, b);
+            }
+            return isvar ? a + b : 0.0;
+        };
+        auto bcast = [&](double v, int j) -> double { return __shfl_sync(WFULL, v, j); };
+
+        // ---- stage 2: unconstrained minimiser with the cached factor (explicitmpc.jl:209) ----
+        double x = 0.0;
+        if (lv_ok) {
+            double b = isvar ? -q : 0.0;
+            const double invd0 = sL[iv * LDH + iv];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double yj = bcast(b * invd0, j);
+                if (lane > j && isvar) b = fma(-sL[iv * LDH + j], yj, b);
+            }
+            b *= invd0;
+#pragma unroll
+            for (int j = NT - 1; j >= 0; --j) {
+                const double xj = bcast(b * invd0, j);
+                if (lane < j) b = fma(-sL[j * LDH + iv], xj, b);
+            }
+            x = isvar ? b * invd0 : 0.0;
+        }
+        __syncwarp();
+        if (lane < 16) vx[lane] = x;
+        __syncwarp();
+        double gx[RPL];
+        row_products(gx);
+        double smin = 1e300;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            sR[t] = hR[t] - gx[t];
+            if (okR[t]) smin = fmin(smin, sR[t]);
+        }
+        smin = (m > 0) ? wmin(smin) : 0.0;
+        const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
+        int status = ST_OPTIMAL, iters = 0;
+        if (!feasible) {
+            // ---- stage 3: Mehrotra predictor-corrector ----
+            const double mu0 = fmax(1e-2 * qs * hscale * minv, 1e-8);
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                sR[t] = fmax(sR[t], 1e-2 * hscale);
+                lamR[t] = okR[t] ? mu0 / sR[t] : 0.0;
+            }
+            // ---- warm start (set_warmstart_mpc! analogue): previous period's solution and multipliers ----
+            if (P.use_ws && P.ws_flag[inst] != 0) {
+                const double* gZp = P.Z + (long)inst * nr;
+                double xw = 0.0;
+                if (isreal)
+                    for (int l = lane % nu; l <= lane; l += nu) xw += gZp[l];
+                if (iseps) xw = gZp[nz];
+                __syncwarp();
+                if (lane < 16) vx[lane] = xw;
+                __syncwarp();
+                x = xw;
+                row_products(gx);
+                const double* glw = P.lam_ws + (long)inst * P.ws_stride;
+                const double lmin = 1e-4 * qs / hscale;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    const int r = lane + 32 * t;
+                    sR[t] = fmax(hR[t] - gx[t], 1e-2 * hscale);
+                    lamR[t] = okR[t] ? fmax(glw[r], lmin) : 0.0;
+                }
+            }
+            status = ST_ITERATION_LIMIT;
+            double best_merit = 1e300, rp_inf = 0.0;
+            // r_p = Gx + s - h is carried by its recurrence r_p <- (1 - a) r_p (ds = -r_p - G dx is formed from the
+            // COMPUTED dx, so the recurrence is exact up to rounding whatever the accuracy of the linear solve)
+            double rpR[RPL];
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) rpR[t] = okR[t] ? gx[t] + sR[t] - hR[t] : 0.0;
+            for (int it = 0; it <= P.max_iter; ++it) {
+                double dR[RPL], isR[RPL];
+                double e_p = 0.0, musum = 0.0;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    const int r = lane + 32 * t;
+                    isR[t] = okR[t] ? __drcp_rn(sR[t]) : 0.0;
+                    dR[t] = lamR[t] * isR[t];
+                    w1[r] = lamR[t];
+                    w2[r] = dR[t] * rpR[t];
+                    wd[r] = dR[t];
+                    e_p = fmax(e_p, fabs(rpR[t]));
+                    musum = fma(sR[t], lamR[t], musum);
+                }
+                __syncwarp();
+                // residuals: rd = Hx + q + G'lam; the predictor's right-hand side needs G'(d rp) -- one pass for both
+                const double Hxq = hess_apply() + q;
+                double Gtl, Gdr;
+                gt_apply2(w1, w2, Gtl, Gdr);
+                if (!isvar) {
+                    Gtl = 0.0;
+                    Gdr = 0.0;
+                }
+                const double rd = Hxq + Gtl;
+                double e_d = fabs(rd), dsc = fmax(fabs(Hxq), fabs(Gtl));
+                wred_mmms(e_d, dsc, e_p, musum);
+                const double qd = qs + dsc;  // scale of the dual residual's terms
+                const double mu = musum * minv;
+                rp_inf = e_p;
+                if (!(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250) {
+                    status = ST_INFEASIBLE;
+                    break;
+                }
+                const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
+                                          mu * (double)m / (P.tol_mu * qs * hscale));
+                if (merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) || (it == P.max_iter && merit <= 1e3)) {
+                    status = ST_OPTIMAL;
+                    break;
+                }
+                best_merit = fmin(best_merit, merit);
+                if (it == P.max_iter) break;
+                iters = it + 1;
+                // ---- Phi = H + Gt' D Gt on the FP64 tensor pipe (lower block-triangle) ----
+                double c00a, c00b, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
+                {
+                    const int hr = fg < NT ? fg : 0, hc = 2 * ft;
+                    const double2 h2 = *reinterpret_cast<const double2*>(sH + hr * LDH + (hc < LDH ? hc : 0));
+                    const bool okr = fg < NT;
+                    c00a = (okr && hc < NT) ? h2.x : 0.0;
+                    c00b = (okr && hc + 1 < NT) ? h2.y : 0.0;
+                    if (NB == 2) {
+                        const int hr1 = 8 + fg < NT ? 8 + fg : 0;
+                        const bool okr1 = 8 + fg < NT;
+                        const double2 g2 = *reinterpret_cast<const double2*>(sH + hr1 * LDH + (hc < LDH ? hc : 0));
+                        c10a = (okr1 && hc < NT) ? g2.x : 0.0;
+                        c10b = (okr1 && hc + 1 < NT) ? g2.y : 0.0;
+                        const int hc1 = 8 + hc;
+                        const double2 k2 = *reinterpret_cast<const double2*>(sH + hr1 * LDH + (hc1 < LDH ? hc1 : 0));
+                        c11a = (okr1 && hc1 < NT) ? k2.x : 0.0;
+                        c11b = (okr1 && hc1 + 1 < NT) ? k2.y : 0.0;
+                    }
+                }
+                {
+                    constexpr bool pred1 = NB == 2 && LDG < 16;  // columns 8+fg exist only for fg < LDG - 8
+                    const bool ok1 = !pred1 || fg < LDG - 8;
+                    const double* ga = sG + ft * LDG + fg;
+                    const double* gb = sG + ft * LDG + (ok1 ? 8 + fg : 0);
+                    const double* wdp = wd + ft;
+#pragma unroll 5
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const double a0 = ga[ks * 4 * LDG];
+                        const double dk = wdp[ks * 4];
+                        const double b0 = dk * a0;
+                        dmma884(c00a, c00b, a0, b0);
+                        if (NB == 2) {
+                            double a1 = gb[ks * 4 * LDG];
+                            if (pred1) a1 = ok1 ? a1 : 0.0;
+                            const double b1 = dk * a1;
+                            dmma884(c10a, c10b, a1, b0);
+                            dmma884(c11a, c11b, a1, b1);
+                        }
+                    }
+                }
+                __syncwarp();
+                *reinterpret_cast<double2*>(sPhi + fg * LDP + 2 * ft) = make_double2(c00a, c00b);
+                if (NB == 2) {
+                    *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 2 * ft) = make_double2(c10a, c10b);
+                    *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 8 + 2 * ft) = make_double2(c11a, c11b);
+                }
+                __syncwarp();
+                double phi[2 * NV2];
+                {
+                    const double2* prow = reinterpret_cast<const double2*>(sPhi + iv * LDP);
+#pragma unroll
+                    for (int jj = 0; jj < NV2; ++jj) {
+                        const double2 p2 = prow[jj];
+                        phi[2 * jj] = p2.x;
+                        phi[2 * jj + 1] = p2.y;
+                    }
+                }
+                double pdiag = 0.0;
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+                    if (j == lane) pdiag = phi[j];
+                __syncwarp();
+                // ---- Cholesky: right-looking, rows in registers, columns exchanged by shuffles ----
+                double invd = 1.0;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    double dk = bcast(pdiag, k);
+                    if (!(dk > 1e-280)) dk = 1e200;
+                    const double rs = rsqrt(dk);
+                    const double lik = (lane > k && isvar) ? phi[k] * rs : 0.0;  // column k of L
+                    if (lane == k) invd = rs;
+                    phi[k] = lik;
+                    pdiag = fma(-lik, lik, pdiag);
+#pragma unroll
+                    for (int j = k + 1; j < NT; ++j) {
+                        const double ljk = bcast(lik, j);
+                        phi[j] = fma(-lik, ljk, phi[j]);
+                    }
+                }
+                // rows of L to shared memory for the backward substitutions
+                if (isvar) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) sPhi[lane * LDN + j] = phi[j];
+                }
+                __syncwarp();
+                double lcol[NT];  // column `lane` of L (entries below the diagonal)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) lcol[j] = (lane < j) ? sPhi[j * LDN + iv] : 0.0;
+                auto solve = [&](double b) -> double {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double yj = bcast(b * invd, j);
+                        b = fma(-((lane > j) ? phi[j] : 0.0), yj, b);
+                    }
+                    b *= invd;
+#pragma unroll
+                    for (int j = NT - 1; j >= 0; --j) {
+                        const double xj = bcast(b * invd, j);
+                        b = fma(-lcol[j], xj, b);
+                    }
+                    return isvar ? b * invd : 0.0;
+                };
+                // ---- predictor ----
+                double dsR[RPL], dlR[RPL], rcR[RPL];
+                double dx = solve(isvar ? -(Hxq + Gdr) : 0.0);
+                __syncwarp();
+                if (lane < 16) vx[lane] = dx;
+                __syncwarp();
+                row_products(gx);
+                double rho = 0.0;  // max over rows of -ds/s and -dl/lambda (step to the boundary = 1/rho)
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    dsR[t] = -rpR[t] - gx[t];
+                    dlR[t] = -lamR[t] - dR[t] * dsR[t];
+                    const double rs_ = -dsR[t] * isR[t];
+                    rho = fmax(rho, fmax(rs_, 1.0 - rs_));  // -dl/lam = 1 + ds/s in the affine step
+                }
+                if (m == 0) rho = 0.0;
+                rho = wmax(rho);
+                const double a_aff = rho > 1.0 ? 1.0 / rho : 1.0;
+                double mua = 0.0;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) mua = fma(sR[t] + a_aff * dsR[t], lamR[t] + a_aff * dlR[t], mua);
+                mua = wsum(mua) * minv;
+                const double ratio = mua / mu;
+                const double sig = ratio * ratio * ratio;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    const int r = lane + 32 * t;
+                    rcR[t] = sR[t] * lamR[t] + dsR[t] * dlR[t] - sig * mu;
+                    w1[r] = (lamR[t] * rpR[t] - rcR[t]) * isR[t];
+                }
+                __syncwarp();
+                // ---- corrector ----
+                const double Gw = gt_apply1(w1);
+                dx = solve(isvar ? -(rd + Gw) : 0.0);
+                __syncwarp();
+                if (lane < 16) vx[lane] = dx;
+                __syncwarp();
+                row_products(gx);
+                rho = 0.0;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    dsR[t] = -rpR[t] - gx[t];
+                    dlR[t] = -(rcR[t] + lamR[t] * dsR[t]) * isR[t];
+                    const double rl = okR[t] ? -dlR[t] * __drcp_rn(lamR[t]) : 0.0;
+                    rho = fmax(rho, fmax(-dsR[t] * isR[t], rl));
+                }
+                rho = wmax(rho);
+                // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
+                const double tau = fmax(0.99, 1.0 - ratio);
+                const double a = rho > tau ? tau / rho : 1.0;
+                x = fma(a, dx, x);
+                const double oma = 1.0 - a;
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    rpR[t] *= oma;
+                    sR[t] = fma(a, dsR[t], sR[t]);
+                    lamR[t] = fma(a, dlR[t], lamR[t]);
+                }
+                __syncwarp();
+                if (lane < 16) vx[lane] = x;
+                __syncwarp();
+            }
+            if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+        }
+        // ---- stage 4: getinput!  (execute.jl:536-546) ----
+        double* gZ = P.Z + (long)inst * nr;
+        __syncwarp();
+        if (status == ST_INFEASIBLE) {
+            // shifted previous solution (set_warmstart_mpc!, transcription.jl:997-1007), in level coordinates
+            double a = 0.0;
+            if (isreal)
+                for (int l = lane % nu; l <= lane; l += nu) a += (l + nu < nz) ? gZ[l + nu] : 0.0;
+            x = isreal ? a : (iseps ? gZ[nz] : 0.0);
+        }
+        __syncwarp();
+        if (lane < 16) vx[lane] = x;
+        __syncwarp();
+        const double Hx = hess_apply();
+        double jacc = isvar ? x * (0.5 * Hx + q) : 0.0;
+        jacc = wsum(jacc) + rconst;
+        // q̃ in reference coordinates: q̃[j] = sum_{l' >= l(j), same input} q_v[l']
+        w1[lane] = q;
+        __syncwarp();
+        if (isreal) {
+            gZ[lane] = x - (lane >= nu ? vx[lane - nu] : 0.0);
+            double a = 0.0;
+            for (int l = lane; l < nz; l += nu) a += w1[l];
+            P.qt_out[(long)inst * nr + lane] = a;
+        }
+        if (iseps) {
+            gZ[nz] = x;
+            P.qt_out[(long)inst * nr + nz] = 0.0;
+        }
+        if (lane < nu) {
+            const double du = vx[lane];
+            const double lu = slu[lane];
+            P.lastu_prev[(long)inst * nu + lane] = lu;
+            P.lastu0[(long)inst * nu + lane] = lu + du;
+            P.u[(long)inst * nu + lane] = lu + du + guop[lane];
+        }
+        if (P.use_ws) {
+            // multipliers for the next period's warm start (valid only after a converged IPM solve)
+            const bool keep = status == ST_OPTIMAL && iters > 0;
+            double* glw = P.lam_ws + (long)inst * P.ws_stride;
+            if (keep) {
+#pragma unroll
+                for (int t = 0; t < RPL; ++t)
+                    if (okR[t]) glw[lane + 32 * t] = lamR[t];
+            }
+            if (lane == 0) P.ws_flag[inst] = keep ? 1 : 0;
+        }
+        if (lane == 0) {
+            P.r_out[inst] = rconst;
+            if (P.J_out) P.J_out[inst] = jacc;
+            P.status[inst] = status;
+            P.iters[inst] = iters;
+            if (Q.order_next) {
+                // next launch's order: slow instances first (front), the rest from the back
+                if (iters >= Q.long_thresh)
+                    Q.order_next[atomicAdd(&Q.ocnt[0], 1u)] = inst;
+                else
+                    Q.order_next[P.N - 1 - (int)atomicAdd(&Q.ocnt[1], 1u)] = inst;
+            }
+        }
+        fence_proxy_async();  // generic-proxy accesses to the TMA destinations precede the next bulk copy
+        __syncwarp();
+    }
+    // ---- reset the work counters for the next launch (last CTA out) ----
+    if (lane == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&P.counters[1], 1u);
+        if (done == gridDim.x - 1) {
+            P.counters[0] = 0u;
+            P.counters[1] = 0u;
+            if (Q.ocnt) {
+                Q.ocnt[0] = 0u;
+                Q.ocnt[1] = 0u;
+            }
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace bmpc
