@@ -86,6 +86,16 @@ __device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, doubl
     }
 }
 
+// one maximum and one sum in one butterfly
+__device__ __forceinline__ void wred_ms(double& a, double& s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(WFULL, a, o), ts = __shfl_xor_sync(WFULL, s, o);
+        a = fmax(a, ta);
+        s += ts;
+    }
+}
+
 template <int NT, int RPL>
 __global__ void __launch_bounds__(32, 16)
     step_warp(const __grid_constant__ StepParams P, const __grid_constant__ WarpParams Q) {
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(32, 16)
         int slot = 0;
         if (lane == 0) slot = (int)atomicAdd(&P.counters[0], 1u);
         slot = __shfl_sync(WFULL, slot, 0);
-        if (slot >= P.N) break;
+        if (__all_sync(WFULL, slot >= P.N)) break;  // vote: provably warp-uniform branch (no divergent-shuffle paths)
         const int inst = Q.order ? Q.order[slot] : slot;
 
         // ---- stage 0: TMA bulk loads of this instance's matrices ----
@@ -165,14 +175,19 @@ __global__ void __launch_bounds__(32, 16)
         const double* guop = P.uop + (long)inst * P.suop;
         const double* gM = P.Mw + (long)inst * P.sM;
         double racc = 0.0;
+#pragma unroll 1
         for (int t = lane; t < nY; t += 32) {
             double f = gB[t];
+#pragma unroll 2
             for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
+#pragma unroll 1
             for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
             if (nd > 0) {
                 const double* gG = P.G + (long)inst * P.sG;
                 const double* gJ = P.J + (long)inst * P.sJ;
+#pragma unroll 1
                 for (int k = 0; k < nd; ++k) f = fma(gG[t + (long)nY * k], sd0[k], f);
+#pragma unroll 1
                 for (int k = 0; k < nd * P.Hp; ++k) f = fma(gJ[t + (long)nY * k], sDh[k], f);
             }
             sF[t] = f;
@@ -187,54 +202,25 @@ __global__ void __launch_bounds__(32, 16)
             const double* gkx = P.kx + (long)inst * P.skx;
             const double* gvx = P.vx + (long)inst * P.svx;
             const double* gbx = P.bx + (long)inst * P.sbx;
+#pragma unroll 1
             for (int i = lane; i < nx; i += 32) {
                 double f = gbx[i];
+#pragma unroll 1
                 for (int k = 0; k < nx; ++k) f = fma(gkx[i + (long)nx * k], sxh[k], f);
+#pragma unroll 1
                 for (int k = 0; k < nu; ++k) f = fma(gvx[i + (long)nx * k], slu[k], f);
                 if (nd > 0) {
                     const double* ggx = P.gx + (long)inst * P.sgx;
                     const double* gjx = P.jx + (long)inst * P.sjx;
+#pragma unroll 1
                     for (int k = 0; k < nd; ++k) f = fma(ggx[i + (long)nx * k], sd0[k], f);
+#pragma unroll 1
                     for (int k = 0; k < nd * P.Hp; ++k) f = fma(gjx[i + (long)nx * k], sDh[k], f);
                 }
                 sfx[i] = f;
             }
         }
         __syncwarp();
-        // q_i = 2 sum_t Ev[t,i] tY[t] (+ input-setpoint term): column i of Ev from HBM, t range split by half-warp
-        double q = 0.0;
-        {
-            const int ir = i16 < nz ? i16 : 0;
-            const double* col = P.Ev + (long)inst * P.sEv + (long)nY * ir;
-            const int th = (nY + 1) >> 1;
-            const int t0 = half ? th : 0, t1 = half ? nY : th;
-            double a0 = 0.0, a1 = 0.0;
-            int t = t0;
-            for (; t + 1 < t1; t += 2) {
-                a0 = fma(col[t], stY[t], a0);
-                a1 = fma(col[t + 1], stY[t + 1], a1);
-            }
-            if (t < t1) a0 = fma(col[t], stY[t], a0);
-            double a = a0 + a1;
-            a += __shfl_xor_sync(WFULL, a, 16);
-            if (P.has_L) {
-                const double* gL = P.Lw + (long)inst * P.sL;
-                const int l = ir / nu, ch = ir % nu;
-                for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) {
-                    const int idx = tt * nu + ch;
-                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
-                    a = fma(gL[idx], slu[ch] + guop[ch] - ru, a);
-                }
-                for (int idx = lane; idx < P.nU; idx += 32) {
-                    const int c2 = idx % nu;
-                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[c2];
-                    const double cu = slu[c2] + guop[c2] - ru;
-                    racc = fma(gL[idx] * cu, cu, racc);
-                }
-            }
-            q = isreal ? 2.0 * a : 0.0;
-        }
-        const double rconst = wsum(racc);
         // ---- linconstraint!  (transcription.jl:811-848): right-hand sides of this lane's rows ----
         double hR[RPL], sR[RPL], lamR[RPL];
         bool okR[RPL];
@@ -245,7 +231,7 @@ __global__ void __launch_bounds__(32, 16)
         for (int t = 0; t < RPL; ++t) {
             const int r = lane + 32 * t;
             okR[t] = r < m;
-            double hv = 0.0;
+            double hv = 0.0, wq = 0.0;
             if (r < nS) {
                 const int ch = rt.s_ch[r];
                 hv = gsb[r] - (ch >= 0 ? rt.row_sig[r] * slu[ch] : 0.0);
@@ -253,17 +239,17 @@ __global__ void __launch_bounds__(32, 16)
                 const int src = rt.dr_src[r - nS];
                 const double fsrc = src < nY ? sF[src] : sfx[src - nY];
                 hv = rt.row_sig[r] * (gdb[r - nS] - fsrc);
+                if (P.pd_is_ev) {
+                    // q = 2 Ev' tY = Gt' w with w = 2 sigma tY on ONE row per prediction (the max-side row if present)
+                    const int kb = rt.dr_base[r - nS];
+                    const int rmax = rt.db_rmax[kb];
+                    if (rmax == r || (rmax < 0 && rt.db_rmin[kb] == r)) wq = 2.0 * rt.row_sig[r] * stY[src];
+                }
             }
             hR[t] = hv;
             hmax = fmax(hmax, fabs(hv));
+            w1[r] = wq;
         }
-        double qabs = fabs(q);
-        {
-            double z0 = 0.0, z1 = 0.0;
-            wred_mmms(hmax, qabs, z0, z1);
-        }
-        const double hscale = 1.0 + hmax;
-        const double qs = 1.0 + qabs;
         mbar_wait(bar, phase);
         phase ^= 1u;
 
@@ -334,9 +320,61 @@ __global__ void __launch_bounds__(32, 16)
         };
         auto bcast = [&](double v, int j) -> double { return __shfl_sync(WFULL, v, j); };
 
+        // q_i = 2 sum_t Ev[t,i] tY[t] (+ input-setpoint term)
+        double q = 0.0;
+        {
+            const int ir = i16 < nz ? i16 : 0;
+            double a;
+            if (P.pd_is_ev) {
+                // the dense rows of Gt ARE +-Ev: no second pass over Ev in HBM
+                __syncwarp();
+                a = 0.5 * gt_apply1(w1);
+            } else {
+                // column i of Ev from HBM, t range split by half-warp
+                const double* col = P.Ev + (long)inst * P.sEv + (long)nY * ir;
+                const int th = (nY + 1) >> 1;
+                const int t0 = half ? th : 0, t1 = half ? nY : th;
+                double a0 = 0.0, a1 = 0.0;
+                int t = t0;
+#pragma unroll 2
+                for (; t + 1 < t1; t += 2) {
+                    a0 = fma(col[t], stY[t], a0);
+                    a1 = fma(col[t + 1], stY[t + 1], a1);
+                }
+                if (t < t1) a0 = fma(col[t], stY[t], a0);
+                a = a0 + a1;
+                a += __shfl_xor_sync(WFULL, a, 16);
+            }
+            if (P.has_L) {
+                const double* gL = P.Lw + (long)inst * P.sL;
+                const int l = ir / nu, ch = ir % nu;
+#pragma unroll 1
+                for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) {
+                    const int idx = tt * nu + ch;
+                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
+                    a = fma(gL[idx], slu[ch] + guop[ch] - ru, a);
+                }
+#pragma unroll 1
+                for (int idx = lane; idx < P.nU; idx += 32) {
+                    const int c2 = idx % nu;
+                    const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[c2];
+                    const double cu = slu[c2] + guop[c2] - ru;
+                    racc = fma(gL[idx] * cu, cu, racc);
+                }
+            }
+            q = isreal ? 2.0 * a : 0.0;
+        }
+        const double rconst = wsum(racc);
+        double qabs = fabs(q);
+        {
+            double z0 = 0.0, z1 = 0.0;
+            wred_mmms(hmax, qabs, z0, z1);
+        }
+        const double hscale = 1.0 + hmax;
+        const double qs = 1.0 + qabs;
         // ---- stage 2: unconstrained minimiser with the cached factor (explicitmpc.jl:209) ----
         double x = 0.0;
-        if (lv_ok) {
+        if (__any_sync(WFULL, lv_ok != 0)) {
             double b = isvar ? -q : 0.0;
             const double invd0 = sL[iv * LDH + iv];
 #pragma unroll
@@ -366,7 +404,7 @@ __global__ void __launch_bounds__(32, 16)
         smin = (m > 0) ? wmin(smin) : 0.0;
         const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
         int status = ST_OPTIMAL, iters = 0;
-        if (!feasible) {
+        if (__any_sync(WFULL, !feasible)) {
             // ---- stage 3: Mehrotra predictor-corrector ----
             const double mu0 = fmax(1e-2 * qs * hscale * minv, 1e-8);
 #pragma unroll
@@ -375,7 +413,7 @@ __global__ void __launch_bounds__(32, 16)
                 lamR[t] = okR[t] ? mu0 / sR[t] : 0.0;
             }
             // ---- warm start (set_warmstart_mpc! analogue): previous period's solution and multipliers ----
-            if (P.use_ws && P.ws_flag[inst] != 0) {
+            if (__any_sync(WFULL, P.use_ws && P.ws_flag[inst] != 0)) {
                 const double* gZp = P.Z + (long)inst * nr;
                 double xw = 0.0;
                 if (isreal)
@@ -431,13 +469,14 @@ __global__ void __launch_bounds__(32, 16)
                 const double qd = qs + dsc;  // scale of the dual residual's terms
                 const double mu = musum * minv;
                 rp_inf = e_p;
-                if (!(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250) {
+                if (__any_sync(WFULL, !(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250)) {
                     status = ST_INFEASIBLE;
                     break;
                 }
                 const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
                                           mu * (double)m / (P.tol_mu * qs * hscale));
-                if (merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) || (it == P.max_iter && merit <= 1e3)) {
+                if (__any_sync(WFULL, merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) ||
+                                              (it == P.max_iter && merit <= 1e3))) {
                     status = ST_OPTIMAL;
                     break;
                 }
@@ -547,55 +586,57 @@ __global__ void __launch_bounds__(32, 16)
                     }
                     return isvar ? b * invd : 0.0;
                 };
-                // ---- predictor ----
+                // ---- predictor (pass 0) and corrector (pass 1) share one copy of the code ----
                 double dsR[RPL], dlR[RPL], rcR[RPL];
-                double dx = solve(isvar ? -(Hxq + Gdr) : 0.0);
-                __syncwarp();
-                if (lane < 16) vx[lane] = dx;
-                __syncwarp();
-                row_products(gx);
-                double rho = 0.0;  // max over rows of -ds/s and -dl/lambda (step to the boundary = 1/rho)
 #pragma unroll
-                for (int t = 0; t < RPL; ++t) {
-                    dsR[t] = -rpR[t] - gx[t];
-                    dlR[t] = -lamR[t] - dR[t] * dsR[t];
-                    const double rs_ = -dsR[t] * isR[t];
-                    rho = fmax(rho, fmax(rs_, 1.0 - rs_));  // -dl/lam = 1 + ds/s in the affine step
+                for (int t = 0; t < RPL; ++t) rcR[t] = 0.0;
+                double rhs = isvar ? -(Hxq + Gdr) : 0.0;
+                double dx = 0.0, rho = 0.0, ratio = 1.0;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    dx = solve(rhs);
+                    __syncwarp();
+                    if (lane < 16) vx[lane] = dx;
+                    __syncwarp();
+                    row_products(gx);
+                    rho = 0.0;  // max over rows of -ds/s and -dl/lambda (step to the boundary = 1/rho)
+                    double sdd = 0.0;  // sum ds*dl
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        dsR[t] = -rpR[t] - gx[t];
+                        const double rs_ = -dsR[t] * isR[t];
+                        double rl;
+                        if (pass == 0) {
+                            dlR[t] = -lamR[t] - dR[t] * dsR[t];
+                            rl = okR[t] ? 1.0 - rs_ : 0.0;  // -dl/lam = 1 + ds/s in the affine step
+                        } else {
+                            dlR[t] = -(rcR[t] + lamR[t] * dsR[t]) * isR[t];
+                            rl = okR[t] ? -dlR[t] * __drcp_rn(lamR[t]) : 0.0;
+                        }
+                        rho = fmax(rho, fmax(rs_, rl));
+                        sdd = fma(dsR[t], dlR[t], sdd);
+                    }
+                    wred_ms(rho, sdd);
+                    if (pass == 0) {
+                        // affine step: s*dl + lam*ds = -s*lam exactly, so
+                        //   sum (s + a ds)(lam + a dl) = (1 - a) sum s*lam + a^2 sum ds*dl   -- no second reduction
+                        const double a_aff = rho > 1.0 ? 1.0 / rho : 1.0;
+                        const double mua = fmax(((1.0 - a_aff) * musum + a_aff * a_aff * sdd) * minv, 0.0);
+                        ratio = mua / mu;
+                        const double sig = ratio * ratio * ratio;
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) {
+                            const int r = lane + 32 * t;
+                            rcR[t] = sR[t] * lamR[t] + dsR[t] * dlR[t] - sig * mu;
+                            w1[r] = (lamR[t] * rpR[t] - rcR[t]) * isR[t];
+                        }
+                        __syncwarp();
+                        const double Gw = gt_apply1(w1);
+                        rhs = isvar ? -(rd + Gw) : 0.0;
+                    }
                 }
-                if (m == 0) rho = 0.0;
-                rho = wmax(rho);
-                const double a_aff = rho > 1.0 ? 1.0 / rho : 1.0;
-                double mua = 0.0;
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) mua = fma(sR[t] + a_aff * dsR[t], lamR[t] + a_aff * dlR[t], mua);
-                mua = wsum(mua) * minv;
-                const double ratio = mua / mu;
-                const double sig = ratio * ratio * ratio;
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) {
-                    const int r = lane + 32 * t;
-                    rcR[t] = sR[t] * lamR[t] + dsR[t] * dlR[t] - sig * mu;
-                    w1[r] = (lamR[t] * rpR[t] - rcR[t]) * isR[t];
-                }
-                __syncwarp();
-                // ---- corrector ----
-                const double Gw = gt_apply1(w1);
-                dx = solve(isvar ? -(rd + Gw) : 0.0);
-                __syncwarp();
-                if (lane < 16) vx[lane] = dx;
-                __syncwarp();
-                row_products(gx);
-                rho = 0.0;
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) {
-                    dsR[t] = -rpR[t] - gx[t];
-                    dlR[t] = -(rcR[t] + lamR[t] * dsR[t]) * isR[t];
-                    const double rl = okR[t] ? -dlR[t] * __drcp_rn(lamR[t]) : 0.0;
-                    rho = fmax(rho, fmax(-dsR[t] * isR[t], rl));
-                }
-                rho = wmax(rho);
                 // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
-                const double tau = fmax(0.99, 1.0 - ratio);
+                const double tau = fmin(fmax(0.99, 1.0 - ratio), 1.0 - 1e-6);  // never exactly onto the boundary
                 const double a = rho > tau ? tau / rho : 1.0;
                 x = fma(a, dx, x);
                 const double oma = 1.0 - a;
@@ -614,7 +655,7 @@ __global__ void __launch_bounds__(32, 16)
         // ---- stage 4: getinput!  (execute.jl:536-546) ----
         double* gZ = P.Z + (long)inst * nr;
         __syncwarp();
-        if (status == ST_INFEASIBLE) {
+        if (__any_sync(WFULL, status == ST_INFEASIBLE)) {
             // shifted previous solution (set_warmstart_mpc!, transcription.jl:997-1007), in level coordinates
             double a = 0.0;
             if (isreal)
