@@ -94,6 +94,13 @@ typedef struct {
     int32_t *iters;       /* N           out: interior-point iterations (0 = unconstrained exit) */
     int32_t device_ptrs;  /* 1: every pointer above is a device pointer on dims.device           */
     int32_t sync;         /* 1: block until the results are complete                             */
+    int32_t resident;     /* host pointers only.  0: lastu0 and Ztilde are uploaded and downloaded every
+                           * call.  1: they are STATE OF THE HANDLE, as mpc.lastu0 and mpc.Z̃ are fields of the
+                           * reference controller (linmpc.jl:3-49) that moveinput! neither takes nor returns:
+                           * nothing is uploaded; lastu0, Ztilde, J and iters may be NULL and are download-only
+                           * when given.  The state is the one left by the previous call (zeros after
+                           * bmpc_create).                                                         */
+    int32_t reserved;
 } bmpc_step_io;
 
 /* Diagnostics of the last step (= getinfo, execute.jl:145-198); any pointer may be NULL.

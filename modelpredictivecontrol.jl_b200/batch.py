@@ -138,7 +138,10 @@ class BatchLinMPC:
         check(_lib.lib().bmpc_set_constraints(self._h, *[dptr(a) for a in arrs], C.byref(S)))
 
     # ---- per-period call (= moveinput!) ----------------------------------------------------
-    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None):
+    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None, resident=False):
+        """One control period (moveinput!).  ``resident=True``: lastu0 and Z̃ stay in the handle between calls
+        (they are fields of the reference controller, not arguments of moveinput!): only x̂0/ry go up and only
+        u/status come back; self.lastu0, self.Ztilde, self.J, self.iters are then NOT refreshed."""
         N = self.N
         x = _vec(xhat0, N, self.nxhat, "xhat0")
         ryv = None if ry is None else _vec(ry, N, self.ny, "ry")
@@ -147,9 +150,13 @@ class BatchLinMPC:
         d0v = None if d0 is None or self.nd == 0 else _vec(d0, N, self.nd, "d0")
         Dh = None if Dhat0 is None or self.nd == 0 else _vec(Dhat0, N, self.nd * self.Hp, "Dhat0")
         p = lambda a: None if a is None else a.ctypes.data
-        io = _lib.StepIO(xhat0=p(x), lastu0=p(self.lastu0), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v),
-                         Dhat0=p(Dh), Ztilde=p(self.Ztilde), u=p(self.u), J=p(self.J), status=p(self.status),
-                         iters=p(self.iters), device_ptrs=0, sync=1)
+        if resident:
+            io = _lib.StepIO(xhat0=p(x), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v), Dhat0=p(Dh), u=p(self.u),
+                             status=p(self.status), device_ptrs=0, sync=1, resident=1)
+        else:
+            io = _lib.StepIO(xhat0=p(x), lastu0=p(self.lastu0), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v),
+                             Dhat0=p(Dh), Ztilde=p(self.Ztilde), u=p(self.u), J=p(self.J), status=p(self.status),
+                             iters=p(self.iters), device_ptrs=0, sync=1)
         check(_lib.lib().bmpc_step(self._h, C.byref(io)))
         return self.u
 

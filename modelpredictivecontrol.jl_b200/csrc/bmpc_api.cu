@@ -860,8 +860,11 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         int rc = bmpc_set_oppoints(h, nullptr, nullptr);
         if (rc != BMPC_OK) return rc;
     }
-    if (!io->xhat0 || !io->lastu0 || (!io->ry && !io->Rhat_y) || !io->Ztilde || !io->u || !io->status || !io->iters)
-        return fail(BMPC_ERR_ARG, "xhat0, lastu0, ry|Rhat_y, Ztilde, u, status, iters are required");
+    const bool resident = io->resident != 0 && io->device_ptrs == 0;
+    if (!io->xhat0 || (!io->ry && !io->Rhat_y) || !io->u || !io->status)
+        return fail(BMPC_ERR_ARG, "xhat0, ry|Rhat_y, u, status are required");
+    if (!resident && (!io->lastu0 || !io->Ztilde || !io->iters))
+        return fail(BMPC_ERR_ARG, "lastu0, Ztilde, iters are required unless io.resident = 1");
     if (d.nd > 0 && !io->d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
     if (h->has_terminal_rows && !h->has_terminal_mats) return fail(BMPC_ERR_STATE, "terminal matrices missing");
     if (h->dirty) {
@@ -893,8 +896,10 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         P.status = io->status;
         P.iters = io->iters;
     } else {
-        CK(cudaMemcpyAsync(h->lastu0.p, io->lastu0, N * nu * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->Z.p, io->Ztilde, N * n * 8, cudaMemcpyHostToDevice, s));
+        if (!resident) {
+            CK(cudaMemcpyAsync(h->lastu0.p, io->lastu0, N * nu * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->Z.p, io->Ztilde, N * n * 8, cudaMemcpyHostToDevice, s));
+        }
         P.lastu0 = h->lastu0.p;
         P.Z = h->Z.p;
         P.u = h->u.p;
@@ -952,12 +957,12 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     h->last_Z = P.Z;
     h->last_xhat0 = P.xhat0;
     if (!dev) {
-        CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
+        if (io->lastu0) CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
+        if (io->Ztilde) CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(io->u, h->u.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
         if (io->J) CK(cudaMemcpyAsync(io->J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(io->status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+        if (io->iters) CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
     }
     if (io->sync || !dev) CK(cudaStreamSynchronize(s));
     return BMPC_OK;

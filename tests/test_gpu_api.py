@@ -136,3 +136,17 @@ def test_full_size_c1_properties():
     mpc_t, info_t = run(ident, team=32)
     assert np.abs(mpc_t.Ztilde - mpc.Ztilde).max() < 2e-6
     assert np.abs(info_t["J"] - info["J"]).max() < 1e-9 * (1 + np.abs(info["J"]).max())
+
+
+def test_resident_state_equals_host_state():
+    """io.resident = 1 (u0(k-1) and Z̃ are state of the handle, as mpc.lastu0 / mpc.Z̃ in linmpc.jl:3-49) gives
+    bitwise the same inputs as round-tripping both through the host every call."""
+    mpcs, plants, rng = c1_controllers(16, seed=21)
+    bH, bR = batch_from_oracle(mpcs), batch_from_oracle(mpcs)
+    for k in range(8):
+        xh = rng.standard_normal((16, mpcs[0].estim.nxhat)) * 0.3
+        ry = rng.choice([-1.0, 1.0], (16, 2))
+        uH = bH.step(xh, ry=ry).copy()
+        uR = bR.step(xh, ry=ry, resident=k > 0).copy()
+        assert (bR.status == bH.status).all()
+        assert np.array_equal(uH, uR), k
