@@ -59,7 +59,7 @@ struct bmpc_handle {
     DevBuf<double> t_sig, t_c, sbase, dbound, Pd;
     std::vector<unsigned char> pattern;  // finiteness pattern of the bounds (frozen after first step)
     int nPd2 = 0;
-    bool pd_is_ev = false, pd_in_smem = false, has_terminal_rows = false;
+    bool pd_is_ev = false, pd_in_smem = false, has_terminal_rows = false, hv_in_smem = true;
     // io staging
     DevBuf<double> xhat0, lastu0, ry, Rhat_y, Rhat_u, d0, Dhat0, Z, u, Jv, F, qt, r, lastu_prev;
     DevBuf<int> status, iters;
@@ -91,13 +91,12 @@ int choose_team(const bmpc_handle* h) {
     if (const char* e = getenv("BMPC_TEAM")) return atoi(e);  // tuning override
     const int n = h->n;
     if (n <= 16) return 16;
-    if (n <= 48) return 32;
-    if (n <= 112) return 128;
+    if (n <= 96) return 128;   // CTA teams: Hessian build on the FP64 tensor pipe (DMMA), several CTAs per SM
     return 256;
 }
 
 // shared-memory slice of one team, in doubles (every offset even => 16-byte aligned)
-void layout_smem(bmpc_handle* h, bool pd_in_smem) {
+void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     const int n = h->n, nz = h->nz, m = h->rt.m, nDb = h->rt.nDb, nY = h->nY, nx = h->d.nxhat;
     bmpc::SmemLayout& L = h->sm;
     int o = 0;
@@ -107,7 +106,7 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem) {
         return at;
     };
     L.Pd = take(pd_in_smem ? h->nPd2 : 0);
-    L.Hv = take(h->nHp2);
+    L.Hv = take(hv_in_smem ? h->nHp2 : 0);
     L.Phi = take(std::max(even(n * (n + 1) / 2), h->nHp2));
     L.x = take(n);
     L.q = take(n);
@@ -146,15 +145,21 @@ int configure(bmpc_handle* h) {
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
     h->team = TEAM;
     h->teams_per_cta = CTA / TEAM;
-    bool in_smem = h->rt.nDb > 0 && pd_bytes <= 96 * 1024;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        layout_smem(h, in_smem);
+    // staging policy: Pd in shared memory only when small (it is re-read from L1/L2 otherwise); for CTA teams keep
+    // the per-CTA footprint low enough for several CTAs per SM; the packed Hessian leaves shared memory last
+    const size_t pd_limit = TEAM >= 64 ? 24 * 1024 : 96 * 1024;
+    bool in_smem = h->rt.nDb > 0 && pd_bytes <= pd_limit;
+    bool hv_smem = true;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        layout_smem(h, in_smem, hv_smem);
         h->smem_bytes = h->sm.total * 8 * h->teams_per_cta;
         if (h->smem_bytes <= max_optin) break;
-        if (!in_smem) return fail(BMPC_ERR_UNSUPPORTED, "problem too large for shared memory (%d B per CTA)", h->smem_bytes);
-        in_smem = false;
+        if (in_smem) { in_smem = false; continue; }
+        if (hv_smem) { hv_smem = false; continue; }
+        return fail(BMPC_ERR_UNSUPPORTED, "problem too large for shared memory (%d B per CTA)", h->smem_bytes);
     }
     h->pd_in_smem = in_smem;
+    h->hv_in_smem = hv_smem;
     CK(cudaFuncSetAttribute(bmpc::step_kernel<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmpc::step_kernel<TEAM>, CTA, h->smem_bytes));
@@ -915,6 +920,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.rt = h->rt;
     P.sm = h->sm;
     P.pd_in_smem = h->pd_in_smem; P.pd_is_ev = h->pd_is_ev; P.has_terminal = h->has_terminal_rows;
+    P.hv_in_smem = h->hv_in_smem ? 1 : 0;
     P.M_dense = h->M_dense; P.has_L = h->has_L;
     const long sh = d.shared_model ? 0 : 1;
     P.sEv = sh * h->nEv2; P.sH = sh * h->nHp2; P.sK = sh * nY * nx; P.sV = sh * nY * nu; P.sB = sh * nY;

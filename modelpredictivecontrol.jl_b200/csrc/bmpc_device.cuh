@@ -52,6 +52,7 @@ struct StepParams {
     RowTables rt;
     SmemLayout sm;
     int pd_in_smem, pd_is_ev, has_terminal, M_dense, has_L;
+    int hv_in_smem;          // 0: the packed Hessian stays in HBM/L2 (large n), read where it is used
     long sPd, sEv, sH, sK, sV, sB, sG, sJ, skx, svx, sbx, sgx, sjx, sM, sL, suop, syop;
     const double *Pd, *Ev, *Hv, *Lv, *Hee, *K, *V, *B, *G, *J, *kx, *vx, *bx, *gx, *jx, *Mw, *Lw,
         *uop, *yop, *sbase, *dbound;
@@ -147,6 +148,13 @@ struct Team {
 };
 
 __device__ __forceinline__ int pidx(int i, int j) { return (i * (i + 1)) / 2 + j; }  // i >= j
+
+// FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8).  Lane l = 4*g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
 // In-place packed (row-major lower) Cholesky, column-Crout with redundant diagonal; invd = 1/L_jj.
 // Returns number of guarded (non-positive) pivots (uniform across the team).
@@ -320,19 +328,76 @@ __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, dou
         c.ybd[k] = g;
     }
     T.sync();
-    const int npair = nz * (nz + 1) / 2;
-    for (int p = T.tid; p < npair; p += TEAM) {
-        const int i = rt.pair_i[p], j = rt.pair_j[p];
-        const double* ci = c.Pd + (long)nDb * i;
-        const double* cj = c.Pd + (long)nDb * j;
-        double a0 = 0.0, a1 = 0.0;
-        int k = 0;
-        for (; k + 1 < nDb; k += 2) {
-            a0 = fma(ci[k] * c.wd[k], cj[k], a0);
-            a1 = fma(ci[k + 1] * c.wd[k + 1], cj[k + 1], a1);
+    if constexpr (TEAM >= 32) {
+        // ---- FP64 tensor pipe: Phi_vv = Hv + Pd' diag(wd) Pd by 8x8x4 DMMA tiles.  Each warp of the team takes
+        // 16x16 blocks (2x2 tiles) of the lower triangle; the A fragments (Pd columns of the block's rows) and the
+        // B fragments (wd * Pd columns of the block's columns) come straight from Pd (column-major: a fragment is
+        // 8 columns x 4 consecutive rows = full 32-byte sectors), which sits in shared memory or in L1/L2.
+        const int warp = T.tid >> 5, lane = T.tid & 31, fg = lane >> 2, ft = lane & 3;
+        constexpr int NW = TEAM / 32;
+        const int nblk = (nz + 15) >> 4;
+        const int ntask = nblk * (nblk + 1) / 2;
+        for (int task = warp; task < ntask; task += NW) {
+            int bi = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) / 2 <= task) ++bi;
+            while (bi * (bi + 1) / 2 > task) --bi;
+            const int bj = task - bi * (bi + 1) / 2;
+            const int ia = 16 * bi + fg, ib = ia + 8, ja = 16 * bj + fg, jb = ja + 8;
+            const bool oia = ia < nz, oib = ib < nz, oja = ja < nz, ojb = jb < nz;
+            const double* pia = c.Pd + (long)nDb * (oia ? ia : 0) + ft;
+            const double* pib = c.Pd + (long)nDb * (oib ? ib : 0) + ft;
+            const double* pja = c.Pd + (long)nDb * (oja ? ja : 0) + ft;
+            const double* pjb = c.Pd + (long)nDb * (ojb ? jb : 0) + ft;
+            const bool diag = bi == bj;
+            double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
+#pragma unroll 4
+            for (int k0 = 0; k0 < nDb; k0 += 4) {
+                const bool okk = k0 + ft < nDb;
+                const int kk = okk ? k0 : 0;  // clamp (the value is masked)
+                const double w = okk ? c.wd[k0 + ft] : 0.0;
+                const double a0 = (okk && oia) ? pia[kk] : 0.0;
+                const double a1 = (okk && oib) ? pib[kk] : 0.0;
+                double b0, b1;
+                if (diag) {
+                    b0 = a0 * w;
+                    b1 = a1 * w;
+                } else {
+                    b0 = ((okk && oja) ? pja[kk] : 0.0) * w;
+                    b1 = ((okk && ojb) ? pjb[kk] : 0.0) * w;
+                }
+                dmma884(c00a, c00b, a0, b0);
+                dmma884(c10a, c10b, a1, b0);
+                dmma884(c11a, c11b, a1, b1);
+                if (!diag) dmma884(c01a, c01b, a0, b1);
+            }
+            // write back the lower-triangle entries this lane holds: rows i = 16bi + 8ti + fg, cols j = 16bj + 8tj + 2ft (+1)
+            auto put = [&](int i, int j, double v0, double v1) {
+                if (i < nz) {
+                    if (j <= i && j < nz) c.Phi[pidx(i, j)] = c.Hv[pidx(i, j)] + v0;
+                    if (j + 1 <= i && j + 1 < nz) c.Phi[pidx(i, j + 1)] = c.Hv[pidx(i, j + 1)] + v1;
+                }
+            };
+            const int jc = 16 * bj + 2 * ft;
+            put(ia, jc, c00a, c00b);
+            put(ib, jc, c10a, c10b);
+            put(ib, jc + 8, c11a, c11b);
+            if (!diag) put(ia, jc + 8, c01a, c01b);
         }
-        if (k < nDb) a0 = fma(ci[k] * c.wd[k], cj[k], a0);
-        c.Phi[p] = c.Hv[p] + a0 + a1;
+    } else {
+        const int npair = nz * (nz + 1) / 2;
+        for (int p = T.tid; p < npair; p += TEAM) {
+            const int i = rt.pair_i[p], j = rt.pair_j[p];
+            const double* ci = c.Pd + (long)nDb * i;
+            const double* cj = c.Pd + (long)nDb * j;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < nDb; k += 2) {
+                a0 = fma(ci[k] * c.wd[k], cj[k], a0);
+                a1 = fma(ci[k + 1] * c.wd[k + 1], cj[k + 1], a1);
+            }
+            if (k < nDb) a0 = fma(ci[k] * c.wd[k], cj[k], a0);
+            c.Phi[p] = c.Hv[p] + a0 + a1;
+        }
     }
     T.sync();
     // 1-/2-variable rows: gather per variable (each packed entry has exactly one writer)
@@ -573,12 +638,13 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
         const double* gLv = P.Lv + (long)inst * P.sH;
         const double* gPd = P.Pd + (long)inst * P.sPd;
         const int lv_ok = P.lv_ok[P.sH ? inst : 0];
+        c.Hv = P.hv_in_smem ? base + P.sm.Hv : const_cast<double*>(gHv);
         if (T.tid == 0) {
             fence_proxy_async();
-            uint32_t bytes = (uint32_t)P.nHp2 * 8u * 2u;
+            uint32_t bytes = (uint32_t)P.nHp2 * 8u * (P.hv_in_smem ? 2u : 1u);
             if (P.pd_in_smem) bytes += (uint32_t)P.nPd2 * 8u;
             mbar_arrive_expect_tx(bar, bytes);
-            tma_bulk_g2s(c.Hv, gHv, (uint32_t)P.nHp2 * 8u, bar);
+            if (P.hv_in_smem) tma_bulk_g2s(c.Hv, gHv, (uint32_t)P.nHp2 * 8u, bar);
             tma_bulk_g2s(c.Phi, gLv, (uint32_t)P.nHp2 * 8u, bar);
             if (P.pd_in_smem) tma_bulk_g2s(sm_Pd, gPd, (uint32_t)P.nPd2 * 8u, bar);
         }

@@ -50,12 +50,6 @@ struct WarpDims {
     static constexpr int LDP = 8 * NB + 2;
 };
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 constexpr unsigned WFULL = 0xffffffffu;
 
 __device__ __forceinline__ double wsum(double v) {
