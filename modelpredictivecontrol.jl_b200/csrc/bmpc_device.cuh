@@ -161,6 +161,49 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int TEAM>
 __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, double* invd, int n) {
     int bad = 0;
+    if constexpr (TEAM >= 64) {
+        // CTA teams: right-looking, ONE barrier per column.  Column k is used unscaled for the trailing update
+        // (A_ij -= A_ik A_jk / d_k) and scaled to L during the next column's phase, when nobody reads it any more.
+        // Threads form a TX x TY grid over the trailing triangle: TY rows per pass, TX threads along a row.
+        constexpr int TX = TEAM >= 256 ? 8 : 4, TY = TEAM / TX;
+        const int tx = T.tid % TX, ty = T.tid / TX;
+        double rs_prev = 0.0, dk_prev = 0.0;
+        for (int k = 0; k <= n; ++k) {
+            T.sync();  // trailing updates of column k-1 are complete: column k is final
+            double invdk = 0.0, rs = 0.0, dk = 0.0;
+            if (k < n) {
+                dk = A[pidx(k, k)];
+                if (!(dk > 1e-280)) {
+                    dk = 1e200;
+                    ++bad;
+                }
+                rs = rsqrt(dk);
+                invdk = rs * rs;
+                const int rem = n - k - 1;
+                for (int a = ty; a < rem; a += TY) {
+                    const int i = k + 1 + a;
+                    const double lik = A[pidx(i, k)] * invdk;
+                    double* row = A + pidx(i, k + 1);
+                    int pj = pidx(k + 1 + tx, k);  // A[k+1+b][k], advanced by TX rows per step
+                    for (int b = tx; b <= a; b += TX) {
+                        row[b] = fma(-lik, A[pj], row[b]);
+                        pj += TX * (k + 1 + b) + TX * (TX + 1) / 2;  // pidx(r+TX,k) - pidx(r,k) with r = k+1+b
+                    }
+                }
+            }
+            if (k > 0) {  // scale column k-1 (nobody reads it in this phase)
+                for (int i = k + T.tid; i < n; i += TEAM) A[pidx(i, k - 1)] *= rs_prev;
+                if (T.tid == 0) {
+                    A[pidx(k - 1, k - 1)] = dk_prev * rs_prev;
+                    invd[k - 1] = rs_prev;
+                }
+            }
+            rs_prev = rs;
+            dk_prev = dk;
+        }
+        T.sync();
+        return bad;
+    }
     for (int j = 0; j < n; ++j) {
         const double* rj = A + pidx(j, 0);
         double dj = rj[j];
@@ -192,6 +235,66 @@ __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, doubl
 template <int TEAM>
 __device__ __forceinline__ void chol_solve(const Team<TEAM>& T, const double* L, const double* invd, double* b,
                                            int n) {
+    if constexpr (TEAM >= 64) {
+        // CTA teams: blocks of 32 unknowns; warp 0 solves the diagonal block on registers + shuffles (no barriers
+        // inside), then every thread takes one remaining row (forward) / column entry (backward) of the update.
+        const int warp = T.tid >> 5, lane = T.tid & 31;
+        T.sync();
+        for (int b0 = 0; b0 < n; b0 += 32) {  // forward: L y = b
+            const int nb = min(32, n - b0);
+            if (warp == 0) {
+                const bool ok = lane < nb;
+                const int i = ok ? b0 + lane : b0;
+                double bi = ok ? b[i] : 0.0;
+                const double inv = ok ? invd[i] : 0.0;
+                const double* ri = L + pidx(i, b0);
+                for (int j = 0; j < nb; ++j) {
+                    const double yj = __shfl_sync(0xffffffffu, bi * inv, j);
+                    if (lane > j && ok) bi = fma(-ri[j], yj, bi);
+                }
+                if (ok) b[i] = bi * inv;
+            }
+            T.sync();
+            for (int i = b0 + 32 + T.tid; i < n; i += TEAM) {
+                const double* ri = L + pidx(i, b0);
+                double a0 = b[i], a1 = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < 32; j += 2) {
+                    a0 = fma(-ri[j], b[b0 + j], a0);
+                    a1 = fma(-ri[j + 1], b[b0 + j + 1], a1);
+                }
+                b[i] = a0 + a1;
+            }
+            T.sync();
+        }
+        for (int b0 = ((n - 1) / 32) * 32; b0 >= 0; b0 -= 32) {  // backward: L' x = y
+            const int nb = min(32, n - b0);
+            if (warp == 0) {
+                const bool ok = lane < nb;
+                const int i = ok ? b0 + lane : b0;
+                double bi = ok ? b[i] : 0.0;
+                const double inv = ok ? invd[i] : 0.0;
+                for (int j = nb - 1; j >= 0; --j) {
+                    const double xj = __shfl_sync(0xffffffffu, bi * inv, j);
+                    if (lane < j) bi = fma(-L[pidx(b0 + j, i)], xj, bi);
+                }
+                if (ok) b[i] = bi * inv;
+            }
+            T.sync();
+            for (int i = T.tid; i < b0; i += TEAM) {
+                double a0 = b[i], a1 = 0.0;
+                int pj = pidx(b0, i);
+                for (int j = 0; j < nb; ++j) {
+                    const double t = L[pj] * b[b0 + j];
+                    if (j & 1) a1 -= t; else a0 -= t;
+                    pj += b0 + j + 1;
+                }
+                b[i] = a0 + a1;
+            }
+            T.sync();
+        }
+        return;
+    }
     for (int j = 0; j < n; ++j) {  // forward
         T.sync();
         const double yj = b[j] * invd[j];
