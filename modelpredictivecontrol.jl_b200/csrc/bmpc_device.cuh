@@ -161,8 +161,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int TEAM>
 __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, double* invd, int n) {
     int bad = 0;
-    if constexpr (TEAM >= 64) {
-        // CTA teams: right-looking, ONE barrier per column.  Column k is used unscaled for the trailing update
+    if (TEAM >= 64 && n < 56) {
+        // CTA teams, small n: right-looking, ONE barrier per column.  Column k is used unscaled for the trailing update
         // (A_ij -= A_ik A_jk / d_k) and scaled to L during the next column's phase, when nobody reads it any more.
         // Threads form a TX x TY grid over the trailing triangle: TY rows per pass, TX threads along a row.
         constexpr int TX = TEAM >= 256 ? 8 : 4, TY = TEAM / TX;
@@ -203,6 +203,134 @@ __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, doubl
         }
         T.sync();
         return bad;
+    }
+    if constexpr (TEAM >= 64) {
+        // CTA teams: blocked right-looking Cholesky with panels of 16 columns (LAPACK potrf structure):
+        //   (a) warp 0 factors the 16x16 diagonal block on registers + shuffles,
+        //   (b) every thread takes one row below the block and solves it against the block (16-step forward
+        //       substitution on registers, block entries broadcast from shared memory),
+        //   (c) the trailing matrix is updated on the FP64 tensor pipe: A22 -= L21 L21' by 8x8x4 DMMA tiles,
+        //       16x16 output blocks per warp, fragments read from the packed factor in shared memory.
+        // Three barriers per panel instead of two per column.
+        constexpr int NBK = 16, NW = TEAM / 32;
+        const int warp = T.tid >> 5, lane = T.tid & 31, fg = lane >> 2, ft = lane & 3;
+        for (int c0 = 0; c0 < n; c0 += NBK) {
+            const int nb = min(NBK, n - c0);
+            T.sync();
+            if (warp == 0) {  // (a)
+                const bool valid = lane < nb;
+                const int ri = c0 + (valid ? lane : 0);
+                const double* src = A + pidx(ri, c0);
+                double row[NBK];
+#pragma unroll
+                for (int j = 0; j < NBK; ++j) row[j] = (valid && j <= lane) ? src[j] : 0.0;
+                double pdiag = 1.0, ldiag = 1.0, inv = 1.0;
+#pragma unroll
+                for (int j = 0; j < NBK; ++j)
+                    if (j == lane && valid) pdiag = row[j];
+#pragma unroll
+                for (int k = 0; k < NBK; ++k) {
+                    double dk = __shfl_sync(0xffffffffu, pdiag, k);
+                    if (!(dk > 1e-280)) {
+                        dk = 1e200;
+                        if (k < nb) ++bad;
+                    }
+                    const double rs = rsqrt(dk);
+                    const double lik = (lane > k && valid) ? row[k] * rs : 0.0;
+                    if (lane == k) {
+                        inv = rs;
+                        ldiag = dk * rs;
+                    }
+                    row[k] = lik;
+                    pdiag = fma(-lik, lik, pdiag);
+#pragma unroll
+                    for (int j = k + 1; j < NBK; ++j) {
+                        const double ljk = __shfl_sync(0xffffffffu, lik, j);
+                        row[j] = fma(-lik, ljk, row[j]);
+                    }
+                }
+                if (valid) {
+                    double* dst = A + pidx(ri, c0);
+#pragma unroll
+                    for (int j = 0; j < NBK; ++j)
+                        if (j < lane) dst[j] = row[j];
+                    dst[lane] = ldiag;
+                    invd[ri] = inv;
+                }
+            }
+            const int r0 = c0 + nb;
+            if (r0 >= n) break;  // (uniform) last panel: nothing below
+            T.sync();
+            for (int i = r0 + T.tid; i < n; i += TEAM) {  // (b)
+                double* ai = A + pidx(i, c0);
+                double a[NBK];
+#pragma unroll
+                for (int j = 0; j < NBK; ++j) a[j] = j < nb ? ai[j] : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < NBK; ++kk) {
+                    if (kk < nb) {
+                        const double* lk = A + pidx(c0 + kk, c0);
+                        double sacc = a[kk];
+#pragma unroll
+                        for (int pp = 0; pp < kk; ++pp) sacc = fma(-a[pp], lk[pp], sacc);
+                        a[kk] = sacc * invd[c0 + kk];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NBK; ++j)
+                    if (j < nb) ai[j] = a[j];
+            }
+            T.sync();
+            {  // (c)
+                const int nrem = n - r0;
+                const int nblk = (nrem + 15) >> 4;
+                const int ntask = nblk * (nblk + 1) / 2;
+                for (int task = warp; task < ntask; task += NW) {
+                    int bi = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
+                    while ((bi + 1) * (bi + 2) / 2 <= task) ++bi;
+                    while (bi * (bi + 1) / 2 > task) --bi;
+                    const int bj = task - bi * (bi + 1) / 2;
+                    const bool diag = bi == bj;
+                    const int ia = r0 + 16 * bi + fg, ib = ia + 8, ja = r0 + 16 * bj + fg, jb = ja + 8;
+                    const bool oia = ia < n, oib = ib < n, oja = ja < n, ojb = jb < n;
+                    const double* pia = A + pidx(oia ? ia : r0, c0) + ft;
+                    const double* pib = A + pidx(oib ? ib : r0, c0) + ft;
+                    const double* pja = A + pidx(oja ? ja : r0, c0) + ft;
+                    const double* pjb = A + pidx(ojb ? jb : r0, c0) + ft;
+                    double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
+#pragma unroll
+                    for (int s4 = 0; s4 < NBK; s4 += 4) {
+                        const bool okc = s4 + ft < nb;
+                        const double a0 = (okc && oia) ? -pia[s4] : 0.0;
+                        const double a1 = (okc && oib) ? -pib[s4] : 0.0;
+                        double b0, b1;
+                        if (diag) {
+                            b0 = -a0;
+                            b1 = -a1;
+                        } else {
+                            b0 = (okc && oja) ? pja[s4] : 0.0;
+                            b1 = (okc && ojb) ? pjb[s4] : 0.0;
+                        }
+                        dmma884(c00a, c00b, a0, b0);
+                        dmma884(c10a, c10b, a1, b0);
+                        dmma884(c11a, c11b, a1, b1);
+                        if (!diag) dmma884(c01a, c01b, a0, b1);
+                    }
+                    auto add = [&](int i, int j, double v0, double v1) {
+                        if (i < n) {
+                            if (j <= i) A[pidx(i, j)] += v0;
+                            if (j + 1 <= i) A[pidx(i, j + 1)] += v1;
+                        }
+                    };
+                    const int jc = r0 + 16 * bj + 2 * ft;
+                    add(ia, jc, c00a, c00b);
+                    add(ib, jc, c10a, c10b);
+                    add(ib, jc + 8, c11a, c11b);
+                    if (!diag) add(ia, jc + 8, c01a, c01b);
+                }
+            }
+        }
+        return __syncthreads_or(bad);  // barrier + team-uniform "some pivot was guarded" flag (warp 0 counted them)
     }
     for (int j = 0; j < n; ++j) {
         const double* rj = A + pidx(j, 0);
@@ -431,7 +559,64 @@ __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, dou
         c.ybd[k] = g;
     }
     T.sync();
-    if constexpr (TEAM >= 32) {
+    if constexpr (TEAM >= 256) {
+        // ---- large n: same DMMA product with 32x32 output blocks (4x4 tiles) per warp: 8 fragment loads feed 16
+        // DMMAs (10 on diagonal blocks), halving the L1/L2 traffic per flop of the 16x16 scheme below.
+        const int warp = T.tid >> 5, lane = T.tid & 31, fg = lane >> 2, ft = lane & 3;
+        constexpr int NW = TEAM / 32;
+        const int nblk = (nz + 31) >> 5;
+        const int ntask = nblk * (nblk + 1) / 2;
+        for (int task = warp; task < ntask; task += NW) {
+            int bi = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) / 2 <= task) ++bi;
+            while (bi * (bi + 1) / 2 > task) --bi;
+            const int bj = task - bi * (bi + 1) / 2;
+            const bool diag = bi == bj;
+            const double* pa[4];
+            const double* pb[4];
+            bool oa[4], ob[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ia = 32 * bi + 8 * u + fg, ja = 32 * bj + 8 * u + fg;
+                oa[u] = ia < nz;
+                ob[u] = ja < nz;
+                pa[u] = c.Pd + (long)nDb * (oa[u] ? ia : 0) + ft;
+                pb[u] = c.Pd + (long)nDb * (ob[u] ? ja : 0) + ft;
+            }
+            double acc[4][4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+#pragma unroll 2
+            for (int k0 = 0; k0 < nDb; k0 += 4) {
+                const bool okk = k0 + ft < nDb;
+                const int kk = okk ? k0 : 0;
+                const double w = okk ? c.wd[k0 + ft] : 0.0;
+                double av[4], bv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) av[u] = (okk && oa[u]) ? pa[u][kk] : 0.0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) bv[v] = (diag ? av[v] : ((okk && ob[v]) ? pb[v][kk] : 0.0)) * w;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        if (!diag || v <= u) dmma884(acc[u][v][0], acc[u][v][1], av[u], bv[v]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (diag && v > u) continue;
+                    const int i = 32 * bi + 8 * u + fg, j = 32 * bj + 8 * v + 2 * ft;
+                    if (i < nz) {
+                        if (j <= i && j < nz) c.Phi[pidx(i, j)] = c.Hv[pidx(i, j)] + acc[u][v][0];
+                        if (j + 1 <= i && j + 1 < nz) c.Phi[pidx(i, j + 1)] = c.Hv[pidx(i, j + 1)] + acc[u][v][1];
+                    }
+                }
+        }
+    } else if constexpr (TEAM >= 32) {
         // ---- FP64 tensor pipe: Phi_vv = Hv + Pd' diag(wd) Pd by 8x8x4 DMMA tiles.  Each warp of the team takes
         // 16x16 blocks (2x2 tiles) of the lower triangle; the A fragments (Pd columns of the block's rows) and the
         // B fragments (wd * Pd columns of the block's columns) come straight from Pd (column-major: a fragment is
