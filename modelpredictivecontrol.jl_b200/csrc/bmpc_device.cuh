@@ -748,6 +748,7 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
     T.sync();
     status = ST_ITERATION_LIMIT;
     double rp_inf = 0.0, best_merit = 1e300;
+    int stall = 0;
     for (int it = 0; it <= P.max_iter; ++it) {
         // residuals
         hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
@@ -844,6 +845,11 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         }
         T.sync();
         const double a = fmin(1.0, 0.99 * max_step(T, c, m));
+        // infeasibility: on an infeasible problem the multipliers of the conflicting rows diverge and the step length
+        // collapses (1e-9, 1e-15, ...) while the primal residual stays where it is; two such steps end the solve
+        // (status INFEASIBLE below) instead of running to the iteration cap.  Feasible problems never step below 1e-3.
+        stall = (a < 1e-8 && e_p > 1e-6 * hscale) ? stall + 1 : 0;
+        if (stall >= 2) break;
         for (int j = T.tid; j < n; j += TEAM) c.x[j] = fma(a, c.dx[j], c.x[j]);
         for (int k = T.tid; k < nDb; k += TEAM) c.yb[k] = fma(a, c.ybd[k], c.yb[k]);
         for (int r = T.tid; r < m; r += TEAM) {

@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(32, 16)
             }
             status = ST_ITERATION_LIMIT;
             double best_merit = 1e300, rp_inf = 0.0;
+            int stall = 0;
             // r_p = Gx + s - h is carried by its recurrence r_p <- (1 - a) r_p (ds = -r_p - G dx is formed from the
             // COMPUTED dx, so the recurrence is exact up to rounding whatever the accuracy of the linear solve)
             double rpR[RPL];
@@ -632,6 +633,10 @@ __global__ void __launch_bounds__(32, 16)
                 // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
                 const double tau = fmin(fmax(0.99, 1.0 - ratio), 1.0 - 1e-6);  // never exactly onto the boundary
                 const double a = rho > tau ? tau / rho : 1.0;
+                // infeasibility: two collapsed steps with the primal residual still open end the solve (ipm_solve,
+                // bmpc_device.cuh)
+                stall = (a < 1e-8 && rp_inf > 1e-6 * hscale) ? stall + 1 : 0;
+                if (__any_sync(WFULL, stall >= 2)) break;
                 x = fma(a, dx, x);
                 const double oma = 1.0 - a;
 #pragma unroll
