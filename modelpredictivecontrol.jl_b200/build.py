@@ -1,5 +1,5 @@
 """Builds libbmpc.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
-The translation units (API + general kernel, and one unit per small-kernel specialisation) are
+The translation units (API + general kernel, and one unit per warp-kernel specialisation) are
 compiled in parallel and linked into one shared object."""
 import concurrent.futures
 import glob
@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(os.environ.get("TMPDIR", "/tmp"), "bmpc_build_objs")  # outside the tree: only libbmpc.so travels
 UNITS = [os.path.join(CSRC, "bmpc_api.cu"), os.path.join(CSRC, "bmpc_mhe_api.cu")] + sorted(
-    glob.glob(os.path.join(CSRC, "small_inst_*.cu")) + glob.glob(os.path.join(CSRC, "warp_inst_*.cu")))
+    glob.glob(os.path.join(CSRC, "warp_inst_*.cu")))
 HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))) + [
     os.path.join(os.path.dirname(HERE), "include", "bmpc.h")]
 OUT = os.path.join(HERE, "libbmpc.so")

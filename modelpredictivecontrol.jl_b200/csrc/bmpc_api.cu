@@ -23,7 +23,6 @@
 #include "bmpc_device.cuh"
 #include "bmpc_setup.cuh"
 #include "bmpc_model.cuh"
-#include "bmpc_small_registry.h"
 #include "bmpc_warp_registry.h"
 
 namespace bmpc_host {
@@ -67,9 +66,7 @@ struct bmpc_handle {
     // launch geometry
     int team = 0, teams_per_cta = 0, grid = 0, smem_bytes = 0;
     bool dirty = true;      // launch geometry / derived arrays must be rebuilt before the next step
-    const bmpc::SmallEntry* small = nullptr;  // chosen small-kernel specialisation, or null (general kernel)
-    bmpc::SmallParams sp{};
-    DevBuf<double> PdR, HvS, LvS, lam_ws;
+    DevBuf<double> lam_ws;
     DevBuf<int> ws_flag;
     // warp-per-controller kernel (bmpc_warp.cuh)
     const bmpc::WarpEntry* warp = nullptr;
@@ -169,98 +166,6 @@ int configure(bmpc_handle* h) {
     return BMPC_OK;
 }
 
-const std::vector<bmpc::SmallEntry>& small_registry() {
-    static std::vector<bmpc::SmallEntry> reg = [] {
-        std::vector<bmpc::SmallEntry> v;
-        bmpc::small_register_02(v);
-        bmpc::small_register_04(v);
-        bmpc::small_register_06(v);
-        bmpc::small_register_08(v);
-        bmpc::small_register_10(v);
-        bmpc::small_register_12(v);
-        bmpc::small_register_15(v);
-        return v;
-    }();
-    return reg;
-}
-
-int configure_small(bmpc_handle* h, const bmpc::SmallEntry& E) {
-    const int nzt = E.nzt, nt = E.nzt + E.neps, DS = E.ds, SS = E.ss;
-    const int nz = h->nz, nDb = h->rt.nDb, nY = h->nY, nx = h->d.nxhat;
-    const int nsr = h->rt.nS + h->d.neps;
-    const int ldp = (nzt + 1) & ~1, ldn = nt | 1;
-    bmpc::SmallLayout& L = h->sp.L;
-    L.nDbp = even(nDb);
-    L.nPdR = L.nDbp * ldp;
-    L.nHS = even(nzt * ldp);
-    int o = 0;
-    auto take = [&](int cnt) { int at = o; o += even(std::max(cnt, 1)); return at; };
-    L.Pd = take(L.nPdR);
-    L.Hv = take(L.nHS);
-    L.Lb = take(std::max(L.nHS, even(nt * ldn)));
-    L.vbuf = take(16);
-    L.wd = take(16 * DS);
-    L.wp = take(32 * DS);
-    L.ws = take(16 * SS);
-    L.bb = take(16);
-    L.F = take(nY);
-    L.tY = take(nY);
-    L.fx = take(nx);
-    L.xh = take(nx);
-    L.lu = take(h->d.nu);
-    L.dd = take(h->d.nd);
-    L.Dh = take(h->d.nd * h->d.Hp);
-    L.bar = take(2);
-    L.team_total = o;
-    o = 0;
-    L.t_sigd = take(nDb); L.t_cd = take(nDb); L.t_srcd = take((nDb + 1) / 2);
-    L.t_sigs = take(nsr); L.t_cs = take(nsr); L.t_i1 = take((nsr + 1) / 2); L.t_i2 = take((nsr + 1) / 2);
-    L.t_ch = take((nsr + 1) / 2); L.t_vptr = take((nzt + 2) / 2);
-    const int nnz = 2 * h->rt.nS;
-    L.t_vrow = take((nnz + 1) / 2); L.t_vsgn = take((nnz + 1) / 2);
-    L.tab_total = o;
-    const int teams = 4;  // 64 threads
-    h->smem_bytes = (L.team_total * teams + L.tab_total) * 8;
-    int max_optin = 0;
-    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
-    if (h->smem_bytes > max_optin) return BMPC_ERR_UNSUPPORTED;
-    CK(cudaFuncSetAttribute(E.func, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, E.func, 64, h->smem_bytes));
-    if (occ < 1) return BMPC_ERR_UNSUPPORTED;
-    h->team = 16;
-    h->teams_per_cta = teams;
-    const int need = (h->d.N + teams - 1) / teams;
-    h->grid = std::max(1, std::min(need, occ * h->num_sms));
-    h->small = &E;
-    h->pd_in_smem = true;
-    h->sp.nsr = nsr;
-    // row-major padded copies (TMA sources)
-    const long NM = h->NM;
-    h->sp.sPdR = h->d.shared_model ? 0 : L.nPdR;
-    h->sp.sHS = h->d.shared_model ? 0 : L.nHS;
-    CK(h->PdR.alloc((size_t)NM * std::max(L.nPdR, 2)));
-    CK(h->HvS.alloc((size_t)NM * L.nHS));
-    CK(h->LvS.alloc((size_t)NM * L.nHS));
-    CK(cudaMemsetAsync(h->PdR.p, 0, (size_t)NM * std::max(L.nPdR, 2) * 8, h->stream));
-    CK(cudaMemsetAsync(h->HvS.p, 0, (size_t)NM * L.nHS * 8, h->stream));
-    CK(cudaMemsetAsync(h->LvS.p, 0, (size_t)NM * L.nHS * 8, h->stream));
-    const double* pdsrc = h->pd_is_ev ? h->Ev.p : h->Pd.p;
-    const long spd = h->pd_is_ev ? h->nEv2 : h->nPd2;
-    bmpc::k_make_small<<<(unsigned)NM, 128, 0, h->stream>>>(pdsrc, spd, nDb, h->Hv.p, h->Lv.p, h->nHp2, h->PdR.p, (long)L.nPdR,
-                                                          h->HvS.p, h->LvS.p, (long)L.nHS, nz, nzt, ldp);
-    h->launches++;
-    CK(cudaGetLastError());
-    CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(h->rt.m, 1))));
-    CK(h->ws_flag.alloc((size_t)h->d.N));
-    CK(cudaMemsetAsync(h->ws_flag.p, 0, (size_t)h->d.N * sizeof(int), h->stream));
-    if (const char* e = getenv("BMPC_WARM")) h->warm_start = atoi(e);
-    h->sp.PdR = h->PdR.p;
-    h->sp.HvS = h->HvS.p;
-    h->sp.LvS = h->LvS.p;
-    return BMPC_OK;
-}
-
 const std::vector<bmpc::WarpEntry>& warp_registry() {
     static std::vector<bmpc::WarpEntry> reg = [] {
         std::vector<bmpc::WarpEntry> v;
@@ -344,11 +249,8 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
 }
 
 int configure_launch(bmpc_handle* h) {
-    h->small = nullptr;
     h->warp = nullptr;
     const int forced = h->d.team ? h->d.team : (getenv("BMPC_TEAM") ? atoi(getenv("BMPC_TEAM")) : 0);
-    const int nsr = h->rt.nS + h->d.neps;
-    const bool one_sided = h->rt.nDr == h->rt.nDb;
     const int m_rows = h->rt.nS + h->rt.nDr;
     if (forced == 0 && h->n <= 16 && m_rows <= 128 && !h->M_dense && h->have_predmat &&
         !(getenv("BMPC_NO_WARP") && atoi(getenv("BMPC_NO_WARP")))) {
@@ -362,20 +264,6 @@ int configure_launch(bmpc_handle* h) {
             if (rc == BMPC_OK) return rc;
             if (rc != BMPC_ERR_UNSUPPORTED) return rc;
             h->warp = nullptr;
-        }
-    }
-    if (forced == 0 && h->n <= 16 && one_sided && !h->M_dense && h->have_predmat) {
-        // smallest specialisation that holds the controller (padding with dummy variables is exact)
-        const bmpc::SmallEntry* best = nullptr;
-        for (const bmpc::SmallEntry& E : small_registry()) {
-            if (E.neps != h->d.neps || E.nzt < h->nz || h->rt.nDb > 16 * E.ds || nsr > 16 * E.ss) continue;
-            if (!best || E.nzt < best->nzt || (E.nzt == best->nzt && E.ds < best->ds)) best = &E;
-        }
-        if (best) {
-            int rc = configure_small(h, *best);
-            if (rc == BMPC_OK) return rc;
-            if (rc != BMPC_ERR_UNSUPPORTED) return rc;
-            h->small = nullptr;
         }
     }
     switch (choose_team(h)) {
@@ -402,6 +290,12 @@ int finalize(bmpc_handle* h) {
     }
     int rc = configure_launch(h);
     if (rc != BMPC_OK) return rc;
+    if (!h->warp) {  // the general kernel keeps the multipliers of the previous period too (IPM warm start)
+        CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(h->rt.m, 1))));
+        CK(h->ws_flag.alloc((size_t)h->d.N));
+        CK(cudaMemsetAsync(h->ws_flag.p, 0, (size_t)h->d.N * sizeof(int), h->stream));
+        if (const char* e = getenv("BMPC_WARM")) h->warm_start = atoi(e);
+    }
     CK(cudaStreamSynchronize(s));
     h->dirty = false;
     return BMPC_OK;
@@ -748,11 +642,10 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     for (int i = 0; i < nx; ++i)
         add_dense(nY + i, pat[oX + i], pat[oX + nx + i], softv(S.c_xmin, i, 1.0), softv(S.c_xmax, i, 1.0), 6, 7, i);
     const int nDr = (int)dr_base.size(), nDb = (int)pd_src.size();
-    if (neps) {
-        sig.push_back(0.0);
-        cc.push_back(1.0);
-    }
-    const int m = nS + nDr + neps;
+    // The reference's eps >= 0 row is NOT compiled: every softness weight is non-negative (checked below, as in
+    // construct.jl:456-506), so a point with eps < 0 is dominated by the same point with eps = 0 -- the optimum is
+    // unchanged, and the row's vanishing multiplier would only slow the interior-point iteration down.
+    const int m = nS + nDr;
     if (h->stepped && m != h->rt.m) return fail(BMPC_ERR_STATE, "constraint structure changed after the first step");
     for (double c : cc)
         if (c < 0) return fail(BMPC_ERR_ARG, "softness weights should be non-negative (construct.jl:456)");
@@ -835,9 +728,6 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     rt.pair_i = h->t_pi.p;
     rt.pair_j = h->t_pj.p;
     h->has_terminal_rows = any_x;
-    h->sp.has_pair_rows = 0;
-    for (int g = 0; g < nS; ++g)
-        if (s_i2[g] >= 0) h->sp.has_pair_rows = 1;
     h->pd_is_ev = (nDb == nY) && !any_x;  // dense base rows are exactly the rows of Ev, in order
     h->nPd2 = even(nDb * nz);
     if (!h->pd_is_ev && nDb > 0) {
@@ -936,7 +826,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.counters = h->counters.p;
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
-    P.use_ws = ((h->small || h->warp) && h->warm_start && h->lam_ws.p) ? 1 : 0;
+    P.use_ws = (h->warm_start && h->lam_ws.p) ? 1 : 0;
     cudaError_t le;
     if (h->warp) {
         bmpc::WarpParams Q = h->wp;
@@ -946,8 +836,6 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         le = h->warp->launch(P, Q, h->grid, h->smem_bytes, h->stream);
         h->order_cur ^= 1;
         h->order_valid = true;
-    } else if (h->small) {
-        le = h->small->launch(P, h->sp, h->grid, h->smem_bytes, h->stream);
     } else
     switch (h->team) {
         case 8: le = launch_step<8>(h, P); break;
@@ -1011,8 +899,8 @@ int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
     out[1] = h->teams_per_cta;
     out[2] = h->grid;
     out[3] = h->smem_bytes;
-    // >= 200: warp-per-controller kernel, NT = value - 200; >= 100: 16-lane small kernel, NZT = value - 100
-    out[4] = h->warp ? 200 + h->warp->nt : (h->small ? 100 + h->small->nzt : (int)h->pd_in_smem);
+    // >= 200: warp-per-controller kernel, NT = value - 200; else 0/1 = dense rows staged in shared memory
+    out[4] = h->warp ? 200 + h->warp->nt : (int)h->pd_in_smem;
     out[5] = h->rt.m;
     out[6] = h->rt.nS;
     out[7] = h->rt.nDr;

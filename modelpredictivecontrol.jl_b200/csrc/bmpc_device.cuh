@@ -734,16 +734,18 @@ __device__ __forceinline__ double max_step(const Team<TEAM>& T, const Ctx& c, in
 
 // Mehrotra predictor-corrector on  min 1/2 x'Hx + q'x  s.t. Gx + s = h  (structured rows, see RowTables).
 // In: c.x = starting point, c.yb = Pd*x_v, c.s = h - Gx (raw slacks), c.q, c.h, c.Hv; out: c.x, status, iters.
+// lam0: multipliers of the previous period (warm start; c.x / c.yb / c.s then describe the previous solution), or nullptr
 template <int TEAM>
 __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, const StepParams& P, double Hee, double qs,
-                                          double hscale, int& status, int& iters) {
+                                          double hscale, int& status, int& iters, const double* lam0 = nullptr) {
     const RowTables& rt = P.rt;
     const int n = P.n, m = rt.m, nDb = rt.nDb;
     const double mu0 = fmax(1e-2 * qs * hscale / (double)m, 1e-8);
+    const double lmin = 1e-4 * qs / hscale;
     for (int r = T.tid; r < m; r += TEAM) {
         const double sv = fmax(c.s[r], 1e-2 * hscale);
         c.s[r] = sv;
-        c.lam[r] = mu0 / sv;
+        c.lam[r] = lam0 ? fmax(lam0[r], lmin) : mu0 / sv;
     }
     T.sync();
     status = ST_ITERATION_LIMIT;
@@ -844,7 +846,9 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
             c.dl[r] = -(rc + c.lam[r] * dsv) / c.s[r];
         }
         T.sync();
-        const double a = fmin(1.0, 0.99 * max_step(T, c, m));
+        // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap (never exactly 1)
+        const double tau = fmin(fmax(0.99, 1.0 - mua / mu), 1.0 - 1e-6);
+        const double a = fmin(1.0, tau * max_step(T, c, m));
         // infeasibility: on an infeasible problem the multipliers of the conflicting rows diverge and the step length
         // collapses (1e-9, 1e-15, ...) while the primal residual stays where it is; two such steps end the solve
         // (status INFEASIBLE below) instead of running to the iteration cap.  Feasible problems never step below 1e-3.
@@ -1101,8 +1105,32 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
         int iters = 0;
         const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
         if (!feasible) {
-            // ---- stage 3: Mehrotra predictor-corrector ----
-            ipm_solve(T, c, P, Hee, qs, hscale, status, iters);
+            // ---- stage 3: Mehrotra predictor-corrector, warm-started from the previous period when it converged ----
+            const double* lam0 = nullptr;
+            if (P.use_ws && P.ws_flag[inst] != 0) {
+                lam0 = P.lam_ws + (long)inst * P.ws_stride;
+                const double* gZp = P.Z + (long)inst * n;
+                for (int j = T.tid; j < nz; j += TEAM) {  // previous Z̃ in level coordinates
+                    double a = 0.0;
+                    for (int l = j % nu; l <= j; l += nu) a += gZp[l];
+                    c.x[j] = a;
+                }
+                if (neps && T.tid == 0) c.x[nz] = gZp[nz];
+                T.sync();
+                dense_apply(T, c, c.x, c.yb);
+                T.sync();
+                for (int r = T.tid; r < m; r += TEAM) c.s[r] = c.h[r] - row_gx(c, r, c.x, c.yb);
+                T.sync();
+            }
+            ipm_solve(T, c, P, Hee, qs, hscale, status, iters, lam0);
+            if (P.use_ws) {
+                const bool keep = status == ST_OPTIMAL && iters > 0;
+                if (keep)
+                    for (int r = T.tid; r < m; r += TEAM) P.lam_ws[(long)inst * P.ws_stride + r] = c.lam[r];
+                if (T.tid == 0) P.ws_flag[inst] = keep ? 1 : 0;
+            }
+        } else if (P.use_ws && T.tid == 0) {
+            P.ws_flag[inst] = 0;
         }
         // ---- stage 4: getinput! ----
         double* gZ = P.Z + (long)inst * n;

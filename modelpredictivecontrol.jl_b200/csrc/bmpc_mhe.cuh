@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
         const double* bnd[6] = {Q.xmin + (long)inst * nx, Q.xmax + (long)inst * nx, Q.wmin + (long)inst * nx,
                                 Q.wmax + (long)inst * nx, Q.vmin + (long)inst * nym, Q.vmax + (long)inst * nym};
         double hmax = 0.0;
-        for (int r = T.tid; r < m - neps; r += TEAM) {
+        for (int r = T.tid; r < m; r += TEAM) {  // (the redundant eps >= 0 row is not compiled)
             const int kind = Q.row_kind[r], bi = Q.row_bidx[r];
             const double sg = rt.row_sig[r];
             const int side = sg > 0 ? 1 : 0;
@@ -272,7 +272,6 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
             c.h[r] = hv;
             hmax = fmax(hmax, fabs(hv));
         }
-        if (neps && T.tid == 0) c.h[m - 1] = 0.0;
         const double hscale = 1.0 + T.max(hmax);
         double qmax = 0.0;
         T.sync();

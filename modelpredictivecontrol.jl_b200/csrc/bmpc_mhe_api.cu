@@ -102,11 +102,8 @@ int compile_rows(bmhe_handle* h, int Nk) {
     for (int t = 0; t < nym * Nk; ++t)
         add_dense(-t - 1, f[4 * nx + t % nym], f[4 * nx + nym + t % nym], soft(h->cv_min, t % nym), soft(h->cv_max, t % nym), 3, t);
     const int nDr = (int)dr_base.size(), nDb = (int)pd_src.size();
-    if (neps) {
-        sig.push_back(0.0);
-        cc.push_back(1.0);
-    }
-    const int m = nS + nDr + neps;
+    // no eps >= 0 row: the softness weights are non-negative, so eps < 0 is never optimal (see bmpc_set_constraints)
+    const int m = nS + nDr;
     std::vector<int> var_ptr(nz + 1, 0), var_row(nS), var_sgn(nS, 1);
     for (int g = 0; g < nS; ++g) var_ptr[s_i1[g] + 1]++;
     for (int j = 0; j < nz; ++j) var_ptr[j + 1] += var_ptr[j];
@@ -332,6 +329,10 @@ int bmhe_set_constraints(bmhe_handle* h, const double* xmin, const double* xmax,
             }
     }
     if (h->Nk > 0 && fin != h->fin) return fail(BMPC_ERR_STATE, "Cannot modify +-Inf constraints after the first step");
+    for (const double* cs : {c_x, c_w, c_v})
+        if (cs && h->neps)
+            for (int k = 0; k < 2 * (cs == c_v ? nym : nx); ++k)
+                if (cs[k] < 0) return fail(BMPC_ERR_ARG, "softness weights should be non-negative (mhe/construct.jl setconstraint!)");
     auto setc = [&](std::vector<double>& dst, const double* src, int len) {
         for (int k = 0; k < len; ++k) dst[k] = (src && h->neps) ? src[k] : 0.0;
     };

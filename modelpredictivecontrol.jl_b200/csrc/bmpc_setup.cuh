@@ -134,33 +134,6 @@ __global__ void k_getinfo(const double* __restrict__ Ev, long sE, const double* 
     }
 }
 
-// Row-major padded copies for the small kernel (TMA sources), padded to NZT variables:
-//   PdR[k*ldp + j] = Pd[k + nDb*j] (j < nz; 0 beyond; one zero row appended when nDb is odd);
-//   HvS[i*ldp + j] = Hv(i,j) (full symmetric; identity on the dummy variables);
-//   LvS[i*ldp + j] = Lv(i,j) for j < i, and 1/Lv(i,i) on the diagonal (1 on the dummy variables).
-__global__ void k_make_small(const double* __restrict__ Pd, long sPd, int nDb, const double* __restrict__ Hv,
-                             const double* __restrict__ Lv, int nHp2, double* __restrict__ PdR, long sPdR,
-                             double* __restrict__ HvS, double* __restrict__ LvS, long sHS, int nz, int nzt, int ldp) {
-    const long inst = blockIdx.x;
-    for (int e = threadIdx.x; e < nDb * nz; e += blockDim.x) {
-        const int k = e % nDb, j = e / nDb;
-        PdR[inst * sPdR + (long)k * ldp + j] = Pd[inst * sPd + e];
-    }
-    for (int e = threadIdx.x; e < nzt * nzt; e += blockDim.x) {
-        const int i = e / nzt, j = e % nzt;
-        double h = (i == j) ? 1.0 : 0.0, l = (i == j) ? 1.0 : 0.0;
-        if (i < nz && j < nz) {
-            const int hi = i > j ? i : j, lo = i > j ? j : i;
-            h = Hv[inst * nHp2 + hi * (hi + 1) / 2 + lo];
-            l = 0.0;
-            if (j < i) l = Lv[inst * nHp2 + i * (i + 1) / 2 + j];
-            if (j == i) l = 1.0 / Lv[inst * nHp2 + i * (i + 1) / 2 + i];
-        }
-        HvS[inst * sHS + (long)i * ldp + j] = h;
-        LvS[inst * sHS + (long)i * ldp + j] = l;
-    }
-}
-
 // Setup: dense row matrix Gt and extended Hessian / factor for the warp kernel (one CTA per instance).
 //   Gt[r, :] = [sigma_r * p_r, -c_r]:  sparse rows p_r = e_i1 - e_i2, dense rows p_r = Pd[base_r, :]
 //   H_ext = blockdiag(Hv, Hee, I_dummy);  L_ext = its Cholesky factor with 1/L_ii on the diagonal

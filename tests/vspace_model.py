@@ -98,11 +98,8 @@ def build_qp_v(mpc):
         if neps:
             g[-1] = -r["c"]
         G.append(g)
-    if neps:
-        g = np.zeros(n)
-        g[-1] = -1.0
-        G.append(g)
-        h.append(0.0)
+    # the reference's eps >= 0 row is not compiled: all softness weights are >= 0 (construct.jl:456-506), so
+    # eps < 0 is never optimal and the row is redundant (its vanishing multiplier only slows the IPM down)
     G = np.array(G).reshape(-1, n)
     return H, q, G, np.array(h), Dt
 
@@ -157,7 +154,8 @@ def ipm_device_model(H, q, G, h, max_iter=60, tol=1e-9, neps=1, verbose=False, t
         dx = solve(-rd - G.T @ ((lam * rp - rc) / s))
         ds = -rp - G @ dx
         dl = -(rc + lam * ds) / s
-        a = min(1.0, 0.99 * _alpha(s, ds, lam, dl))
+        tau = min(max(0.99, 1.0 - mu_a / mu), 1.0 - 1e-6)  # fraction to the boundary -> 1 as the affine step closes the gap
+        a = min(1.0, tau * _alpha(s, ds, lam, dl))
         x, s, lam = x + a * dx, s + a * ds, lam + a * dl
         if not np.isfinite(x).all():
             status = 2
