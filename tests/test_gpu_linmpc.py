@@ -82,6 +82,33 @@ def test_c2_shapes_parity():
     print("C2 worst", worst, b.launch_info())
 
 
+@pytest.mark.parametrize("shape", ["n81", "c4"])
+def test_mid_and_large_shapes_parity(shape):
+    """CTA-team paths of the general kernel: n = 81 (128 threads, blocked DMMA Cholesky, 16x16-block DMMA Hessian build)
+    and the config C4 recipe (8x8 plant, Hp=50, Hc=20 -> n = 161, 256 threads, packed Hessian left in HBM/L2, 32x32-block
+    DMMA build; hard u box + hard du box + soft ymin/ymax), warm-started from period to period."""
+    from helpers import random_plant
+    rng = np.random.default_rng(44)
+    nx, nu, ny, Hp, Hc = (8, 8, 4, 20, 10) if shape == "n81" else (16, 8, 8, 50, 20)
+    mpcs, plants = [], []
+    for _ in range(3):
+        m = random_plant(rng, nx, nu, ny)
+        mpc = LinMPC(m, Hp=Hp, Hc=Hc, Cwt=1e5)
+        if shape == "c4":
+            mpc.setconstraint(umin=[-1.0] * nu, umax=[1.0] * nu, dumin=[-0.2] * nu, dumax=[0.2] * nu,
+                              ymin=[-1.2] * ny, ymax=[0.8] * ny)
+        else:
+            mpc.setconstraint(umin=[-1.0] * nu, umax=[1.0] * nu, ymax=[0.8] * ny)
+        mpcs.append(mpc)
+        plants.append(LinModel(m.A, m.Bu, m.C))
+    b = batch_from_oracle(mpcs)
+    worst, n_active = closed_loop_compare(mpcs, plants, b, rng, steps=6, switch=3)
+    assert n_active > 6
+    info = b.launch_info()
+    assert info["team"] == (128 if shape == "n81" else 256)
+    print(shape, "worst", worst, info)
+
+
 def test_reference_known_answers_on_gpu():
     """test/3_test_predictive_control.jl:93-106 through the CUDA path (Hp=1000, Hc=1, Nwt=0)."""
     A, B, C = zoh_first_order(5, 2, 3.0)
