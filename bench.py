@@ -146,7 +146,7 @@ def main():
                           "setpoint steps +-1 every 25 periods, closed loop (plant = model, SteadyKalmanFilter)",
               "instances_per_gpu": N, "nu": nu, "ny": ny, "Hp": Hp, "Hc": Hc, "n_decision": nu * Hc + 1,
               "rows_reference": 2 * nu * Hp + ny * Hp + 1, "l2": "flushed (256 MiB memset) before every timed launch",
-              "parallelism": f"{world} independent shard(s) of {N} instances" + (", NCCL all-gather of Ztilde per step" if world > 1 else "")}
+              "parallelism": f"{world} independent shard(s) of {N} instances"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -199,13 +199,33 @@ def main():
     tI = torch.zeros((N,), dtype=torch.int32, device=dev)
     gather = torch.zeros((world, N, n), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    # Collection of the moves on every rank (north_star: "all-gather only to collect ΔŨ").  Preferred: FUSED -- the
+    # gather buffers live in symmetric memory (peer-mapped over NVLink) and the step kernel's epilogue stores Z̃ into
+    # every peer's buffer; the only extra work per step is a device-side barrier.  Fallback: ncclAllGather.
+    symm, gather_mode = None, "none"
+    if world > 1:
+        gather_mode = "ncclAllGather of Ztilde after every step"
+        if os.environ.get("BMPC_FUSED_GATHER", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                gsym = symm_mem.empty((world, N, n), dtype=torch.float64, device=dev)
+                gsym.zero_()
+                symm = symm_mem.rendezvous(gsym, dist.group.WORLD)
+                b.set_gather([int(symm.buffer_ptrs[p]) for p in range(world)], rank)
+                gather_mode = "fused: step-kernel epilogue stores Ztilde into every peer's symmetric-memory buffer (NVLink) + device barrier"
+            except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory path falls back to NCCL
+                sys.stderr.write(f"[bench] symmetric memory unavailable ({e!r}); using ncclAllGather\n")
+                symm = None
 
     def launch(k):
         b.step_device(dict(xhat0=tX[k].data_ptr(), lastu0=tLU[k].data_ptr(), ry=tRY[k].data_ptr(),
                            Ztilde=tZ[k].data_ptr(), u=tU.data_ptr(), J=tJ.data_ptr(), status=tS.data_ptr(),
                            iters=tI.data_ptr()))
         if world > 1:
-            dist.all_gather_into_tensor(gather.view(-1), tZ[k].reshape(-1))
+            if symm is not None:
+                symm.barrier()  # every peer's stores of this period have landed
+            else:
+                dist.all_gather_into_tensor(gather.view(-1), tZ[k].reshape(-1))
 
     tLU0, tZ0 = tLU.clone(), tZ.clone()
     BUSY_PASSES = 20
@@ -237,6 +257,12 @@ def main():
                 launch(k)
         torch.cuda.synchronize()
     launches_timed = (b.launch_count() - l_before) - BUSY_PASSES * K  # exclude the clock-sampling passes
+    gather_check = None
+    if world > 1 and symm is not None:
+        # the fused gather against ncclAllGather on the last period's Z̃
+        dist.all_gather_into_tensor(gather.view(-1), tZ[W + K - 1].reshape(-1))
+        torch.cuda.synchronize()
+        gather_check = bool(torch.equal(gather, gsym))
     dev_ms = sum(a.elapsed_time(c) for a, c in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,6 +343,7 @@ def main():
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "gpu_launches": int(launches_timed),
+        "gather": {"mode": gather_mode, "equals_ncclAllGather": gather_check},
         "solver": {"mean_ipm_iters_per_instance": mean_iters, "unconstrained_exit_fraction": frac_exit,
                    "non_optimal_statuses": n_nonopt, "tol": 1e-11, "launch": b.launch_info()},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,

@@ -163,6 +163,13 @@ int bmpc_step(bmpc_handle *h, const bmpc_step_io *io);
 /* getinfo quantities of the last step. */
 int bmpc_getinfo(bmpc_handle *h, const bmpc_info *info);
 
+/* Multi-GPU collection of the moves ("NCCL all-gather only to collect ΔŨ"), fused into the step:
+ * peer_bufs[p] is rank p's gather buffer [world x N x n] doubles, mapped into THIS process (CUDA IPC / symmetric
+ * memory, peer access over NVLink).  The step kernel's epilogue then stores every instance's Z̃ straight into slot
+ * (rank, instance) of every peer's buffer, so no separate collective kernel runs; the caller only needs a
+ * cross-rank barrier before reading the buffer.  world = 0 or peer_bufs = NULL switches it off.  world <= 8. */
+int bmpc_set_gather(bmpc_handle *h, void *const *peer_bufs, int32_t world, int32_t rank);
+
 /* Launch geometry actually used: {team, teams_per_cta, grid, smem_bytes_per_cta,
  * pd_in_smem, n_rows_m, n_sparse_rows, n_dense_rows} -- for DESIGN.md / bench reporting. */
 int bmpc_launch_info(bmpc_handle *h, int32_t out[8]);

@@ -165,6 +165,13 @@ class BatchLinMPC:
         io = _lib.StepIO(device_ptrs=1, sync=int(sync), **ptrs)
         check(_lib.lib().bmpc_step(self._h, C.byref(io)))
 
+    def set_gather(self, peer_ptrs, rank):
+        """Fused all-gather of Z̃: ``peer_ptrs[p]`` = device address (int) of rank p's [world, N, n] float64 gather
+        buffer mapped into this process (symmetric memory); the step kernel then stores Z̃ into every peer's buffer."""
+        world = len(peer_ptrs) if peer_ptrs else 0
+        arr = (C.c_void_p * max(world, 1))(*[C.c_void_p(int(p)) for p in (peer_ptrs or [])])
+        check(_lib.lib().bmpc_set_gather(self._h, arr if world else None, world, int(rank)))
+
     def set_stream(self, stream_ptr):
         check(_lib.lib().bmpc_set_stream(self._h, C.c_void_p(stream_ptr)))
 

@@ -74,6 +74,8 @@ struct bmpc_handle {
     DevBuf<double> Gw, HLw;
     DevBuf<int> order[2];
     DevBuf<unsigned int> ocnt;
+    double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather)
+    int zg_world = 0, zg_rank = 0;
     int order_cur = 0;       // order[order_cur] drives the next launch
     bool order_valid = false;
     int warm_start = 1;
@@ -828,6 +830,9 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
     P.use_ws = (h->warm_start && h->lam_ws.p) ? 1 : 0;
+    for (int pr = 0; pr < 8; ++pr) P.zg[pr] = h->zg[pr];
+    P.zg_world = h->zg_world;
+    P.zg_rank = h->zg_rank;
     cudaError_t le;
     if (h->warp) {
         bmpc::WarpParams Q = h->wp;
@@ -891,6 +896,22 @@ int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
     Y.release();
     U.release();
     X.release();
+    return BMPC_OK;
+}
+
+int bmpc_set_gather(bmpc_handle* h, void* const* peer_bufs, int32_t world, int32_t rank) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    if (world == 0 || !peer_bufs) {
+        h->zg_world = 0;
+        return BMPC_OK;
+    }
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BMPC_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
+    for (int pr = 0; pr < world; ++pr) {
+        if (!peer_bufs[pr]) return fail(BMPC_ERR_ARG, "null peer buffer");
+        h->zg[pr] = static_cast<double*>(peer_bufs[pr]);
+    }
+    h->zg_world = world;
+    h->zg_rank = rank;
     return BMPC_OK;
 }
 

@@ -68,6 +68,10 @@ struct StepParams {
     int* ws_flag;            // [N] 1 if lam_ws holds a converged IPM solution of the previous period
     int ws_stride, use_ws;
     int nHp2, nPd2;          // padded (even) sizes in doubles of packed Hv and of Pd: TMA needs 16-byte multiples
+    // fused all-gather of Z̃ (multi-GPU): every rank's gather buffer [world x N x n], peer-mapped over NVLink; the
+    // epilogue stores this instance's Z̃ straight into slot (rank, inst) of EVERY peer's buffer (world = 0: off)
+    double* zg[8];
+    int zg_world, zg_rank;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1155,6 +1159,14 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
         jacc = T.sum(jacc) + rconst;
         for (int j = T.tid; j < nz; j += TEAM) gZ[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
         if (neps && T.tid == 0) gZ[nz] = c.x[nz];
+        if (P.zg_world > 0) {  // fused all-gather: peer stores over NVLink
+            const long off = ((long)P.zg_rank * P.N + inst) * n;
+            for (int pr = 0; pr < P.zg_world; ++pr) {
+                double* dst = P.zg[pr] + off;
+                for (int j = T.tid; j < nz; j += TEAM) dst[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
+                if (neps && T.tid == 0) dst[nz] = c.x[nz];
+            }
+        }
         // q̃ in reference coordinates: q̃[j] = sum_{l' >= l(j)} q_v[l' nu + ch]
         for (int j = T.tid; j < nz; j += TEAM) {
             double a = 0.0;

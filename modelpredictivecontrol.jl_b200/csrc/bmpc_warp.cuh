@@ -670,6 +670,11 @@ __global__ void __launch_bounds__(32, 16)
         // q̃ in reference coordinates: q̃[j] = sum_{l' >= l(j), same input} q_v[l']
         w1[lane] = q;
         __syncwarp();
+        if (P.zg_world > 0 && lane < nr) {  // fused all-gather of Z̃: peer stores over NVLink (slot (rank, inst) of every peer)
+            const double zv = isreal ? x - (lane >= nu ? vx[lane - nu] : 0.0) : x;
+            const long off = ((long)P.zg_rank * P.N + inst) * nr + lane;
+            for (int pr = 0; pr < P.zg_world; ++pr) P.zg[pr][off] = zv;
+        }
         if (isreal) {
             gZ[lane] = x - (lane >= nu ? vx[lane - nu] : 0.0);
             double a = 0.0;

@@ -150,3 +150,20 @@ def test_resident_state_equals_host_state():
         uR = bR.step(xh, ry=ry, resident=k > 0).copy()
         assert (bR.status == bH.status).all()
         assert np.array_equal(uH, uR), k
+
+
+@pytest.mark.parametrize("team", [0, 128])
+def test_fused_gather_epilogue_single_rank(team):
+    """bmpc_set_gather with world = 1: the step kernel's epilogue writes Z̃ into slot (rank, instance) of the gather
+    buffer (the multi-GPU run checks the same stores against ncclAllGather inside bench.py)."""
+    import torch
+    mpcs, plants, rng = c1_controllers(12, seed=31)
+    b = batch_from_oracle(mpcs, team=team)
+    gbuf = torch.zeros((1, 12, b.n), dtype=torch.float64, device="cuda:0")
+    b.set_gather([gbuf.data_ptr()], 0)
+    for k in range(3):
+        xh = rng.standard_normal((12, mpcs[0].estim.nxhat)) * 0.3
+        b.step(xh, ry=rng.choice([-1.0, 1.0], (12, 2)))
+        torch.cuda.synchronize()
+        assert np.array_equal(gbuf[0].cpu().numpy(), b.Ztilde)
+    b.set_gather(None, 0)
