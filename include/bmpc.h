@@ -101,6 +101,9 @@ typedef struct {
                            * when given.  The state is the one left by the previous call (zeros after
                            * bmpc_create).                                                         */
     int32_t reserved;
+    const double *y0m;    /* N x nym  measured outputs, deviation (ym - yop[i_ym]).  Used instead of xhat0 (which must
+                           * then be NULL) after bmpc_set_estimator: the step kernel runs the observer's correction
+                           * before the controller and its prediction after it (one launch per control period).   */
 } bmpc_step_io;
 
 /* Diagnostics of the last step (= getinfo, execute.jl:145-198); any pointer may be NULL.
@@ -162,6 +165,20 @@ int bmpc_step(bmpc_handle *h, const bmpc_step_io *io);
 
 /* getinfo quantities of the last step. */
 int bmpc_getinfo(bmpc_handle *h, const bmpc_info *info);
+
+/* Fused observer -- SURVEY 8f-1.  SteadyKalmanFilter in direct form, as the reference's default LinMPC estimator:
+ *   preparestate!  x̂0 <- x̂0 + K̂ (y0m - Ĉm x̂0 - D̂dm d0)              (correct_estimate_obsv!, kalman.jl:284-296)
+ *   updatestate!   x̂0 <- Â x̂0 + B̂u u0 + B̂d d0 + (f̂op - x̂op)        (predict_estimate_obsv!, kalman.jl:298-309)
+ * run inside the step kernel around moveinput!, with x̂0 owned by the handle (estim.x̂0).  Matrices column-major,
+ * N x len or 1 x len when dims.shared_model = 1; K̂ is the steady-state gain (nxhat x nym), Ĉm/D̂dm the measured rows.
+ * Bdhat/Ddmhat may be NULL when nd = 0, fop_minus_xop may be NULL (= 0). */
+int bmpc_set_estimator(bmpc_handle *h, const double *Ahat, const double *Buhat, const double *Bdhat,
+                       const double *Cmhat, const double *Ddmhat, const double *Khat,
+                       const double *fop_minus_xop, int32_t nym);
+/* setstate! / read-back of the observer state: x̂0 (prediction for the next period) and the corrected estimate the
+ * last step used; either output may be NULL. */
+int bmpc_set_state(bmpc_handle *h, const double *xhat0);
+int bmpc_get_state(bmpc_handle *h, double *xhat0, double *xhat0_corrected);
 
 /* Multi-GPU collection of the moves ("NCCL all-gather only to collect ΔŨ"), fused into the step:
  * peer_bufs[p] is rank p's gather buffer [world x N x n] doubles, mapped into THIS process (CUDA IPC / symmetric

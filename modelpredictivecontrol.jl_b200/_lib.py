@@ -32,7 +32,8 @@ class StepIO(C.Structure):
     _fields_ = ([("xhat0", C.c_void_p), ("lastu0", C.c_void_p), ("ry", C.c_void_p), ("Rhat_y", C.c_void_p),
                  ("Rhat_u", C.c_void_p), ("d0", C.c_void_p), ("Dhat0", C.c_void_p), ("Ztilde", C.c_void_p),
                  ("u", C.c_void_p), ("J", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p),
-                 ("device_ptrs", C.c_int32), ("sync", C.c_int32), ("resident", C.c_int32), ("reserved", C.c_int32)])
+                 ("device_ptrs", C.c_int32), ("sync", C.c_int32), ("resident", C.c_int32), ("reserved", C.c_int32),
+                 ("y0m", C.c_void_p)])
 
 
 class MheDims(C.Structure):
@@ -55,7 +56,7 @@ _lib = None
 # every symbol include/bmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bmpc_set_stream", "bmpc_set_model",
            "bmpc_set_predmat", "bmpc_set_weights", "bmpc_set_oppoints", "bmpc_set_constraints", "bmpc_step",
-           "bmpc_getinfo", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
+           "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_launch_count"]
 
@@ -83,6 +84,9 @@ def lib():
     L.bmpc_step.argtypes = [C.c_void_p, C.POINTER(StepIO)]
     L.bmpc_getinfo.argtypes = [C.c_void_p, C.POINTER(Info)]
     L.bmpc_launch_info.argtypes = [C.c_void_p, c_int32_p]
+    L.bmpc_set_estimator.argtypes = [C.c_void_p] + [c_double_p] * 7 + [C.c_int32]
+    L.bmpc_set_state.argtypes = [C.c_void_p, c_double_p]
+    L.bmpc_get_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.bmpc_set_gather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]
     L.bmpc_launch_count.argtypes = [C.c_void_p]
     L.bmpc_launch_count.restype = C.c_int64

@@ -137,13 +137,35 @@ class BatchLinMPC:
                 setattr(S, k, dptr(a))
         check(_lib.lib().bmpc_set_constraints(self._h, *[dptr(a) for a in arrs], C.byref(S)))
 
+    def set_estimator(self, Ahat, Buhat, Cmhat, Khat, Bdhat=None, Ddmhat=None, fop_minus_xop=None):
+        """Fused SteadyKalmanFilter (bmpc_set_estimator): the handle owns x̂0; ``step(None, y0m=...)`` then runs
+        correct -> moveinput! -> predict in one launch."""
+        nx, nu, nd = self.nxhat, self.nu, self.nd
+        nym = np.asarray(Cmhat).shape[-2]
+        fx = None if fop_minus_xop is None else _vec(fop_minus_xop, self.NM, nx, "fop_minus_xop")
+        args = [self._mat(Ahat, nx, nx, "Ahat"), self._mat(Buhat, nx, nu, "Buhat"),
+                self._mat(Bdhat, nx, nd, "Bdhat") if nd else None, self._mat(Cmhat, nym, nx, "Cmhat"),
+                self._mat(Ddmhat, nym, nd, "Ddmhat") if nd else None, self._mat(Khat, nx, nym, "Khat"), fx]
+        check(_lib.lib().bmpc_set_estimator(self._h, *[dptr(a) for a in args], int(nym)))
+        self.nym = nym
+
+    def set_state(self, xhat0):
+        check(_lib.lib().bmpc_set_state(self._h, dptr(_vec(xhat0, self.N, self.nxhat, "xhat0"))))
+
+    def get_state(self):
+        """(x̂0 predicted for the next period, corrected x̂0 the last step used)."""
+        a, b = np.zeros((self.N, self.nxhat)), np.zeros((self.N, self.nxhat))
+        check(_lib.lib().bmpc_get_state(self._h, dptr(a), dptr(b)))
+        return a, b
+
     # ---- per-period call (= moveinput!) ----------------------------------------------------
-    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None, resident=False):
+    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None, resident=False, y0m=None):
         """One control period (moveinput!).  ``resident=True``: lastu0 and Z̃ stay in the handle between calls
         (they are fields of the reference controller, not arguments of moveinput!): only x̂0/ry go up and only
         u/status come back; self.lastu0, self.Ztilde, self.J, self.iters are then NOT refreshed."""
         N = self.N
-        x = _vec(xhat0, N, self.nxhat, "xhat0")
+        x = None if xhat0 is None else _vec(xhat0, N, self.nxhat, "xhat0")
+        ym = None if y0m is None else _vec(y0m, N, self.nym, "y0m")
         ryv = None if ry is None else _vec(ry, N, self.ny, "ry")
         Ry = None if Rhat_y is None else _vec(Rhat_y, N, self.nY, "Rhat_y")
         Ru = None if Rhat_u is None else _vec(Rhat_u, N, self.nU, "Rhat_u")
@@ -152,11 +174,11 @@ class BatchLinMPC:
         p = lambda a: None if a is None else a.ctypes.data
         if resident:
             io = _lib.StepIO(xhat0=p(x), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v), Dhat0=p(Dh), u=p(self.u),
-                             status=p(self.status), device_ptrs=0, sync=1, resident=1)
+                             status=p(self.status), device_ptrs=0, sync=1, resident=1, y0m=p(ym))
         else:
             io = _lib.StepIO(xhat0=p(x), lastu0=p(self.lastu0), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v),
                              Dhat0=p(Dh), Ztilde=p(self.Ztilde), u=p(self.u), J=p(self.J), status=p(self.status),
-                             iters=p(self.iters), device_ptrs=0, sync=1)
+                             iters=p(self.iters), device_ptrs=0, sync=1, y0m=p(ym))
         check(_lib.lib().bmpc_step(self._h, C.byref(io)))
         return self.u
 

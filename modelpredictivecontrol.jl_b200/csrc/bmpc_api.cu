@@ -74,6 +74,11 @@ struct bmpc_handle {
     DevBuf<double> Gw, HLw;
     DevBuf<int> order[2];
     DevBuf<unsigned int> ocnt;
+    // fused observer (bmpc_set_estimator): model matrices, state x̂0 (handle-owned), corrected estimate of the last step
+    bool have_estimator = false;
+    int nym = 0;
+    DevBuf<double> eA, eBu, eBd, eCm, eDdm, eK, efx, xstate, xcorr, y0m;
+    bool e_has_fx = false;
     double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather)
     int zg_world = 0, zg_rank = 0;
     int order_cur = 0;       // order[order_cur] drives the next launch
@@ -132,6 +137,7 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.Dh = take(h->d.nd * h->d.Hp);
     L.red = take(40);
     L.bar = take(2);
+    L.ev = take(h->d.ny);
     L.total = o;
     (void)nz;
 }
@@ -207,6 +213,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     L.dd = take(h->d.nd);
     L.Dh = take(h->d.nd * h->d.Hp);
     L.bar = take(2);
+    L.ev = take(h->d.ny);
     L.total = o;
     if (L.H + NT * E.ldh != L.L) return BMPC_ERR_UNSUPPORTED;  // H and its factor are one TMA copy
     h->smem_bytes = L.total * 8;
@@ -759,8 +766,10 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         if (rc != BMPC_OK) return rc;
     }
     const bool resident = io->resident != 0 && io->device_ptrs == 0;
-    if (!io->xhat0 || (!io->ry && !io->Rhat_y) || !io->u || !io->status)
-        return fail(BMPC_ERR_ARG, "xhat0, ry|Rhat_y, u, status are required");
+    const bool fused_est = io->xhat0 == nullptr && io->y0m != nullptr;
+    if (fused_est && !h->have_estimator) return fail(BMPC_ERR_STATE, "io.y0m needs bmpc_set_estimator");
+    if ((!io->xhat0 && !fused_est) || (!io->ry && !io->Rhat_y) || !io->u || !io->status)
+        return fail(BMPC_ERR_ARG, "xhat0 (or y0m with a fused estimator), ry|Rhat_y, u, status are required");
     if (!resident && (!io->lastu0 || !io->Ztilde || !io->iters))
         return fail(BMPC_ERR_ARG, "lastu0, Ztilde, iters are required unless io.resident = 1");
     if (d.nd > 0 && !io->d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
@@ -781,6 +790,16 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         return e;
     };
     CK(in(h->xhat0, io->xhat0, N * nx, &P.xhat0));
+    if (fused_est) {
+        CK(in(h->y0m, io->y0m, N * (size_t)h->nym, &P.y0m));
+        const long she = d.shared_model ? 0 : 1;
+        P.est_on = 1; P.nym = h->nym;
+        P.eA = h->eA.p; P.eBu = h->eBu.p; P.eBd = h->eBd.p; P.eCm = h->eCm.p; P.eDdm = h->eDdm.p; P.eK = h->eK.p;
+        P.efx = h->e_has_fx ? h->efx.p : nullptr;
+        P.s_eA = she * nx * nx; P.s_eBu = she * nx * nu; P.s_eBd = she * nx * nd; P.s_eCm = she * h->nym * nx;
+        P.s_eDdm = she * h->nym * nd; P.s_eK = she * nx * h->nym; P.s_efx = she * nx;
+        P.xstate = h->xstate.p; P.xcorr = h->xcorr.p;
+    }
     CK(in(h->ry, io->ry, N * ny, &P.ry));
     CK(in(h->Rhat_y, io->Rhat_y, N * nY, &P.Rhat_y));
     CK(in(h->Rhat_u, io->Rhat_u, N * nU, &P.Rhat_u));
@@ -855,7 +874,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     h->launches++;
     h->stepped = true;
     h->last_Z = P.Z;
-    h->last_xhat0 = P.xhat0;
+    h->last_xhat0 = fused_est ? h->xcorr.p : P.xhat0;
     if (!dev) {
         if (io->lastu0) CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
         if (io->Ztilde) CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
@@ -896,6 +915,55 @@ int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
     Y.release();
     U.release();
     X.release();
+    return BMPC_OK;
+}
+
+int bmpc_set_estimator(bmpc_handle* h, const double* Ahat, const double* Buhat, const double* Bdhat, const double* Cmhat,
+                       const double* Ddmhat, const double* Khat, const double* fop_minus_xop, int32_t nym) {
+    if (!h || !Ahat || !Buhat || !Cmhat || !Khat) return fail(BMPC_ERR_ARG, "null argument");
+    const bmpc_dims& d = h->d;
+    if (nym < 1 || nym > d.ny) return fail(BMPC_ERR_ARG, "nym must be 1..ny");
+    if (d.nd > 0 && (!Bdhat || !Ddmhat)) return fail(BMPC_ERR_ARG, "Bdhat and Ddmhat are required when nd > 0");
+    CK(cudaSetDevice(d.device));
+    cudaStream_t s = h->stream;
+    const size_t NM = (size_t)h->NM, nx = d.nxhat, nu = d.nu, nd = d.nd, N = d.N;
+    CK(h->eA.upload(Ahat, NM * nx * nx, s));
+    CK(h->eBu.upload(Buhat, NM * nx * nu, s));
+    if (nd) {
+        CK(h->eBd.upload(Bdhat, NM * nx * nd, s));
+        CK(h->eDdm.upload(Ddmhat, NM * nym * nd, s));
+    }
+    CK(h->eCm.upload(Cmhat, NM * nym * nx, s));
+    CK(h->eK.upload(Khat, NM * nx * nym, s));
+    h->e_has_fx = fop_minus_xop != nullptr;
+    if (fop_minus_xop) CK(h->efx.upload(fop_minus_xop, NM * nx, s));
+    CK(h->xstate.alloc(N * nx));
+    CK(h->xcorr.alloc(N * nx));
+    CK(cudaMemsetAsync(h->xstate.p, 0, N * nx * 8, s));
+    CK(cudaMemsetAsync(h->xcorr.p, 0, N * nx * 8, s));
+    CK(cudaStreamSynchronize(s));
+    h->nym = nym;
+    h->have_estimator = true;
+    return BMPC_OK;
+}
+
+int bmpc_set_state(bmpc_handle* h, const double* xhat0) {
+    if (!h || !xhat0) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->have_estimator) return fail(BMPC_ERR_STATE, "bmpc_set_state needs bmpc_set_estimator");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaMemcpyAsync(h->xstate.p, xhat0, (size_t)h->d.N * h->d.nxhat * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BMPC_OK;
+}
+
+int bmpc_get_state(bmpc_handle* h, double* xhat0, double* xhat0_corrected) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    if (!h->have_estimator) return fail(BMPC_ERR_STATE, "bmpc_get_state needs bmpc_set_estimator");
+    CK(cudaSetDevice(h->d.device));
+    const size_t bytes = (size_t)h->d.N * h->d.nxhat * 8;
+    if (xhat0) CK(cudaMemcpyAsync(xhat0, h->xstate.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (xhat0_corrected) CK(cudaMemcpyAsync(xhat0_corrected, h->xcorr.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return BMPC_OK;
 }
 

@@ -42,7 +42,7 @@ struct RowTables {
 
 struct SmemLayout {  // offsets in doubles inside a team's slice
     int Pd, Hv, Phi, x, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
-        xhat, lastu, dd, Dh, red, bar, total;
+        xhat, lastu, dd, Dh, red, bar, ev, total;
 };
 
 struct StepParams {
@@ -72,6 +72,12 @@ struct StepParams {
     // epilogue stores this instance's Z̃ straight into slot (rank, inst) of EVERY peer's buffer (world = 0: off)
     double* zg[8];
     int zg_world, zg_rank;
+    // fused observer (SteadyKalmanFilter, kalman.jl:284-309): correct before the step, predict after it.
+    // est_on: x̂0 is STATE OF THE HANDLE (xstate, in/out); the corrected estimate used by the step goes to xcorr.
+    int est_on, nym;
+    long s_eA, s_eBu, s_eBd, s_eCm, s_eDdm, s_eK, s_efx;
+    const double *eA, *eBu, *eBd, *eCm, *eDdm, *eK, *efx, *y0m;
+    double *xstate, *xcorr;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -443,6 +449,53 @@ __device__ __forceinline__ void chol_solve(const Team<TEAM>& T, const double* L,
         if (T.tid == 0) b[j] = xj;
     }
     T.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused SteadyKalmanFilter (direct form): the reference's correct_estimate_obsv! / predict_estimate_obsv!
+// (src/estimator/kalman.jl:284-309) on the team's shared-memory copy of x̂0.  tid/nth: thread index and count of the
+// team; sync: the team's barrier.  Matrices are column-major.
+// ------------------------------------------------------------------------------------------
+template <class Sync>
+__device__ __forceinline__ void skf_correct(const StepParams& P, long inst, int tid, int nth, double* sxh, const double* sd0,
+                                            double* sev, Sync sync) {
+    const int nx = P.nx, nym = P.nym, nd = P.nd;
+    const double* Cm = P.eCm + inst * P.s_eCm;
+    const double* K = P.eK + inst * P.s_eK;
+    for (int j = tid; j < nym; j += nth) {  // innovation v = y0m - Ĉm x̂0 - D̂dm d0
+        double v = P.y0m[inst * nym + j];
+        for (int k = 0; k < nx; ++k) v = fma(-Cm[j + (long)nym * k], sxh[k], v);
+        if (nd > 0) {
+            const double* Dm = P.eDdm + inst * P.s_eDdm;
+            for (int l = 0; l < nd; ++l) v = fma(-Dm[j + (long)nym * l], sd0[l], v);
+        }
+        sev[j] = v;
+    }
+    sync();
+    for (int i = tid; i < nx; i += nth) {  // x̂0 <- x̂0 + K̂ v
+        double a = sxh[i];
+        for (int j = 0; j < nym; ++j) a = fma(K[i + (long)nx * j], sev[j], a);
+        sxh[i] = a;
+        P.xcorr[inst * nx + i] = a;
+    }
+    sync();
+}
+// x̂0(k+1) = Â x̂0 + B̂u u0 + B̂d d0 + (f̂op - x̂op), written to the handle's state; u0[l] = su[l] + du[l]
+__device__ __forceinline__ void skf_predict(const StepParams& P, long inst, int tid, int nth, const double* sxh,
+                                            const double* su, const double* du, const double* sd0) {
+    const int nx = P.nx, nu = P.nu, nd = P.nd;
+    const double* A = P.eA + inst * P.s_eA;
+    const double* Bu = P.eBu + inst * P.s_eBu;
+    for (int i = tid; i < nx; i += nth) {
+        double a = P.efx ? P.efx[inst * P.s_efx + i] : 0.0;
+        for (int k = 0; k < nx; ++k) a = fma(A[i + (long)nx * k], sxh[k], a);
+        for (int l = 0; l < nu; ++l) a = fma(Bu[i + (long)nx * l], su[l] + du[l], a);
+        if (nd > 0) {
+            const double* Bd = P.eBd + inst * P.s_eBd;
+            for (int l = 0; l < nd; ++l) a = fma(Bd[i + (long)nx * l], sd0[l], a);
+        }
+        P.xstate[inst * nx + i] = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -953,7 +1006,8 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
         c.Pd = P.pd_in_smem ? sm_Pd : gPd;
 
         // ---- stage 1: initpred! ----
-        for (int k = T.tid; k < nx; k += TEAM) sm_xhat[k] = P.xhat0[(long)inst * nx + k];
+        const double* gxh = P.est_on ? P.xstate : P.xhat0;
+        for (int k = T.tid; k < nx; k += TEAM) sm_xhat[k] = gxh[(long)inst * nx + k];
         for (int k = T.tid; k < nu; k += TEAM) sm_lastu[k] = P.lastu0[(long)inst * nu + k];
         if (nd > 0) {
             for (int k = T.tid; k < nd; k += TEAM) sm_d0[k] = P.d0[(long)inst * nd + k];
@@ -961,6 +1015,7 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
                 sm_Dh[k] = P.Dhat0 ? P.Dhat0[(long)inst * nd * P.Hp + k] : P.d0[(long)inst * nd + (k % nd)];
         }
         T.sync();
+        if (P.est_on) skf_correct(P, inst, T.tid, TEAM, sm_xhat, sm_d0, base + P.sm.ev, [&] { T.sync(); });
         const double* gK = P.K + (long)inst * P.sK;
         const double* gV = P.V + (long)inst * P.sV;
         const double* gB = P.B + (long)inst * P.sB;
@@ -1173,6 +1228,7 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
             for (int l = j; l < nz; l += nu) a += c.q[l];
             P.qt_out[(long)inst * n + j] = a;
         }
+        if (P.est_on) skf_predict(P, inst, T.tid, TEAM, sm_xhat, sm_lastu, c.x, sm_d0);
         for (int k = T.tid; k < nu; k += TEAM) {
             const double du = c.x[k];  // DU_0 = v_0
             const double lu = sm_lastu[k];

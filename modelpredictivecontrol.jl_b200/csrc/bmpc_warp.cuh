@@ -25,7 +25,7 @@
 namespace bmpc {
 
 struct WarpLayout {  // per-warp shared-memory offsets (doubles)
-    int G, H, L, phi, vx, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, total;
+    int G, H, L, phi, vx, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, ev, total;
 };
 
 struct WarpParams {
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(32, 16)
             tma_bulk_g2s(sG, Q.Gw + (long)inst * Q.sGw, bG, bar);
         }
         // ---- stage 1: initpred!  (execute.jl:247-277) ----
-        for (int k = lane; k < nx; k += 32) sxh[k] = P.xhat0[(long)inst * nx + k];
+        const double* gxh = P.est_on ? P.xstate : P.xhat0;
+        for (int k = lane; k < nx; k += 32) sxh[k] = gxh[(long)inst * nx + k];
         for (int k = lane; k < nu; k += 32) slu[k] = P.lastu0[(long)inst * nu + k];
         if (nd > 0) {
             for (int k = lane; k < nd; k += 32) sd0[k] = P.d0[(long)inst * nd + k];
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(32, 16)
                 sDh[k] = P.Dhat0 ? P.Dhat0[(long)inst * nd * P.Hp + k] : P.d0[(long)inst * nd + (k % nd)];
         }
         __syncwarp();
+        if (__any_sync(WFULL, P.est_on != 0)) skf_correct(P, inst, lane, 32, sxh, sd0, smem + L.ev, [] { __syncwarp(); });
         const double* gK = P.K + (long)inst * P.sK;
         const double* gV = P.V + (long)inst * P.sV;
         const double* gB = P.B + (long)inst * P.sB;
@@ -685,6 +687,7 @@ __global__ void __launch_bounds__(32, 16)
             gZ[nz] = x;
             P.qt_out[(long)inst * nr + nz] = 0.0;
         }
+        if (__any_sync(WFULL, P.est_on != 0)) skf_predict(P, inst, lane, 32, sxh, slu, vx, sd0);
         if (lane < nu) {
             const double du = vx[lane];
             const double lu = slu[lane];

@@ -15,7 +15,7 @@ DEFAULT_HP0, DEFAULT_HC, DEFAULT_MWT, DEFAULT_NWT, DEFAULT_LWT, DEFAULT_CWT = 10
 
 class LinMPC:
     def __init__(self, model_or_estim, Hp=None, Hc=DEFAULT_HC, Mwt=None, Nwt=None, Lwt=None, Cwt=DEFAULT_CWT,
-                 device=0, team=0, max_iter=0, tol=0.0, **estim_kwargs):
+                 device=0, team=0, max_iter=0, tol=0.0, fused_estimator=False, **estim_kwargs):
         estim = model_or_estim if hasattr(model_or_estim, "Ahat") else SteadyKalmanFilter(model_or_estim, **estim_kwargs)
         model = estim.model
         self.estim, self.model = estim, model
@@ -46,6 +46,16 @@ class LinMPC:
                          C_dumax=np.zeros(nu * self.Hc), C_ymin=np.ones(ny * Hp), C_ymax=np.ones(ny * Hp),
                          c_xmin=np.ones(estim.nxhat), c_xmax=np.ones(estim.nxhat))
         self._solved = False
+        # fused_estimator: the SteadyKalmanFilter runs INSIDE the step kernel (correct before moveinput!, predict after
+        # it) and x̂0 lives in the handle: preparestate only notes ym, updatestate does nothing, one launch per period.
+        self.fused_estimator = bool(fused_estimator)
+        if self.fused_estimator:
+            if not hasattr(estim, "Khat"):
+                raise ValueError("fused_estimator needs a SteadyKalmanFilter")
+            b.set_estimator(estim.Ahat, estim.Buhat, estim.Cmhat, estim.Khat, estim.Bdhat if nd else None,
+                            estim.Ddmhat if nd else None, estim.fophat - estim.xophat)
+            b.set_state(estim.xhat0)
+            self._y0m = None
         self._push()
 
     @property
@@ -103,13 +113,21 @@ class LinMPC:
 
     # ---- estimator pass-throughs ----
     def preparestate(self, ym, d=None):
+        if self.fused_estimator:
+            m = self.model
+            self._y0m = _b(ym, m.N, (len(self.estim.i_ym),)) - m.yop[:, self.estim.i_ym]
+            return None
         return self.estim.preparestate(ym, d)
 
     def updatestate(self, u, ym, d=None):
+        if self.fused_estimator:
+            return None  # done by the step kernel
         return self.estim.updatestate(u, ym, d)
 
     def setstate(self, xhat):
         self.estim.setstate(xhat)
+        if self.fused_estimator:
+            self.batch.set_state(self.estim.xhat0)
         return self
 
     # ---- the hot path ----
@@ -125,6 +143,10 @@ class LinMPC:
             if Dhat is not None:
                 Dh0 = _b(Dhat, N, (m.nd * self.Hp,)) - np.tile(m.dop, (1, self.Hp))
         self._solved = True
+        if self.fused_estimator:
+            if self._y0m is None:
+                raise RuntimeError("call preparestate(ym) before moveinput with fused_estimator")
+            return self.batch.step(None, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0, y0m=self._y0m).copy()
         return self.batch.step(self.estim.xhat0, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0).copy()
 
     def getinfo(self):

@@ -167,3 +167,33 @@ def test_fused_gather_epilogue_single_rank(team):
         torch.cuda.synchronize()
         assert np.array_equal(gbuf[0].cpu().numpy(), b.Ztilde)
     b.set_gather(None, 0)
+
+
+@pytest.mark.parametrize("team", [0, 128])
+def test_fused_estimator_equals_host_estimator(team):
+    """SteadyKalmanFilter correct/predict fused into the step kernel (x̂0 owned by the handle) against the
+    host-side estimator mirror driving the same controller, and against the oracle's closed loop."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    N = 16
+    model, rng = workloads.random_plants(N, 4, 2, 2, seed=77)
+    mk = lambda fused: mpc_b200.LinMPC(model, Hp=20, Hc=5, Cwt=1e5, team=team, fused_estimator=fused).setconstraint(
+        umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+    mF, mH = mk(True), mk(False)
+    plantF = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N)
+    plantH = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N)
+    ry = workloads.setpoints(rng, N, 2, 30, period=10)
+    for k in range(30):
+        yF, yH = plantF.evaloutput(), plantH.evaloutput()
+        mF.preparestate(yF)
+        mH.preparestate(yH)
+        uF, uH = mF.moveinput(ry[k]), mH.moveinput(ry[k])
+        assert (mF.batch.status == 0).all() and (mH.batch.status == 0).all()
+        assert np.abs(uF - uH).max() < 1e-8, (k, np.abs(uF - uH).max())
+        xnext, xcorr = mF.batch.get_state()
+        assert np.abs(xcorr - mH.estim.xhat0).max() < 1e-8
+        plantF.updatestate(uF)
+        plantH.updatestate(uH)
+        mF.updatestate(uF, yF)
+        mH.updatestate(uH, yH)
+        assert np.abs(xnext - mH.estim.xhat0).max() < 1e-8
