@@ -166,7 +166,7 @@ int configure(bmpc_handle* h) {
     }
     h->pd_in_smem = in_smem;
     h->hv_in_smem = hv_smem;
-    CK(cudaFuncSetAttribute(bmpc::step_kernel<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(bmpc::step_kernel<TEAM>), h->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmpc::step_kernel<TEAM>, CTA, h->smem_bytes));
     if (occ < 1) return fail(BMPC_ERR_UNSUPPORTED, "step kernel does not fit on an SM (smem %d B)", h->smem_bytes);
@@ -220,7 +220,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
     if (h->smem_bytes > max_optin) return BMPC_ERR_UNSUPPORTED;
-    CK(cudaFuncSetAttribute(E.func, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(E.func), h->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, E.func, 32, h->smem_bytes));
     if (occ < 1) return BMPC_ERR_UNSUPPORTED;
@@ -1069,7 +1069,7 @@ int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, cons
     P.Hee = h->Hee.p; P.blk_start = h->t_blkstart.p;
     const size_t smem = (3 * nx * nx + 3 * ny * nx + 3 * nx * nu + 5 * nx + 2 * nx * nd + 8) * sizeof(double);
     if (smem > 200 * 1024) return fail(BMPC_ERR_UNSUPPORTED, "model too large for the on-device builder (use bmpc_set_predmat)");
-    CK(cudaFuncSetAttribute(bmpc::k_build_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(bmpc::k_build_model), (int)smem));
     bmpc::k_build_model<<<(unsigned)NM, 128, smem, s>>>(P);
     bmpc::k_chol_serial<<<(unsigned)((NM + 63) / 64), 64, 0, s>>>(h->Hv.p, h->Lv.p, h->lv_ok.p, (int)nz, h->nHp2, (int)NM);
     h->launches += 2;

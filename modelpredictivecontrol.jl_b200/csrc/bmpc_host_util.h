@@ -33,6 +33,16 @@ inline int fail(int code, const char* fmt, ...) {
 
 inline int even(int v) { return (v + 1) & ~1; }
 
+// The dynamic shared-memory limit of a kernel is a per-FUNCTION attribute shared by every handle of the process:
+// only ever raise it (a handle with a smaller footprint must not shrink the limit under another handle's launch).
+inline cudaError_t raise_dyn_smem(const void* func, int bytes) {
+    cudaFuncAttributes at{};
+    cudaError_t e = cudaFuncGetAttributes(&at, func);
+    if (e != cudaSuccess) return e;
+    if (bytes <= at.maxDynamicSharedSizeBytes) return cudaSuccess;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;

@@ -165,7 +165,7 @@ int compile_rows(bmhe_handle* h, int Nk) {
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
     if (h->smem_bytes > max_optin)
         return fail(BMPC_ERR_UNSUPPORTED, "MHE window too large for one CTA's shared memory (%d B): n = %d", h->smem_bytes, n);
-    CK(cudaFuncSetAttribute(bmpc::mhe_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(bmpc::mhe_step_kernel<256>), h->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmpc::mhe_step_kernel<256>, 256, h->smem_bytes));
     if (occ < 1) return fail(BMPC_ERR_UNSUPPORTED, "MHE kernel does not fit on an SM");

@@ -197,3 +197,21 @@ def test_fused_estimator_equals_host_estimator(team):
         mF.updatestate(uF, yF)
         mH.updatestate(uH, yH)
         assert np.abs(xnext - mH.estim.xhat0).max() < 1e-8
+
+
+def test_two_handles_with_different_footprints_interleave():
+    """Two handles that run the SAME kernel specialisation with different shared-memory footprints (Hp differs) step
+    alternately: the per-function dynamic shared-memory limit is only ever raised."""
+    rng = np.random.default_rng(8)
+    groups = []
+    for Hp in (24, 10):
+        mpcs = []
+        for _ in range(4):
+            m = random_plant(rng)
+            mpcs.append(OLinMPC(m, Hp=Hp, Hc=5, Cwt=1e5).setconstraint(umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8]))
+        groups.append((mpcs, batch_from_oracle(mpcs)))
+    for k in range(3):
+        for mpcs, b in groups:
+            xh = rng.standard_normal((4, mpcs[0].estim.nxhat)) * 0.3
+            b.step(xh, ry=rng.choice([-1.0, 1.0], (4, 2)))
+            assert (b.status == 0).all()
