@@ -229,7 +229,7 @@ def main():
                 dist.all_gather_into_tensor(gather.view(-1), tZ[k].reshape(-1))
 
     tLU0, tZ0 = tLU.clone(), tZ.clone()
-    BUSY_PASSES = 20
+    BUSY_PASSES = 60
     for k in range(W):
         flush.zero_()
         launch(k)
