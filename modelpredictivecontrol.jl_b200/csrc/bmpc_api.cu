@@ -113,6 +113,7 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.Hv = take(hv_in_smem ? h->nHp2 : 0);
     L.Phi = take(std::max(even(n * (n + 1) / 2), h->nHp2));
     L.x = take(n);
+    L.xb = take(n);
     L.q = take(n);
     L.rd = take(n);
     L.rhs = take(n);

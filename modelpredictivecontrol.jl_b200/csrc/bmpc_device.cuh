@@ -41,7 +41,7 @@ struct RowTables {
 };
 
 struct SmemLayout {  // offsets in doubles inside a team's slice
-    int Pd, Hv, Phi, x, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
+    int Pd, Hv, Phi, x, xb, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
         xhat, lastu, dd, Dh, red, bar, ev, total;
 };
 
@@ -504,7 +504,7 @@ __device__ __forceinline__ void skf_predict(const StepParams& P, long inst, int 
 struct Ctx {
     const StepParams* P;
     const double* Pd;  // dense base rows [nDb x nz], column-major, ld = nDb (shared or global memory)
-    double *x, *q, *rd, *rhs, *dx, *invd, *F, *tY, *fx, *yb, *ybd, *wd, *s, *lam, *h, *rp, *t, *ds, *dl, *Hv, *Phi;
+    double *x, *xb, *q, *rd, *rhs, *dx, *invd, *F, *tY, *fx, *yb, *ybd, *wd, *s, *lam, *h, *rp, *t, *ds, *dl, *Hv, *Phi;
 };
 
 // yout[k] = sum_j Pd[k, j] * v[j]
@@ -807,7 +807,7 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
     T.sync();
     status = ST_ITERATION_LIMIT;
     double rp_inf = 0.0, best_merit = 1e300;
-    int stall = 0;
+    int stall = 0, stagn = 0;
     for (int it = 0; it <= P.max_iter; ++it) {
         // residuals
         hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
@@ -849,6 +849,19 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         // the normal equations lose accuracy as lam/s spreads over > 1e24 and the dual residual
         // starts to grow again.
         if (best_merit <= 1e3 && merit >= best_merit) {
+            status = ST_OPTIMAL;
+            break;
+        }
+        // degenerate problems (many nearly active rows with vanishing multipliers): Phi's condition number passes 1e16
+        // before the tolerance is met and the dual residual starts to drift.  The best iterate is kept; three
+        // iterations without improvement from a KKT residual already below 1e-6 (relative) end the solve there.
+        if (merit < best_merit) {
+            stagn = 0;
+            for (int j = T.tid; j < n; j += TEAM) c.xb[j] = c.x[j];
+        } else if (++stagn >= 3 && best_merit <= 1e5) {
+            T.sync();
+            for (int j = T.tid; j < n; j += TEAM) c.x[j] = c.xb[j];
+            T.sync();
             status = ST_OPTIMAL;
             break;
         }
@@ -945,6 +958,7 @@ __global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM)
     Ctx c;
     c.P = &P;
     c.x = base + P.sm.x;
+    c.xb = base + P.sm.xb;
     c.q = base + P.sm.q;
     c.rd = base + P.sm.rd;
     c.rhs = base + P.sm.rhs;

@@ -17,7 +17,7 @@
 namespace bmpc {
 
 struct MheLayout {  // shared-memory offsets in doubles
-    int Hv, Phi, x, q, rd, rhs, dx, invd, yb, ybd, wd, s, lam, h, rp, t, ds, dl, F, FX, wrow, P, P2, K, M, red, total;
+    int Hv, Phi, x, xb, q, rd, rhs, dx, invd, yb, ybd, wd, s, lam, h, rp, t, ds, dl, F, FX, wrow, P, P2, K, M, red, total;
 };
 
 struct MheParams {
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
     T.red = smem + L.red;
     Ctx c;
     c.P = &P;
-    c.x = smem + L.x; c.q = smem + L.q; c.rd = smem + L.rd; c.rhs = smem + L.rhs; c.dx = smem + L.dx;
+    c.x = smem + L.x; c.xb = smem + L.xb; c.q = smem + L.q; c.rd = smem + L.rd; c.rhs = smem + L.rhs; c.dx = smem + L.dx;
     c.invd = smem + L.invd; c.yb = smem + L.yb; c.ybd = smem + L.ybd; c.wd = smem + L.wd; c.s = smem + L.s;
     c.lam = smem + L.lam; c.h = smem + L.h; c.rp = smem + L.rp; c.t = smem + L.t; c.ds = smem + L.ds;
     c.dl = smem + L.dl; c.Hv = smem + L.Hv; c.Phi = smem + L.Phi;

@@ -153,7 +153,7 @@ int compile_rows(bmhe_handle* h, int Nk) {
     const int nYm = nym * h->He, nXm = nx * h->He, nq = std::max(nx, nym);
     L.Hv = take(nz * (nz + 1) / 2);
     L.Phi = take(std::max(n * (n + 1) / 2, nXm + h->nd * (h->He + 1)));
-    L.x = take(n); L.q = take(n); L.rd = take(n); L.rhs = take(n); L.dx = take(n); L.invd = take(n);
+    L.x = take(n); L.xb = take(n); L.q = take(n); L.rd = take(n); L.rhs = take(n); L.dx = take(n); L.invd = take(n);
     L.yb = take(nDb); L.ybd = take(nDb); L.wd = take(nDb);
     L.s = take(m); L.lam = take(m); L.h = take(m); L.rp = take(m); L.t = take(m); L.ds = take(m); L.dl = take(m);
     L.F = take(nYm); L.FX = take(nXm); L.wrow = take(nYm);
