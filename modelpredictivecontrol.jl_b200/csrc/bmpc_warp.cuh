@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(32, 16)
                     const double* ga = sG + ft * LDG + fg;
                     const double* gb = sG + ft * LDG + (ok1 ? 8 + fg : 0);
                     const double* wdp = wd + ft;
-#pragma unroll 5
+#pragma unroll 3
                     for (int ks = 0; ks < KS; ++ks) {
                         const double a0 = ga[ks * 4 * LDG];
                         const double dk = wdp[ks * 4];
