@@ -297,13 +297,17 @@ def main():
     import ctypes as C
     from mpc_b200 import _lib
 
+    # zero-copy: the pinned host buffers are device-accessible, the step kernel reads x̂0, ry from and writes u, status to
+    # them directly over PCIe (io.host_mapped = 1; BMPC_E2E_ZEROCOPY=0 selects the library's explicit copies instead)
+    zero_copy = int(os.environ.get("BMPC_E2E_ZEROCOPY", "1") != "0")
+
     def host_step(k, resident=1):
         # resident = 1: u0(k-1) and the previous Z̃ are state of the handle, as mpc.lastu0 / mpc.Z̃ are fields of the
         # reference LinMPC; x̂0 is state of the fused observer: per call ym, ry go up, u and the status come back.
         src = dict(y0m=hY[k].ctypes.data) if fused_obs else dict(xhat0=hX[k].ctypes.data)
         if resident:
             io = _lib.StepIO(ry=hRY[k].ctypes.data, u=hU.ctypes.data, status=hS.ctypes.data, device_ptrs=0, sync=1,
-                             resident=1, **src)
+                             resident=1, host_mapped=zero_copy, **src)
         else:
             io = _lib.StepIO(lastu0=hLU[k].ctypes.data, ry=hRY[k].ctypes.data, Ztilde=hZ[k].ctypes.data, u=hU.ctypes.data,
                              J=hJ.ctypes.data, status=hS.ctypes.data, iters=hI.ctypes.data, device_ptrs=0, sync=1, **src)
@@ -369,7 +373,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "instance-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K, "copies_per_step": ("H2D ym, ry; D2H u, status (x̂0, u0(k-1), Z̃ are handle state: "
                 "fused SteadyKalmanFilter + io.resident = 1)" if fused_obs else "H2D xhat0, ry; D2H u, status (u0(k-1), Z̃ "
-                "are handle state, io.resident = 1)"), "u_vs_recorded_last_period": e2e_check},
+                "are handle state, io.resident = 1)") + ("; zero-copy: the kernel reads / writes the pinned host buffers "
+                "over PCIe (io.host_mapped = 1)" if zero_copy else "; cudaMemcpyAsync staging copies"), "u_vs_recorded_last_period": e2e_check},
         "clocks": clk.summary(),
         "wall_s_timed_region": t_wall1 - t_wall0,
     }

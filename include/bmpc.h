@@ -100,7 +100,10 @@ typedef struct {
                            * nothing is uploaded; lastu0, Ztilde, J and iters may be NULL and are download-only
                            * when given.  The state is the one left by the previous call (zeros after
                            * bmpc_create).                                                         */
-    int32_t reserved;
+    int32_t host_mapped;  /* host pointers only.  1: the caller's arrays are page-locked, device-accessible host memory
+                           * (cudaHostAlloc / cudaHostRegister under unified addressing): the step kernel reads the
+                           * inputs from and writes u, J, status, iters to them directly over PCIe -- zero-copy, no
+                           * staging copies or copy launches (lastu0 / Ztilde still follow `resident`).            */
     const double *y0m;    /* N x nym  measured outputs, deviation (ym - yop[i_ym]).  Used instead of xhat0 (which must
                            * then be NULL) after bmpc_set_estimator: the step kernel runs the observer's correction
                            * before the controller and its prediction after it (one launch per control period).   */

@@ -32,7 +32,7 @@ class StepIO(C.Structure):
     _fields_ = ([("xhat0", C.c_void_p), ("lastu0", C.c_void_p), ("ry", C.c_void_p), ("Rhat_y", C.c_void_p),
                  ("Rhat_u", C.c_void_p), ("d0", C.c_void_p), ("Dhat0", C.c_void_p), ("Ztilde", C.c_void_p),
                  ("u", C.c_void_p), ("J", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p),
-                 ("device_ptrs", C.c_int32), ("sync", C.c_int32), ("resident", C.c_int32), ("reserved", C.c_int32),
+                 ("device_ptrs", C.c_int32), ("sync", C.c_int32), ("resident", C.c_int32), ("host_mapped", C.c_int32),
                  ("y0m", C.c_void_p)])
 
 

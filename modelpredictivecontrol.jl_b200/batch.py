@@ -182,6 +182,20 @@ class BatchLinMPC:
         check(_lib.lib().bmpc_step(self._h, C.byref(io)))
         return self.u
 
+    def step_mapped(self, xhat0, ry, u, status, resident=True, y0m=None):
+        """Zero-copy call (io.host_mapped = 1): every array must be PAGE-LOCKED host memory that the device can address
+        (e.g. ``torch.Tensor.pin_memory().numpy()``); the kernel reads x̂0/ry from and writes u/status to it directly."""
+        p = lambda a: None if a is None else a.ctypes.data
+        kw = dict(xhat0=p(xhat0)) if y0m is None else dict(y0m=p(y0m))
+        if resident:
+            io = _lib.StepIO(ry=p(ry), u=p(u), status=p(status), device_ptrs=0, sync=1, resident=1, host_mapped=1, **kw)
+        else:
+            # lastu0 / Z̃ go through staging copies (pageable memory is fine); iters would have to be pinned: omitted
+            io = _lib.StepIO(lastu0=p(self.lastu0), ry=p(ry), Ztilde=p(self.Ztilde), u=p(u), status=p(status),
+                             device_ptrs=0, sync=1, host_mapped=1, **kw)
+        check(_lib.lib().bmpc_step(self._h, C.byref(io)))
+        return u
+
     def step_device(self, ptrs, sync=False):
         """Device-pointer variant: ``ptrs`` maps StepIO field names to raw device addresses (ints)."""
         io = _lib.StepIO(device_ptrs=1, sync=int(sync), **ptrs)

@@ -771,7 +771,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     if (fused_est && !h->have_estimator) return fail(BMPC_ERR_STATE, "io.y0m needs bmpc_set_estimator");
     if ((!io->xhat0 && !fused_est) || (!io->ry && !io->Rhat_y) || !io->u || !io->status)
         return fail(BMPC_ERR_ARG, "xhat0 (or y0m with a fused estimator), ry|Rhat_y, u, status are required");
-    if (!resident && (!io->lastu0 || !io->Ztilde || !io->iters))
+    if (!resident && (!io->lastu0 || !io->Ztilde || (!io->iters && !io->host_mapped)))
         return fail(BMPC_ERR_ARG, "lastu0, Ztilde, iters are required unless io.resident = 1");
     if (d.nd > 0 && !io->d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
     if (h->has_terminal_rows && !h->has_terminal_mats) return fail(BMPC_ERR_STATE, "terminal matrices missing");
@@ -783,9 +783,13 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     const size_t N = d.N, nx = d.nxhat, nu = d.nu, ny = d.ny, nd = d.nd, Hp = d.Hp, n = h->n, nY = h->nY, nU = h->nU;
     bmpc::StepParams P{};
     const bool dev = io->device_ptrs != 0;
+    // host_mapped: the caller's HOST arrays are page-locked and device-accessible (cudaHostAlloc / cudaHostRegister,
+    // unified addressing): the kernel reads the inputs from and writes u/J/status/iters to them directly over PCIe
+    // (zero-copy) -- no staging copies.  lastu0 / Z̃ still follow io.resident.
+    const bool mapped = !dev && io->host_mapped != 0;
     auto in = [&](DevBuf<double>& buf, const double* src, size_t cnt, const double** dst) -> cudaError_t {
         if (!src) { *dst = nullptr; return cudaSuccess; }
-        if (dev) { *dst = src; return cudaSuccess; }
+        if (dev || mapped) { *dst = src; return cudaSuccess; }
         cudaError_t e = buf.upload(src, cnt, s);
         *dst = buf.p;
         return e;
@@ -820,10 +824,10 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
         }
         P.lastu0 = h->lastu0.p;
         P.Z = h->Z.p;
-        P.u = h->u.p;
-        P.J_out = h->Jv.p;
-        P.status = h->status.p;
-        P.iters = h->iters.p;
+        P.u = mapped ? io->u : h->u.p;
+        P.J_out = mapped ? (io->J ? io->J : h->Jv.p) : h->Jv.p;
+        P.status = mapped ? io->status : h->status.p;
+        P.iters = (mapped && io->iters) ? io->iters : h->iters.p;
     }
     P.N = d.N; P.nu = d.nu; P.ny = d.ny; P.nd = d.nd; P.nx = d.nxhat; P.Hp = d.Hp; P.Hc = d.Hc;
     P.nz = h->nz; P.n = h->n; P.neps = d.neps; P.nY = h->nY; P.nU = h->nU;
@@ -879,10 +883,12 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     if (!dev) {
         if (io->lastu0) CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
         if (io->Ztilde) CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(io->u, h->u.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
-        if (io->J) CK(cudaMemcpyAsync(io->J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(io->status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
-        if (io->iters) CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+        if (!mapped) {
+            CK(cudaMemcpyAsync(io->u, h->u.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
+            if (io->J) CK(cudaMemcpyAsync(io->J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(io->status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
+            if (io->iters) CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+        }
     }
     if (io->sync || !dev) CK(cudaStreamSynchronize(s));
     return BMPC_OK;

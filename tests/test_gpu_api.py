@@ -215,3 +215,21 @@ def test_two_handles_with_different_footprints_interleave():
             xh = rng.standard_normal((4, mpcs[0].estim.nxhat)) * 0.3
             b.step(xh, ry=rng.choice([-1.0, 1.0], (4, 2)))
             assert (b.status == 0).all()
+
+
+def test_host_mapped_zero_copy_equals_staged_copies():
+    """io.host_mapped = 1 (the kernel reads x̂0/ry from and writes u/status to the caller's page-locked host arrays over
+    PCIe) gives bitwise the same result as the library's staging copies."""
+    import torch
+    mpcs, plants, rng = c1_controllers(32, seed=41)
+    bS, bM = batch_from_oracle(mpcs), batch_from_oracle(mpcs)
+    pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+    xh, ry = pin((32, mpcs[0].estim.nxhat), torch.float64), pin((32, 2), torch.float64)
+    u, st = pin((32, 2), torch.float64), pin((32,), torch.int32)
+    for k in range(6):
+        xh[:] = rng.standard_normal(xh.shape) * 0.3
+        ry[:] = rng.choice([-1.0, 1.0], ry.shape)
+        uS = bS.step(xh, ry=ry).copy()
+        bM.step_mapped(xh, ry, u, st, resident=k > 0)
+        assert (st == bS.status).all() and (st == 0).all()
+        assert np.array_equal(uS, u), k
