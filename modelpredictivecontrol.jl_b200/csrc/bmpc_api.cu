@@ -153,7 +153,7 @@ int configure(bmpc_handle* h) {
     h->teams_per_cta = CTA / TEAM;
     // staging policy: Pd in shared memory only when small (it is re-read from L1/L2 otherwise); for CTA teams keep
     // the per-CTA footprint low enough for several CTAs per SM; the packed Hessian leaves shared memory last
-    size_t pd_limit = TEAM >= 64 ? 48 * 1024 : 96 * 1024;
+    size_t pd_limit = TEAM >= 64 ? 24 * 1024 : 96 * 1024;
     if (const char* e = getenv("BMPC_PD_LIMIT")) pd_limit = (size_t)atol(e);  // tuning override (bytes)
     bool in_smem = h->rt.nDb > 0 && pd_bytes <= pd_limit;
     bool hv_smem = true;
