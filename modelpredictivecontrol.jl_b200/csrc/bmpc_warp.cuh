@@ -67,27 +67,39 @@ __device__ __forceinline__ double wmin(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(WFULL, v, o));
     return v;
 }
-// three maxima and one sum in ONE butterfly (the shuffles of the four values overlap)
+// three maxima and one sum in ONE butterfly (the shuffles of the four values overlap).  The maxima feed thresholds
+// and scale estimates only: they are reduced in fp32 (one shuffle + one FMNMX each, rounded UP so that a convergence
+// test can only become stricter); the sum stays fp64.
+__device__ __forceinline__ float f32_up(double v) { return __double2float_ru(v); }
 __device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, double& s) {
+    float fa = f32_up(a), fb = f32_up(b), fc = f32_up(c);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ta = __shfl_xor_sync(WFULL, a, o), tb = __shfl_xor_sync(WFULL, b, o);
-        const double tc = __shfl_xor_sync(WFULL, c, o), ts = __shfl_xor_sync(WFULL, s, o);
-        a = fmax(a, ta);
-        b = fmax(b, tb);
-        c = fmax(c, tc);
+        const float ta = __shfl_xor_sync(WFULL, fa, o), tb = __shfl_xor_sync(WFULL, fb, o);
+        const float tc = __shfl_xor_sync(WFULL, fc, o);
+        const double ts = __shfl_xor_sync(WFULL, s, o);
+        fa = fmaxf(fa, ta);
+        fb = fmaxf(fb, tb);
+        fc = fmaxf(fc, tc);
         s += ts;
     }
+    a = (double)fa;
+    b = (double)fb;
+    c = (double)fc;
 }
 
-// one maximum and one sum in one butterfly
+// one maximum and one sum in one butterfly; the maximum (rho = 1 / step to the boundary) in fp32 rounded UP, which
+// can only shorten the step (by < 1.2e-7 relative, inside the 1e-6 margin of the fraction to the boundary)
 __device__ __forceinline__ void wred_ms(double& a, double& s) {
+    float fa = f32_up(a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ta = __shfl_xor_sync(WFULL, a, o), ts = __shfl_xor_sync(WFULL, s, o);
-        a = fmax(a, ta);
+        const float ta = __shfl_xor_sync(WFULL, fa, o);
+        const double ts = __shfl_xor_sync(WFULL, s, o);
+        fa = fmaxf(fa, ta);
         s += ts;
     }
+    a = (double)fa;
 }
 
 template <int NT, int RPL>
@@ -550,7 +562,9 @@ __global__ void __launch_bounds__(32, 16)
                     double dk = bcast(pdiag, k);
                     if (!(dk > 1e-280)) dk = 1e200;
                     const double rs = rsqrt(dk);
-                    const double lik = (lane > k && isvar) ? phi[k] * rs : 0.0;  // column k of L
+                    // column k of L.  Lanes <= k (and the idle lanes) compute finite-or-NaN garbage here: it only ever
+                    // lands in their own upper-triangle entries and spent pivots, which nothing reads.
+                    const double lik = phi[k] * rs;
                     if (lane == k) invd = rs;
                     phi[k] = lik;
                     pdiag = fma(-lik, lik, pdiag);
@@ -568,12 +582,15 @@ __global__ void __launch_bounds__(32, 16)
                 __syncwarp();
                 double lcol[NT];  // column `lane` of L (entries below the diagonal)
 #pragma unroll
-                for (int j = 0; j < NT; ++j) lcol[j] = (lane < j) ? sPhi[j * LDN + iv] : 0.0;
+                for (int j = 0; j < NT; ++j) {
+                    lcol[j] = (lane < j) ? sPhi[j * LDN + iv] : 0.0;
+                    phi[j] = (lane > j && isvar) ? phi[j] : 0.0;  // row `lane` of L, strictly lower part, for the forward sweeps
+                }
                 auto solve = [&](double b) -> double {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         const double yj = bcast(b * invd, j);
-                        b = fma(-((lane > j) ? phi[j] : 0.0), yj, b);
+                        b = fma(-phi[j], yj, b);
                     }
                     b *= invd;
 #pragma unroll
