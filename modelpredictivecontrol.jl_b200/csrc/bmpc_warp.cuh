@@ -566,15 +566,17 @@ __global__ void __launch_bounds__(32, 16)
                     // lands in their own upper-triangle entries and spent pivots, which nothing reads.
                     const double lik = phi[k] * rs;
                     if (lane == k) invd = rs;
-                    phi[k] = lik;
                     pdiag = fma(-lik, lik, pdiag);
 #pragma unroll
                     for (int j = k + 1; j < NT; ++j) {
                         const double ljk = bcast(lik, j);
                         phi[j] = fma(-lik, ljk, phi[j]);
                     }
+                    // keep the COLUMN-SCALED factor M = L diag(L)^-1 (unit diagonal): both substitutions then run on
+                    // raw broadcasts, without a multiply by 1/L_jj on their dependent chains
+                    phi[k] = lik * rs;
                 }
-                // rows of L to shared memory for the backward substitutions
+                // rows of M to shared memory for the backward substitutions
                 if (isvar) {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) sPhi[lane * LDN + j] = phi[j];
@@ -586,19 +588,15 @@ __global__ void __launch_bounds__(32, 16)
                     lcol[j] = (lane < j) ? sPhi[j * LDN + iv] : 0.0;
                     phi[j] = (lane > j && isvar) ? phi[j] : 0.0;  // row `lane` of L, strictly lower part, for the forward sweeps
                 }
+                // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b
+                const double invd2 = invd * invd;
                 auto solve = [&](double b) -> double {
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const double yj = bcast(b * invd, j);
-                        b = fma(-phi[j], yj, b);
-                    }
-                    b *= invd;
+                    for (int j = 0; j < NT; ++j) b = fma(-phi[j], bcast(b, j), b);  // M^-1 (unit lower)
+                    b *= invd2;
 #pragma unroll
-                    for (int j = NT - 1; j >= 0; --j) {
-                        const double xj = bcast(b * invd, j);
-                        b = fma(-lcol[j], xj, b);
-                    }
-                    return isvar ? b * invd : 0.0;
+                    for (int j = NT - 1; j >= 0; --j) b = fma(-lcol[j], bcast(b, j), b);  // M'^-1 (unit upper)
+                    return isvar ? b : 0.0;
                 };
                 // ---- predictor (pass 0) and corrector (pass 1) share one copy of the code ----
                 double dsR[RPL], dlR[RPL], rcR[RPL];
