@@ -71,18 +71,15 @@ __device__ __forceinline__ double wmin(double v) {
 // and scale estimates only: they are reduced in fp32 (one shuffle + one FMNMX each, rounded UP so that a convergence
 // test can only become stricter); the sum stays fp64.
 __device__ __forceinline__ float f32_up(double v) { return __double2float_ru(v); }
+// All the maxima are of NON-NEGATIVE values, whose fp32 bit patterns order like unsigned integers: one REDUX
+// (redux.sync.max.u32) per maximum replaces a five-step shuffle butterfly (a NaN, whose pattern is above +Inf, wins).
+__device__ __forceinline__ float wmax_nonneg_f32(float v) {
+    return __uint_as_float(__reduce_max_sync(WFULL, __float_as_uint(v)));
+}
 __device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, double& s) {
-    float fa = f32_up(a), fb = f32_up(b), fc = f32_up(c);
+    const float fa = wmax_nonneg_f32(f32_up(a)), fb = wmax_nonneg_f32(f32_up(b)), fc = wmax_nonneg_f32(f32_up(c));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ta = __shfl_xor_sync(WFULL, fa, o), tb = __shfl_xor_sync(WFULL, fb, o);
-        const float tc = __shfl_xor_sync(WFULL, fc, o);
-        const double ts = __shfl_xor_sync(WFULL, s, o);
-        fa = fmaxf(fa, ta);
-        fb = fmaxf(fb, tb);
-        fc = fmaxf(fc, tc);
-        s += ts;
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(WFULL, s, o);
     a = (double)fa;
     b = (double)fb;
     c = (double)fc;
@@ -91,14 +88,9 @@ __device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, doubl
 // one maximum and one sum in one butterfly; the maximum (rho = 1 / step to the boundary) in fp32 rounded UP, which
 // can only shorten the step (by < 1.2e-7 relative, inside the 1e-6 margin of the fraction to the boundary)
 __device__ __forceinline__ void wred_ms(double& a, double& s) {
-    float fa = f32_up(a);
+    const float fa = wmax_nonneg_f32(f32_up(a));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ta = __shfl_xor_sync(WFULL, fa, o);
-        const double ts = __shfl_xor_sync(WFULL, s, o);
-        fa = fmaxf(fa, ta);
-        s += ts;
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(WFULL, s, o);
     a = (double)fa;
 }
 
@@ -559,9 +551,10 @@ __global__ void __launch_bounds__(32, 16)
                 double invd = 1.0;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) {
-                    double dk = bcast(pdiag, k);
-                    if (!(dk > 1e-280)) dk = 1e200;
-                    const double rs = rsqrt(dk);
+                    const double dk = bcast(pdiag, k);
+                    // guarded pivot (non-positive or NaN -> huge pivot = the variable is frozen); the test runs beside the
+                    // reciprocal square root, not before it
+                    const double rs = (dk > 1e-280) ? rsqrt(dk) : 1e-100;
                     // column k of L.  Lanes <= k (and the idle lanes) compute finite-or-NaN garbage here: it only ever
                     // lands in their own upper-triangle entries and spent pivots, which nothing reads.
                     const double lik = phi[k] * rs;
