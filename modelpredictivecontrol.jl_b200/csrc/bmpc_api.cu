@@ -206,8 +206,14 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     L.w1 = take(MP);
     L.w2 = take(MP);
     L.wd = take(MP);
-    L.F = take(nY);
-    L.tY = take(nY);
+    // F and M*Cy are dead before the interior-point loop first writes wd / w2: share the storage when they fit
+    if (nY <= MP) {
+        L.F = L.wd;
+        L.tY = L.w2;
+    } else {
+        L.F = take(nY);
+        L.tY = take(nY);
+    }
     L.fx = take(nx);
     L.xh = take(nx);
     L.lu = take(h->d.nu);
