@@ -554,6 +554,36 @@ __device__ __forceinline__ void gt_apply(const Team<TEAM>& T, const Ctx& c, cons
     if (c.P->neps)
         for (int r = T.tid; r < rt.m; r += TEAM) ce = fma(rt.row_c[r], w[r], ce);
     T.sync();
+    if constexpr (TEAM >= 256) {
+        // long columns (large problems): one warp per column of Pd, lanes stride over the rows (coalesced 256-byte
+        // requests instead of 32 scattered sectors), shuffle reduction; the few sparse rows in a second pass
+        const int warp = T.tid >> 5, lane = T.tid & 31;
+        for (int j = warp; j < nz; j += TEAM / 32) {
+            const double* col = c.Pd + (long)nDb * j;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = lane;
+            for (; k + 96 < nDb; k += 128) {
+                a0 = fma(col[k], c.wd[k], a0);
+                a1 = fma(col[k + 32], c.wd[k + 32], a1);
+                a2 = fma(col[k + 64], c.wd[k + 64], a2);
+                a3 = fma(col[k + 96], c.wd[k + 96], a3);
+            }
+            for (; k < nDb; k += 32) a0 = fma(col[k], c.wd[k], a0);
+            double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) out[j] = acc;
+        }
+        T.sync();
+        for (int j = T.tid; j < nz; j += TEAM) {
+            double acc = out[j];
+            for (int e = rt.var_ptr[j]; e < rt.var_ptr[j + 1]; ++e) {
+                const int r = rt.var_row[e];
+                acc = fma((double)rt.var_sgn[e] * rt.row_sig[r], w[r], acc);
+            }
+            out[j] = (base ? base[j] : 0.0) + alpha * acc;
+        }
+    } else
     for (int j = T.tid; j < nz; j += TEAM) {
         double a0 = 0.0, a1 = 0.0;
         const double* col = c.Pd + (long)nDb * j;
@@ -645,21 +675,36 @@ __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, dou
             for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-#pragma unroll 2
-            for (int k0 = 0; k0 < nDb; k0 += 4) {
+            // software pipeline: the fragments of k-step k0+4 are requested from L1/L2 BEFORE the 16 DMMAs of k-step k0
+            // are issued, so that the ~700-cycle L2 latency overlaps a full k-step of tensor work
+            double av[4], bv[4], an[4], bn[4], w, wn;
+            auto fetch = [&](int k0, double (&a4)[4], double (&b4)[4], double& wk) {
                 const bool okk = k0 + ft < nDb;
                 const int kk = okk ? k0 : 0;
-                const double w = okk ? c.wd[k0 + ft] : 0.0;
-                double av[4], bv[4];
+                wk = okk ? c.wd[kk + ft] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) av[u] = (okk && oa[u]) ? pa[u][kk] : 0.0;
+                for (int u = 0; u < 4; ++u) a4[u] = (okk && oa[u]) ? pa[u][kk] : 0.0;
+                if (!diag) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) bv[v] = (diag ? av[v] : ((okk && ob[v]) ? pb[v][kk] : 0.0)) * w;
+                    for (int v = 0; v < 4; ++v) b4[v] = (okk && ob[v]) ? pb[v][kk] : 0.0;
+                }
+            };
+            fetch(0, av, bv, w);
+            for (int k0 = 0; k0 < nDb; k0 += 4) {
+                fetch(k0 + 4, an, bn, wn);  // (masked past the end)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) bv[v] = (diag ? av[v] : bv[v]) * w;
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int v = 0; v < 4; ++v)
                         if (!diag || v <= u) dmma884(acc[u][v][0], acc[u][v][1], av[u], bv[v]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    av[u] = an[u];
+                    bv[u] = bn[u];
+                }
+                w = wn;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
