@@ -214,3 +214,48 @@ def test_dense_M_and_L_weights_lqr():
         assert b.J[0] == pytest.approx(mpc.getinfo()["J"], rel=1e-10, abs=1e-12)
         mpc.updatestate(u, y)
         plant.updatestate(u)
+
+
+@pytest.mark.parametrize("team", [0, 128])
+def test_all_features_vs_oracle(team):
+    """Everything the linear path offers at once, GPU (route B) against the oracle per call: operating points on
+    u/y/d/x, measured disturbance with a preview D̂, input setpoints R̂u with Lwt, an output setpoint trajectory R̂y,
+    custom move blocking, hard u box, soft du box, two-sided soft y bounds and terminal state bounds."""
+    from helpers import random_plant
+    rng = np.random.default_rng(123)
+    mpcs = []
+    for i in range(6):
+        p = random_plant(rng, nx=3, nu=2, ny=2)
+        m = LinModel(p.A, p.Bu, p.C, Bd=rng.standard_normal((3, 1)), Dd=rng.standard_normal((2, 1)) * 0.1,
+                     uop=[0.5, -0.2], yop=[1.0, 2.0], dop=[0.3], xop=[0.1, 0.0, -0.1], fop=[0.05, 0.1, 0.0])
+        mpc = LinMPC(m, Hp=12, Hc=[1, 2, 3], Lwt=[0.3, 0.1], Cwt=1e4)
+        mpc.setconstraint(umin=[-2, -2], umax=[2, 2], dumin=[-0.7, -0.7], dumax=[0.7, 0.7], ymin=[0, 1],
+                          ymax=[2.5, 3.5], xhatmin=[-5] * mpc.estim.nxhat, xhatmax=[5] * mpc.estim.nxhat,
+                          c_dumin=[0.1, 0.1], c_dumax=[0.1, 0.1])
+        mpcs.append(mpc)
+    b = batch_from_oracle(mpcs, team=team, with_terminal=True)
+    N, Hp = len(mpcs), 12
+    worst, n_active = 0.0, 0
+    for k in range(8):
+        xh = rng.standard_normal((N, mpcs[0].estim.nxhat)) * 0.4
+        ry = rng.standard_normal((N, 2)) * 0.5 + np.array([1.0, 2.0])
+        Ry = np.tile(ry, (1, Hp)) + 0.1 * rng.standard_normal((N, 2 * Hp)) if k % 2 else None
+        Ru = np.tile(np.array([0.5, -0.2]), (N, Hp)) + 0.2 * rng.standard_normal((N, 2 * Hp))
+        d = 0.3 + 0.2 * rng.standard_normal((N, 1))
+        Dh = np.tile(d, (1, Hp)) + 0.05 * rng.standard_normal((N, Hp))
+        for i, m in enumerate(mpcs):
+            m.estim.xhat0 = xh[i].copy()
+        b.lastu0[:] = np.stack([m.lastu0 for m in mpcs])
+        b.step(xh, ry=ry, Rhat_y=Ry, Rhat_u=Ru,
+               d0=d - 0.3, Dhat0=Dh - 0.3)
+        for i, m in enumerate(mpcs):
+            u = m.moveinput(ry[i], d=d[i], Dhat=Dh[i], Rhat_y=None if Ry is None else Ry[i], Rhat_u=Ru[i])
+            assert b.status[i] == 0 and m.last_status == qp.OPTIMAL, (k, i, b.status[i], b.iters[i])
+            ez = np.abs(b.Ztilde[i] - m.Ztilde).max() / (1 + np.abs(m.Ztilde).max())
+            tz = TOL_Z if b.iters[i] > 0 else 1e-9
+            assert ez < tz, (k, i, ez, b.iters[i])
+            assert np.abs(b.u[i] - u).max() < tz * (1 + np.abs(u).max())
+            n_active += b.iters[i] > 0
+            worst = max(worst, ez)
+    assert n_active > 10
+    print("all features worst", worst, "active", n_active, b.launch_info())
