@@ -290,17 +290,21 @@ __global__ void __launch_bounds__(32, 16)
         auto gt_apply2 = [&](const double* wa_, const double* wb_, double& outa, double& outb) {
             const double2* wva = reinterpret_cast<const double2*>(wa_ + half * mh);
             const double2* wvb = reinterpret_cast<const double2*>(wb_ + half * mh);
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll 2
-            for (int r = 0; r < mh; r += 2) {
-                const double2 wa = wva[r >> 1], wb = wvb[r >> 1];
-                const double g0 = gcol[r * LDG], g1 = gcol[(r + 1) * LDG];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll 1
+            for (int r = 0; r < mh; r += 4) {  // mh is a multiple of 4
+                const double2 wa = wva[r >> 1], wa2 = wva[(r >> 1) + 1], wb = wvb[r >> 1], wb2 = wvb[(r >> 1) + 1];
+                const double g0 = gcol[r * LDG], g1 = gcol[(r + 1) * LDG], g2 = gcol[(r + 2) * LDG], g3 = gcol[(r + 3) * LDG];
                 a0 = fma(g0, wa.x, a0);
                 a1 = fma(g1, wa.y, a1);
+                a2 = fma(g2, wa2.x, a2);
+                a3 = fma(g3, wa2.y, a3);
                 b0 = fma(g0, wb.x, b0);
                 b1 = fma(g1, wb.y, b1);
+                b2 = fma(g2, wb2.x, b2);
+                b3 = fma(g3, wb2.y, b3);
             }
-            double a = a0 + a1, b = b0 + b1;
+            double a = (a0 + a1) + (a2 + a3), b = (b0 + b1) + (b2 + b3);
             a += __shfl_xor_sync(WFULL, a, 16);
             b += __shfl_xor_sync(WFULL, b, 16);
             outa = a;
@@ -441,6 +445,7 @@ __global__ void __launch_bounds__(32, 16)
             double rpR[RPL];
 #pragma unroll
             for (int t = 0; t < RPL; ++t) rpR[t] = okR[t] ? gx[t] + sR[t] - hR[t] : 0.0;
+            const double inv_tol_p = 1.0 / (P.tol * hscale), inv_tol_mu = 1.0 / (P.tol_mu * qs * hscale);
             for (int it = 0; it <= P.max_iter; ++it) {
                 double dR[RPL], isR[RPL];
                 double e_p = 0.0, musum = 0.0;
@@ -474,8 +479,8 @@ __global__ void __launch_bounds__(32, 16)
                     status = ST_INFEASIBLE;
                     break;
                 }
-                const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
-                                          mu * (double)m / (P.tol_mu * qs * hscale));
+                // (the scales of the primal residual and of the gap are loop invariants: multiplications, one reciprocal)
+                const double merit = fmax(fmax(e_d * __drcp_rn(P.tol * qd), e_p * inv_tol_p), musum * inv_tol_mu);
                 if (__any_sync(WFULL, merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) ||
                                               (it == P.max_iter && merit <= 1e3))) {
                     status = ST_OPTIMAL;
@@ -625,9 +630,9 @@ __global__ void __launch_bounds__(32, 16)
                     if (pass == 0) {
                         // affine step: s*dl + lam*ds = -s*lam exactly, so
                         //   sum (s + a ds)(lam + a dl) = (1 - a) sum s*lam + a^2 sum ds*dl   -- no second reduction
-                        const double a_aff = rho > 1.0 ? 1.0 / rho : 1.0;
+                        const double a_aff = rho > 1.0 ? __drcp_rn(rho) : 1.0;
                         const double mua = fmax(((1.0 - a_aff) * musum + a_aff * a_aff * sdd) * minv, 0.0);
-                        ratio = mua / mu;
+                        ratio = mua * __drcp_rn(mu);
                         const double sig = ratio * ratio * ratio;
 #pragma unroll
                         for (int t = 0; t < RPL; ++t) {
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(32, 16)
                 }
                 // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
                 const double tau = fmin(fmax(0.99, 1.0 - ratio), 1.0 - 1e-6);  // never exactly onto the boundary
-                const double a = rho > tau ? tau / rho : 1.0;
+                const double a = rho > tau ? tau * __drcp_rn(rho) : 1.0;
                 // infeasibility: two collapsed steps with the primal residual still open end the solve (ipm_solve,
                 // bmpc_device.cuh)
                 stall = (a < 1e-8 && rp_inf > 1e-6 * hscale) ? stall + 1 : 0;
