@@ -853,6 +853,8 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
     status = ST_ITERATION_LIMIT;
     double rp_inf = 0.0, best_merit = 1e300;
     int stall = 0, stagn = 0;
+    double mu_first = 0.0, ep_chk = 1e300;
+    bool ray_prev = false;
     for (int it = 0; it <= P.max_iter; ++it) {
         // residuals
         hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
@@ -969,6 +971,23 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         // (status INFEASIBLE below) instead of running to the iteration cap.  Feasible problems never step below 1e-3.
         stall = (a < 1e-8 && e_p > 1e-6 * hscale) ? stall + 1 : 0;
         if (stall >= 2) break;
+        // ... and before the collapse: an infeasible problem's iterates drift along a Farkas ray for 20-30 iterations
+        // (primal residual on a plateau, complementarity GROWING by orders of magnitude, h'lam < 0) -- measured on
+        // infeasible MHE windows, tools/studies/mhe_infeas.py.  Checked every 8 iterations from the 16th on; all three
+        // signs at TWO consecutive checkpoints end the solve, and only for problems without a slack variable (with one,
+        // the dense rows can always be satisfied and a long plateau is just a hard but feasible problem).
+        if (it == 0) mu_first = mu;
+        if (P.neps == 0 && (it & 7) == 0) {
+            bool ray = false;
+            if (it >= 16 && e_p > 0.5 * ep_chk && e_p > 1e-4 * hscale && mu > 100.0 * mu_first) {
+                double hl = 0.0;
+                for (int r = T.tid; r < m; r += TEAM) hl = fma(c.h[r], c.lam[r], hl);
+                ray = T.sum(hl) < 0.0;
+            }
+            if (ray && ray_prev) break;
+            ray_prev = ray;
+            ep_chk = e_p;
+        }
         for (int j = T.tid; j < n; j += TEAM) c.x[j] = fma(a, c.dx[j], c.x[j]);
         for (int k = T.tid; k < nDb; k += TEAM) c.yb[k] = fma(a, c.ybd[k], c.yb[k]);
         for (int r = T.tid; r < m; r += TEAM) {
