@@ -9,9 +9,10 @@
 //            transcription.jl:811-848)
 //   stage 2  unconstrained exit: x = -Hv^-1 q with the cached factor; feasible -> done
 //            (ExplicitMPC, explicitmpc.jl:209)
-//   stage 3  Mehrotra predictor-corrector interior point; per iteration
-//            Phi = Hv + P' D P (dense rows by a pair loop, 1-/2-variable rows by a gather),
-//            packed Cholesky in shared memory, two triangular solve pairs
+//   stage 3  Mehrotra predictor-corrector interior point (warm-started from the previous period); per iteration
+//            Phi = Hv + P' D P -- dense rows on the FP64 tensor pipe (DMMA 8x8x4 tiles, 16x16 or 32x32 blocks per
+//            warp) for teams of a warp or more, a scalar pair loop for sub-warp teams; 1-/2-variable rows by a gather;
+//            packed Cholesky in shared memory (CTA teams: blocked, DMMA trailing updates), two blocked solve pairs
 //   stage 4  getinput!: Z = D x, u, lastu0, J, status               (execute.jl:536-546)
 // Coordinates: "input levels" x = [v; eps], v_l = sum_{i<=l} DU_i  (DESIGN.md section 3).
 #pragma once
