@@ -197,7 +197,7 @@ int bmpc_launch_info(bmpc_handle *h, int32_t out[8]);
 int64_t bmpc_launch_count(bmpc_handle *h);
 
 /* ------------------------------------------------------------------------------------------------
- * Linear MovingHorizonEstimator (LinModel + SingleShooting, direct = true), batched.
+ * Linear MovingHorizonEstimator (LinModel + SingleShooting, direct = true or false), batched.
  * Replaces preparestate!/correct_estimate! and updatestate!/update_estimate! of the reference
  * (src/estimator/mhe/execute.jl:44-84): the handle owns the data windows, the arrival state and
  * the arrival covariance of every instance (estim.Y0m/U0/D0/X̂0_old/x̂0arr_old/P̂arr_old/invP̄, Nk).
@@ -211,7 +211,7 @@ typedef struct {
     int32_t nxhat;        /* augmented state size (<= 32)                                          */
     int32_t He;           /* estimation horizon                                                    */
     int32_t neps;         /* 1 if Cwt finite                                                       */
-    int32_t direct;       /* must be 1 (current form, the reference default)                       */
+    int32_t direct;       /* 1: current form (reference default, p = 0); 0: prediction form (p = 1) */
     int32_t shared_model; /* 1: matrices given once                                                */
     int32_t max_iter;     /* 0 -> 50                                                               */
     int32_t device;
@@ -239,8 +239,14 @@ int bmhe_reset(bmhe_handle *h);
  * moves, rebuild H̃/q̃, solve, return x̂0(k) (N x nxhat).  Optional outputs may be NULL. */
 int bmhe_correct(bmhe_handle *h, const double *y0m, const double *d0, double *xhat0, double *Ztilde, double *J,
                  int32_t *status, int32_t *iters, double *Vhat, double *X0);
-/* updatestate!: store u0(k); when the window is full, P̄ <- Â P̄ Â' + Q̂ (update_cov!). */
+/* updatestate! (direct = 1): store u0(k); when the window is full, P̄ <- Â P̄ Â' + Q̂ (update_cov!). */
 int bmhe_update(bmhe_handle *h, const double *u0);
+/* updatestate! (direct = 0, update_estimate! src/estimator/mhe/execute.jl:71-84): add u0(k), y0m(k), d0(k) to the
+ * windows, rebuild H̃/q̃ with the p = 1 prediction matrices, solve, return x̂0(k+1) (N x nxhat); then, when the
+ * window is full, update_cov! = KalmanFilter correction + prediction of P̄ (kalman.jl:520-525).  With direct = 0
+ * bmhe_correct (preparestate!) only returns the current x̂0, as correct_estimate! is empty in that mode. */
+int bmhe_update_solve(bmhe_handle *h, const double *u0, const double *y0m, const double *d0, double *xhat0,
+                      double *Ztilde, double *J, int32_t *status, int32_t *iters, double *Vhat, double *X0);
 int64_t bmhe_launch_count(bmhe_handle *h);
 
 #ifdef __cplusplus

@@ -58,7 +58,7 @@ SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bm
            "bmpc_set_predmat", "bmpc_set_weights", "bmpc_set_oppoints", "bmpc_set_constraints", "bmpc_step",
            "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
-           "bmhe_correct", "bmhe_update", "bmhe_launch_count"]
+           "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_launch_count"]
 
 
 def lib():
@@ -99,6 +99,8 @@ def lib():
     L.bmhe_correct.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p,
                                c_int32_p, c_double_p, c_double_p]
     L.bmhe_update.argtypes = [C.c_void_p, c_double_p]
+    L.bmhe_update_solve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                    c_int32_p, c_int32_p, c_double_p, c_double_p]
     L.bmhe_launch_count.argtypes = [C.c_void_p]
     L.bmhe_launch_count.restype = C.c_int64
     _lib = L

@@ -40,7 +40,7 @@ struct bmpc_handle {
     bmpc_dims d;
     std::vector<int> nb, blk_of_t, blk_start;
     int nz, n, nY, nU, nHp2, nEv2;
-    const double *last_Z = nullptr, *last_xhat0 = nullptr;  // device pointers used by the last step (getinfo)
+    const double *last_Z = nullptr, *last_xhat0 = nullptr, *last_d0 = nullptr, *last_Dhat0 = nullptr;  // device pointers used by the last step (getinfo)
     long NM;  // number of model copies: N or 1 (shared_model)
     cudaStream_t stream = nullptr, own_stream = nullptr;
     int num_sms = 148;
@@ -886,6 +886,8 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     h->stepped = true;
     h->last_Z = P.Z;
     h->last_xhat0 = fused_est ? h->xcorr.p : P.xhat0;
+    h->last_d0 = P.d0;
+    h->last_Dhat0 = P.Dhat0;
     if (!dev) {
         if (io->lastu0) CK(cudaMemcpyAsync(io->lastu0, h->lastu0.p, N * nu * 8, cudaMemcpyDeviceToHost, s));
         if (io->Ztilde) CK(cudaMemcpyAsync(io->Ztilde, h->Z.p, N * n * 8, cudaMemcpyDeviceToHost, s));
@@ -915,7 +917,8 @@ int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
     bmpc::k_getinfo<<<(unsigned)N, 128, h->nz * sizeof(double), s>>>(
         h->Ev.p, sh * (long)h->nEv2, h->has_terminal_mats ? h->exv.p : nullptr, sh * (long)(nx * h->nz), h->kx.p,
         sh * (long)(nx * nx), h->vx.p, sh * (long)(nx * d.nu), h->bx.p, sh * (long)nx, h->last_Z, h->F.p, h->last_xhat0,
-        h->lastu_prev.p, h->t_blk.p, Y.p, U.p, X.p, (int)nY, h->nz, (int)n, d.nu, (int)nx, d.Hp);
+        h->lastu_prev.p, h->t_blk.p, Y.p, U.p, X.p, (int)nY, h->nz, (int)n, d.nu, (int)nx, d.Hp, d.nd, h->gx.p,
+        sh * (long)(nx * d.nd), h->jx.p, sh * (long)(nx * d.nd * d.Hp), h->last_d0, h->last_Dhat0);
     h->launches++;
     CK(cudaGetLastError());
     if (info->Yhat0) CK(cudaMemcpyAsync(info->Yhat0, Y.p, N * nY * 8, cudaMemcpyDeviceToHost, s));

@@ -67,6 +67,52 @@ __device__ inline bool small_spd_inverse(const double* A, double* inv, double* L
     return true;
 }
 
+
+// Kalman correction of a covariance (correct_estimate_kf!, kalman.jl:1235-1268): out[0:nx*nx] <- (I - K Cm) P with
+// K = P Cm' (Cm P Cm' + R)^-1, raw (not symmetrised).  P (nx x nx, symmetric) in shared memory; scratch: K nx*nym,
+// M nym*nym + max(nx,nym)^2, out 2*max(nx,nym)^2 + nx*nym doubles.  Called by every thread of the CTA.
+template <class Sync>
+__device__ inline void kf_correct_cov(int tid, int nth, Sync sync, int nx, int nym, const double* __restrict__ gCm,
+                                      const double* __restrict__ gRm, const double* sP, double* sK, double* sM,
+                                      double* out) {
+    for (int e = tid; e < nx * nym; e += nth) {  // K <- P Cm'   (nx x nym)
+        const int i = e % nx, j = e / nx;
+        double a = 0.0;
+        for (int k = 0; k < nx; ++k) a = fma(sP[i + nx * k], gCm[j + nym * k], a);
+        sK[e] = a;
+    }
+    sync();
+    for (int e = tid; e < nym * nym; e += nth) {  // M <- Cm P Cm' + R
+        const int i = e % nym, j = e / nym;
+        double a = gRm[e];
+        for (int k = 0; k < nx; ++k) a = fma(gCm[i + nym * k], sK[k + nx * j], a);
+        sM[e] = a;
+    }
+    sync();
+    if (tid == 0) small_spd_inverse(sM, out, sM + nym * nym, nym);  // out[0:nym^2] = M^-1
+    sync();
+    for (int e = tid; e < nym * nym; e += nth) sM[e] = out[e];
+    sync();
+    for (int e = tid; e < nx * nym; e += nth) {  // Kg <- (P Cm') M^-1 into out[nx*nx ...]
+        const int i = e % nx, j = e / nx;
+        double a = 0.0;
+        for (int k = 0; k < nym; ++k) a = fma(sK[i + nx * k], sM[k + nym * j], a);
+        out[nx * nx + e] = a;
+    }
+    sync();
+    for (int e = tid; e < nx * nx; e += nth) {  // Pnew = P - Kg (Cm P) ; (Cm P) = (P Cm')' for symmetric P
+        const int i = e % nx, j = e / nx;
+        double a = sP[e];
+        for (int k = 0; k < nym; ++k) {
+            double cp = 0.0;  // (Cm P)[k, j]
+            for (int l = 0; l < nx; ++l) cp = fma(gCm[k + nym * l], sP[l + nx * j], cp);
+            a = fma(-out[nx * nx + i + nx * k], cp, a);
+        }
+        out[e] = a;
+    }
+    sync();
+}
+
 template <int TEAM>
 __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ StepParams P,
                                                          const __grid_constant__ MheParams Q) {
@@ -138,46 +184,12 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
         for (int k = T.tid; k < nx; k += TEAM) x0arr[k] = X0old[k];
         T.sync();
 
-        // ---- correct_cov!: Kalman correction of the arrival covariance, then its inverse ----
-        if (Q.moving) {
+        // ---- correct_cov!: Kalman correction of the arrival covariance, then its inverse (direct = true only:
+        //      with direct = false the correction is part of update_cov!, k_mhe_update) ----
+        if (Q.moving && Q.direct) {
             for (int e = T.tid; e < nx * nx; e += TEAM) sP[e] = Parr[e];
             T.sync();
-            for (int e = T.tid; e < nx * nym; e += TEAM) {  // K <- P Cm'   (nx x nym)
-                const int i = e % nx, j = e / nx;
-                double a = 0.0;
-                for (int k = 0; k < nx; ++k) a = fma(sP[i + nx * k], gCm[j + nym * k], a);
-                sK[e] = a;
-            }
-            T.sync();
-            for (int e = T.tid; e < nym * nym; e += TEAM) {  // M <- Cm P Cm' + R
-                const int i = e % nym, j = e / nym;
-                double a = gRm[e];
-                for (int k = 0; k < nx; ++k) a = fma(gCm[i + nym * k], sK[k + nx * j], a);
-                sM[e] = a;
-            }
-            T.sync();
-            if (T.tid == 0) small_spd_inverse(sM, sP2, sM + nym * nym, nym);  // sP2[0:nym^2] = M^-1
-            T.sync();
-            for (int e = T.tid; e < nym * nym; e += TEAM) sM[e] = sP2[e];
-            T.sync();
-            for (int e = T.tid; e < nx * nym; e += TEAM) {  // Kg <- (P Cm') M^-1 into sP2
-                const int i = e % nx, j = e / nx;
-                double a = 0.0;
-                for (int k = 0; k < nym; ++k) a = fma(sK[i + nx * k], sM[k + nym * j], a);
-                sP2[nx * nx + e] = a;
-            }
-            T.sync();
-            for (int e = T.tid; e < nx * nx; e += TEAM) {  // Pnew = P - Kg (Cm P) ; (Cm P) = (P Cm')' for symmetric P
-                const int i = e % nx, j = e / nx;
-                double a = sP[e];
-                for (int k = 0; k < nym; ++k) {
-                    double cp = 0.0;  // (Cm P)[k, j]
-                    for (int l = 0; l < nx; ++l) cp = fma(gCm[k + nym * l], sP[l + nx * j], cp);
-                    a = fma(-sP2[nx * nx + i + nx * k], cp, a);
-                }
-                sP2[e] = a;
-            }
-            T.sync();
+            kf_correct_cov(T.tid, TEAM, [&] { T.sync(); }, nx, nym, gCm, gRm, sP, sK, sM, sP2);
             for (int e = T.tid; e < nx * nx; e += TEAM) {  // Hermitian(:L)
                 const int i = e % nx, j = e / nx;
                 Parr[e] = i >= j ? sP2[e] : sP2[j + nx * i];
@@ -341,16 +353,25 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
     }
 }
 
-// update_estimate! (direct = true): if the window is full, P̄ <- Â P̄ Â' + Q̂ and its inverse; lastu0 <- u0.
-__global__ void k_mhe_update(int N, int nx, int nu, int full, const double* __restrict__ A, long sA,
-                             const double* __restrict__ Qc, long sQ, double* __restrict__ Parr,
+// update_estimate!: lastu0 <- u0 and, if the window is full, update_cov! (execute.jl:755-779):
+//   direct = true :  P̄ <- Â P̄ Â' + Q̂                      (the correction ran in correct_cov!, step kernel)
+//   direct = false:  P̄ <- Â [(I - K Ĉm) P̄] Â' + Q̂          (KalmanFilter update_estimate! = correct + predict,
+//                                                           kalman.jl:520-525)
+// then Hermitian(:L) and the inverse (kept when the factorisation fails, :785-793).
+// Shared memory (doubles): P nx^2 | T1 nx^2 | P2 2 nq^2 + nx nym | K nx nym | M nym^2 + nq^2, nq = max(nx, nym).
+__global__ void k_mhe_update(int N, int nx, int nu, int nym, int full, int direct, const double* __restrict__ A, long sA,
+                             const double* __restrict__ Qc, long sQ, const double* __restrict__ Cm, long sCm,
+                             const double* __restrict__ Rm, long sR, double* __restrict__ Parr,
                              double* __restrict__ invP, double* __restrict__ lastu0, const double* __restrict__ u0) {
     extern __shared__ double sm[];
     const int inst = blockIdx.x;
     if (inst >= N) return;
+    const int nq = nx > nym ? nx : nym;
     double* P = sm;
     double* T1 = sm + nx * nx;
     double* P2 = T1 + nx * nx;
+    double* K = P2 + 2 * nq * nq + nx * nym;
+    double* M = K + nx * nym;
     const double* gA = A + inst * sA;
     const double* gQ = Qc + inst * sQ;
     for (int k = threadIdx.x; k < nu; k += blockDim.x) lastu0[(long)inst * nu + k] = u0[(long)inst * nu + k];
@@ -358,30 +379,36 @@ __global__ void k_mhe_update(int N, int nx, int nu, int full, const double* __re
     double* gP = Parr + (long)inst * nx * nx;
     for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) P[e] = gP[e];
     __syncthreads();
-    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {  // T1 = P A'
+    const double* src = P;
+    if (!direct) {
+        kf_correct_cov((int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); }, nx, nym, Cm + inst * sCm, Rm + inst * sR,
+                       P, K, M, P2);
+        src = P2;
+    }
+    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {  // T1 = src A'
         const int i = e % nx, j = e / nx;
         double a = 0.0;
-        for (int k = 0; k < nx; ++k) a = fma(P[i + nx * k], gA[j + nx * k], a);
+        for (int k = 0; k < nx; ++k) a = fma(src[i + nx * k], gA[j + nx * k], a);
         T1[e] = a;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {  // P2 = A T1 + Q
+    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {  // P = A T1 + Q  (src is dead)
         const int i = e % nx, j = e / nx;
         double a = gQ[e];
         for (int k = 0; k < nx; ++k) a = fma(gA[i + nx * k], T1[k + nx * j], a);
-        P2[e] = a;
+        P[e] = a;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {
+    for (int e = threadIdx.x; e < nx * nx; e += blockDim.x) {  // Hermitian(:L) -> gP, T1
         const int i = e % nx, j = e / nx;
-        const double v = i >= j ? P2[e] : P2[j + nx * i];
+        const double v = i >= j ? P[e] : P[j + nx * i];
         gP[e] = v;
-        P[e] = v;
+        T1[e] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (small_spd_inverse(P, T1, P2, nx))
-            for (int e = 0; e < nx * nx; ++e) invP[(long)inst * nx * nx + e] = T1[e];
+        if (small_spd_inverse(T1, P2, P, nx))
+            for (int e = 0; e < nx * nx; ++e) invP[(long)inst * nx * nx + e] = P2[e];
     }
 }
 

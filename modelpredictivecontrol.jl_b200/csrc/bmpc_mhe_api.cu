@@ -177,6 +177,69 @@ int compile_rows(bmhe_handle* h, int Nk) {
 
 }  // namespace
 
+extern "C" int bmhe_set_constraints(bmhe_handle* h, const double* xmin, const double* xmax, const double* wmin,
+                                    const double* wmax, const double* vmin, const double* vmax, const double* c_x,
+                                    const double* c_w, const double* c_v);
+
+// add_data_windows! + (correct_cov!) + initpred! + linconstraint! + optim_objective! + getstate! for the whole batch:
+// the body shared by correct_estimate! (direct = true, window input = the stored u0(k-1)) and update_estimate!
+// (direct = false, window input = u0(k), already uploaded to h->u0): src/estimator/mhe/execute.jl:44-84.
+static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, const double* u_window_dev, double* xhat0,
+                        double* Ztilde, double* J, int32_t* status, int32_t* iters, double* Vhat, double* X0) {
+    if (!h || !y0m || !xhat0 || !status || !iters) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->have_predmat || !h->have_cov) return fail(BMPC_ERR_STATE, "bmhe_set_predmat and bmhe_set_cov must be called first");
+    if (h->nd > 0 && !d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
+    CK(cudaSetDevice(h->d.device));
+    if (!h->have_con) {
+        int rc = bmhe_set_constraints(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc != BMPC_OK) return rc;
+    }
+    const int moving = h->Nk + 1 > h->He;
+    const int Nk = std::min(h->Nk + 1, h->He);
+    if (Nk != h->compiled_Nk) {
+        int rc = compile_rows(h, Nk);
+        if (rc != BMPC_OK) return rc;
+    }
+    cudaStream_t s = h->stream;
+    const size_t N = h->d.N, nx = h->nx, nym = h->nym, nd = h->nd, He = h->He;
+    CK(cudaMemcpyAsync(h->y0m.p, y0m, N * nym * 8, cudaMemcpyHostToDevice, s));
+    if (nd) CK(cudaMemcpyAsync(h->d0.p, d0, N * nd * 8, cudaMemcpyHostToDevice, s));
+    bmpc::StepParams P{};
+    P.N = h->d.N; P.nz = h->nz; P.n = h->n; P.neps = h->neps; P.max_iter = h->d.max_iter; P.tol = h->d.tol;
+    P.tol_mu = h->d.tol * 1e-3; P.rt = h->rt;
+    bmpc::MheParams Q{};
+    Q.N = h->d.N; Q.nx = h->nx; Q.nu = h->nu; Q.nym = h->nym; Q.nd = h->nd; Q.He = h->He; Q.Nk = Nk; Q.neps = h->neps;
+    Q.moving = moving; Q.direct = h->d.direct ? 1 : 0; Q.ldE = h->nym * h->He; Q.ldEX = h->nx * h->He;
+    const long sh = h->d.shared_model ? 0 : 1;
+    const long nZ = h->nZfull;
+    Q.sE = sh * nym * He * nZ; Q.sEX = sh * nx * He * nZ; Q.sG = sh * nym * He * h->nu * He; Q.sGX = sh * nx * He * h->nu * He;
+    Q.sJ = sh * nym * He * nd * (He + 1); Q.sJX = sh * nx * He * nd * (He + 1); Q.sB = sh * nym * He; Q.sBX = sh * nx * He;
+    Q.sCm = sh * nym * nx; Q.sCov = sh;
+    Q.E = h->E.p; Q.EX = h->EX.p; Q.G = h->G.p; Q.GX = h->GX.p; Q.J = h->J.p; Q.JX = h->JX.p; Q.B = h->B.p; Q.BX = h->BX.p;
+    Q.Cm = h->Cm.p; Q.Rm = h->Rm.p; Q.rinv = h->rinv.p; Q.Qinv = h->Qinv.p; Q.Cwt = h->Cwt;
+    Q.Y0m = h->Y0m.p; Q.U0 = h->U0.p; Q.D0 = h->D0.p; Q.X0old = h->X0old.p; Q.x0arr = h->x0arr.p; Q.Parr = h->Parr.p;
+    Q.invP = h->invP.p; Q.Z = h->Z.p; Q.xhat0 = h->xhat0.p; Q.lastu0 = const_cast<double*>(u_window_dev);
+    Q.xmin = h->xmin.p; Q.xmax = h->xmax.p; Q.wmin = h->wmin.p; Q.wmax = h->wmax.p; Q.vmin = h->vmin.p; Q.vmax = h->vmax.p;
+    Q.row_kind = h->t_kind.p; Q.row_bidx = h->t_bidx.p; Q.Pd = h->Pd.p; Q.sPd = sh * h->nPd;
+    Q.y0m = h->y0m.p; Q.d0 = h->d0.p; Q.J_out = h->Jv.p; Q.Vhat_out = Vhat ? h->Vhat.p : nullptr; Q.X0_out = X0 ? h->X0.p : nullptr;
+    Q.status = h->status.p; Q.iters = h->iters.p; Q.L = h->L;
+    bmpc::mhe_step_kernel<256><<<h->grid, 256, h->smem_bytes, s>>>(P, Q);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE kernel launch failed: %s", cudaGetErrorString(le));
+    h->launches++;
+    h->Nk = Nk;
+    CK(cudaMemcpyAsync(xhat0, h->xhat0.p, N * nx * 8, cudaMemcpyDeviceToHost, s));
+    if (Ztilde) CK(cudaMemcpyAsync(Ztilde, h->Z.p, N * (h->neps + nx * (1 + He)) * 8, cudaMemcpyDeviceToHost, s));
+    if (J) CK(cudaMemcpyAsync(J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
+    if (Vhat) CK(cudaMemcpyAsync(Vhat, h->Vhat.p, N * nym * He * 8, cudaMemcpyDeviceToHost, s));
+    if (X0) CK(cudaMemcpyAsync(X0, h->X0.p, N * nx * He * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return BMPC_OK;
+}
+
+
 extern "C" {
 
 int bmhe_create(bmhe_handle** out, const bmhe_dims* dims) {
@@ -185,7 +248,6 @@ int bmhe_create(bmhe_handle** out, const bmhe_dims* dims) {
     if (d.N < 1 || d.nu < 1 || d.nym < 1 || d.nd < 0 || d.nxhat < 1 || d.He < 1 || (d.neps != 0 && d.neps != 1))
         return fail(BMPC_ERR_ARG, "invalid dimensions");
     if (d.nxhat > 32 || d.nym > 16) return fail(BMPC_ERR_UNSUPPORTED, "nxhat <= 32 and nym <= 16 are supported");
-    if (!d.direct) return fail(BMPC_ERR_UNSUPPORTED, "only direct = true (current form, the MHE default) is built");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -395,74 +457,52 @@ int bmhe_reset(bmhe_handle* h) {
 
 int bmhe_correct(bmhe_handle* h, const double* y0m, const double* d0, double* xhat0, double* Ztilde, double* J,
                  int32_t* status, int32_t* iters, double* Vhat, double* X0) {
-    if (!h || !y0m || !xhat0 || !status || !iters) return fail(BMPC_ERR_ARG, "null argument");
-    if (!h->have_predmat || !h->have_cov) return fail(BMPC_ERR_STATE, "bmhe_set_predmat and bmhe_set_cov must be called first");
-    if (h->nd > 0 && !d0) return fail(BMPC_ERR_ARG, "d0 is required when nd > 0");
-    CK(cudaSetDevice(h->d.device));
-    if (!h->have_con) {
-        int rc = bmhe_set_constraints(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        if (rc != BMPC_OK) return rc;
+    if (!h || !xhat0) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->d.direct) {
+        // prediction form: preparestate! leaves the estimate untouched (correct_estimate! is empty, execute.jl:44-55)
+        CK(cudaSetDevice(h->d.device));
+        CK(cudaMemcpyAsync(xhat0, h->xhat0.p, (size_t)h->d.N * h->nx * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return BMPC_OK;
     }
-    const int moving = h->Nk + 1 > h->He;
-    const int Nk = std::min(h->Nk + 1, h->He);
-    if (Nk != h->compiled_Nk) {
-        int rc = compile_rows(h, Nk);
-        if (rc != BMPC_OK) return rc;
-    }
+    return solve_window(h, y0m, d0, h->lastu0.p, xhat0, Ztilde, J, status, iters, Vhat, X0);
+}
+
+static int launch_update(bmhe_handle* h) {
     cudaStream_t s = h->stream;
-    const size_t N = h->d.N, nx = h->nx, nym = h->nym, nd = h->nd, He = h->He;
-    CK(cudaMemcpyAsync(h->y0m.p, y0m, N * nym * 8, cudaMemcpyHostToDevice, s));
-    if (nd) CK(cudaMemcpyAsync(h->d0.p, d0, N * nd * 8, cudaMemcpyHostToDevice, s));
-    bmpc::StepParams P{};
-    P.N = h->d.N; P.nz = h->nz; P.n = h->n; P.neps = h->neps; P.max_iter = h->d.max_iter; P.tol = h->d.tol;
-    P.tol_mu = h->d.tol * 1e-3; P.rt = h->rt;
-    bmpc::MheParams Q{};
-    Q.N = h->d.N; Q.nx = h->nx; Q.nu = h->nu; Q.nym = h->nym; Q.nd = h->nd; Q.He = h->He; Q.Nk = Nk; Q.neps = h->neps;
-    Q.moving = moving; Q.direct = 1; Q.ldE = h->nym * h->He; Q.ldEX = h->nx * h->He;
+    const size_t N = h->d.N, nx = h->nx, nym = h->nym, nq = std::max(nx, nym);
     const long sh = h->d.shared_model ? 0 : 1;
-    const long nZ = h->nZfull;
-    Q.sE = sh * nym * He * nZ; Q.sEX = sh * nx * He * nZ; Q.sG = sh * nym * He * h->nu * He; Q.sGX = sh * nx * He * h->nu * He;
-    Q.sJ = sh * nym * He * nd * (He + 1); Q.sJX = sh * nx * He * nd * (He + 1); Q.sB = sh * nym * He; Q.sBX = sh * nx * He;
-    Q.sCm = sh * nym * nx; Q.sCov = sh;
-    Q.E = h->E.p; Q.EX = h->EX.p; Q.G = h->G.p; Q.GX = h->GX.p; Q.J = h->J.p; Q.JX = h->JX.p; Q.B = h->B.p; Q.BX = h->BX.p;
-    Q.Cm = h->Cm.p; Q.Rm = h->Rm.p; Q.rinv = h->rinv.p; Q.Qinv = h->Qinv.p; Q.Cwt = h->Cwt;
-    Q.Y0m = h->Y0m.p; Q.U0 = h->U0.p; Q.D0 = h->D0.p; Q.X0old = h->X0old.p; Q.x0arr = h->x0arr.p; Q.Parr = h->Parr.p;
-    Q.invP = h->invP.p; Q.Z = h->Z.p; Q.xhat0 = h->xhat0.p; Q.lastu0 = h->lastu0.p;
-    Q.xmin = h->xmin.p; Q.xmax = h->xmax.p; Q.wmin = h->wmin.p; Q.wmax = h->wmax.p; Q.vmin = h->vmin.p; Q.vmax = h->vmax.p;
-    Q.row_kind = h->t_kind.p; Q.row_bidx = h->t_bidx.p; Q.Pd = h->Pd.p; Q.sPd = sh * h->nPd;
-    Q.y0m = h->y0m.p; Q.d0 = h->d0.p; Q.J_out = h->Jv.p; Q.Vhat_out = Vhat ? h->Vhat.p : nullptr; Q.X0_out = X0 ? h->X0.p : nullptr;
-    Q.status = h->status.p; Q.iters = h->iters.p; Q.L = h->L;
-    bmpc::mhe_step_kernel<256><<<h->grid, 256, h->smem_bytes, s>>>(P, Q);
+    const int smem = (int)((2 * nx * nx + 2 * nq * nq + 2 * nx * nym + nym * nym + nq * nq) * 8);
+    CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(bmpc::k_mhe_update), smem));
+    bmpc::k_mhe_update<<<(unsigned)N, 64, smem, s>>>((int)N, (int)nx, h->nu, (int)nym, h->Nk == h->He ? 1 : 0, h->d.direct ? 1 : 0,
+                                                    h->A.p, sh * (long)(nx * nx), h->Qc.p, sh * (long)(nx * nx), h->Cm.p,
+                                                    sh * (long)(nym * nx), h->Rm.p, sh * (long)(nym * nym), h->Parr.p, h->invP.p,
+                                                    h->lastu0.p, h->u0.p);
     cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE kernel launch failed: %s", cudaGetErrorString(le));
+    if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE update kernel launch failed: %s", cudaGetErrorString(le));
     h->launches++;
-    h->Nk = Nk;
-    CK(cudaMemcpyAsync(xhat0, h->xhat0.p, N * nx * 8, cudaMemcpyDeviceToHost, s));
-    if (Ztilde) CK(cudaMemcpyAsync(Ztilde, h->Z.p, N * (h->neps + nx * (1 + He)) * 8, cudaMemcpyDeviceToHost, s));
-    if (J) CK(cudaMemcpyAsync(J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
-    if (Vhat) CK(cudaMemcpyAsync(Vhat, h->Vhat.p, N * nym * He * 8, cudaMemcpyDeviceToHost, s));
-    if (X0) CK(cudaMemcpyAsync(X0, h->X0.p, N * nx * He * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return BMPC_OK;
 }
 
 int bmhe_update(bmhe_handle* h, const double* u0) {
     if (!h || !u0) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->d.direct) return fail(BMPC_ERR_STATE, "direct = false: updatestate! needs ym and d, call bmhe_update_solve");
     if (h->Nk < 1) return fail(BMPC_ERR_STATE, "bmhe_correct (preparestate!) must be called before bmhe_update");
     CK(cudaSetDevice(h->d.device));
-    cudaStream_t s = h->stream;
-    const size_t N = h->d.N, nx = h->nx;
-    CK(cudaMemcpyAsync(h->u0.p, u0, N * h->nu * 8, cudaMemcpyHostToDevice, s));
-    const long sh = h->d.shared_model ? 0 : 1;
-    bmpc::k_mhe_update<<<(unsigned)N, 64, 3 * nx * nx * 8, s>>>((int)N, (int)nx, h->nu, h->Nk == h->He ? 1 : 0, h->A.p, sh * (long)(nx * nx),
-                                                             h->Qc.p, sh * (long)(nx * nx), h->Parr.p, h->invP.p, h->lastu0.p, h->u0.p);
-    cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE update kernel launch failed: %s", cudaGetErrorString(le));
-    h->launches++;
-    CK(cudaStreamSynchronize(s));
-    return BMPC_OK;
+    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyHostToDevice, h->stream));
+    return launch_update(h);
+}
+
+int bmhe_update_solve(bmhe_handle* h, const double* u0, const double* y0m, const double* d0, double* xhat0,
+                      double* Ztilde, double* J, int32_t* status, int32_t* iters, double* Vhat, double* X0) {
+    if (!h || !u0) return fail(BMPC_ERR_ARG, "null argument");
+    if (h->d.direct) return fail(BMPC_ERR_STATE, "direct = true: the window is solved in bmhe_correct; call bmhe_update");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = solve_window(h, y0m, d0, h->u0.p, xhat0, Ztilde, J, status, iters, Vhat, X0);
+    if (rc != BMPC_OK) return rc;
+    return launch_update(h);
 }
 
 int64_t bmhe_launch_count(bmhe_handle* h) { return h ? h->launches : 0; }

@@ -92,14 +92,17 @@ __global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restr
 
 // getinfo predictions (predict!, transcription.jl:1136-1145; getU0!, :1115) evaluated in level
 // coordinates: v = cumsum(ΔU) per input, Ŷ0 = Ev v + F, U0 = v[block(t)] + lastu0, x̂0end = exv v + fx̂.
-// One CTA per instance.  Measured-disturbance terms of fx̂ are not included (nd = 0 scope).
+// One CTA per instance.  fx̂ = bx̂ + kx̂ x̂0 + vx̂ u0(k-1) + gx̂ d0 + jx̂ D̂0 (linconstraint!, transcription.jl:818-822;
+// D̂0 = NULL means d0 repeated over Hp, as moveinput! does by default, execute.jl:64).
 __global__ void k_getinfo(const double* __restrict__ Ev, long sE, const double* __restrict__ exv, long sex,
                           const double* __restrict__ kx, long skx, const double* __restrict__ vx, long svx,
                           const double* __restrict__ bx, long sbx, const double* __restrict__ Z,
                           const double* __restrict__ F, const double* __restrict__ xhat0,
                           const double* __restrict__ lastu_prev, const int* __restrict__ blk_of_t,
                           double* __restrict__ Yhat0, double* __restrict__ U0, double* __restrict__ xend, int nY, int nz,
-                          int n, int nu, int nx, int Hp) {
+                          int n, int nu, int nx, int Hp, int nd, const double* __restrict__ gx, long sgx,
+                          const double* __restrict__ jx, long sjx, const double* __restrict__ d0,
+                          const double* __restrict__ Dhat0) {
     extern __shared__ double v[];
     const int inst = blockIdx.x;
     const double* z = Z + (long)inst * n;
@@ -129,6 +132,14 @@ __global__ void k_getinfo(const double* __restrict__ Ev, long sE, const double* 
             for (int k = 0; k < nx; ++k) a = fma(kxi[i + (long)nx * k], xhat0[(long)inst * nx + k], a);
             for (int k = 0; k < nu; ++k) a = fma(vxi[i + (long)nx * k], lastu_prev[(long)inst * nu + k], a);
             for (int j = 0; j < nz; ++j) a = fma(exi[i + (long)nx * j], v[j], a);
+            if (nd > 0 && d0) {
+                const double* gxi = gx + inst * sgx;
+                const double* jxi = jx + inst * sjx;
+                const double* di = d0 + (long)inst * nd;
+                for (int k = 0; k < nd; ++k) a = fma(gxi[i + (long)nx * k], di[k], a);
+                for (int k = 0; k < nd * Hp; ++k)
+                    a = fma(jxi[i + (long)nx * k], Dhat0 ? Dhat0[(long)inst * nd * Hp + k] : di[k % nd], a);
+            }
             xend[(long)inst * nx + i] = a;
         }
     }

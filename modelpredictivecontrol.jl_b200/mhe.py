@@ -1,6 +1,7 @@
 """``MovingHorizonEstimator``: host-side mirror of the reference's linear MHE for a BATCH of estimators
 (src/estimator/mhe/construct.jl:528-630, ``setconstraint!`` :858-1046, ``preparestate!/updatestate!``
-src/estimator/execute.jl:334-386).  LinModel + SingleShooting, ``direct=true`` (the reference default).
+src/estimator/execute.jl:334-386).  LinModel + SingleShooting, ``direct=true`` (the reference default, the
+window is solved in ``preparestate``) or ``direct=false`` (prediction form, solved in ``updatestate``).
 The per-period work (windows, arrival covariance, Hessian rebuild, QP) runs in libbmpc.so."""
 import ctypes as C
 
@@ -11,14 +12,19 @@ from ._lib import check, colmajor, dptr
 from .host import _b, augment_model
 
 
-def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He):
-    """Batched init_predmat_mhe for p = 0 (direct = true), src/estimator/mhe/transcription.jl:151-260.
-    Block (i, j) formulas (i = 0-based step, j = block column; column 0 = arrival state):
-      E[i, arr] = -Cm A^(i+1),  E[i, w_j] = -Cm A^(i-j),  G[i, u_j] = -Cm A^(i-j) Bu   (j <= i),
-      J[i, d_j] = -Cm A^(i-j) Bd (j <= i),  J[i, d_(i+1)] = -Ddm,  B[i] = -Cm S(i) f,
-      EX[i, arr] = A^(i+1),  EX[i, w_j] = A^(i-j),  GX[i, u_j] = A^(i-j) Bu,  JX[i, d_j] = A^(i-j) Bd,  BX[i] = S(i) f."""
+def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He, direct=True):
+    """Batched init_predmat_mhe, src/estimator/mhe/transcription.jl:151-260, p = 0 (direct) or 1.
+    Block (i, j) formulas (i = 0-based step, j = block column; column 0 = arrival state x̂(k-Nk+p)):
+      p = 0:  E[i, arr] = -Cm A^(i+1),  E[i, w_j] = -Cm A^(i-j)  (j <= i),  G[i, u_j] = -Cm A^(i-j) Bu  (j <= i),
+              J[i, d_j] = -Cm A^(i-j) Bd (j <= i),  J[i, d_(i+1)] = -Ddm,  B[i] = -Cm S(i) f;
+      p = 1:  E[i, arr] = -Cm A^i,      E[i, w_j] = -Cm A^(i-1-j) (j < i),  G[i, u_j] = -Cm A^(i-1-j) Bu (j < i),
+              J[i, d_j] = -Cm A^(i-j) Bd (1 <= j <= i),  J[i, d_(i+1)] = -Ddm,
+              B[i] = -Cm S(i-1) f for 1 <= i <= He-2 (the reference's own row range, :244-245);
+      both:   EX[i, arr] = A^(i+1),  EX[i, w_j] = A^(i-j),  GX[i, u_j] = A^(i-j) Bu,  JX[i, d_(j+p)] = A^(i-j) Bd,
+              BX[i] = S(i) f."""
     N, nx = A.shape[0], A.shape[1]
     nu, nym, nd = Bu.shape[2], Cm.shape[1], Bd.shape[2]
+    p = 0 if direct else 1
     Ap = [np.broadcast_to(np.eye(nx), (N, nx, nx)).copy()]
     for _ in range(He):
         Ap.append(Ap[-1] @ A)
@@ -30,30 +36,31 @@ def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He):
     B, BX = np.zeros((N, nym * He)), np.zeros((N, nx * He))
     for i in range(He):
         ry, rx = slice(i * nym, (i + 1) * nym), slice(i * nx, (i + 1) * nx)
-        E[:, ry, :nx] = -Cm @ Ap[i + 1]
+        E[:, ry, :nx] = -Cm @ Ap[i + 1 - p]
         EX[:, rx, :nx] = Ap[i + 1]
-        B[:, ry] = -np.einsum("nij,nj->ni", Cm @ S[i], f)
+        if p == 0 or 1 <= i <= He - 2:
+            B[:, ry] = -np.einsum("nij,nj->ni", Cm @ S[i - p], f)
         BX[:, rx] = np.einsum("nij,nj->ni", S[i], f)
         if nd:
             J[:, ry, (i + 1) * nd:(i + 2) * nd] = -Ddm
         for j in range(i + 1):
-            E[:, ry, nx + j * nx:nx + (j + 1) * nx] = -Cm @ Ap[i - j]
             EX[:, rx, nx + j * nx:nx + (j + 1) * nx] = Ap[i - j]
-            G[:, ry, j * nu:(j + 1) * nu] = -Cm @ Ap[i - j] @ Bu
             GX[:, rx, j * nu:(j + 1) * nu] = Ap[i - j] @ Bu
             if nd:
-                J[:, ry, j * nd:(j + 1) * nd] = -Cm @ Ap[i - j] @ Bd
-                JX[:, rx, j * nd:(j + 1) * nd] = Ap[i - j] @ Bd
+                JX[:, rx, (j + p) * nd:(j + p + 1) * nd] = Ap[i - j] @ Bd
+                if j >= p:
+                    J[:, ry, j * nd:(j + 1) * nd] = -Cm @ Ap[i - j] @ Bd
+            if j <= i - p:
+                E[:, ry, nx + j * nx:nx + (j + 1) * nx] = -Cm @ Ap[i - p - j]
+                G[:, ry, j * nu:(j + 1) * nu] = -Cm @ Ap[i - p - j] @ Bu
     return E, G, J, B, EX, GX, JX, BX
 
 
 class MovingHorizonEstimator:
-    direct = True
-
     def __init__(self, model, He, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None, nint_u=0, nint_ym=None,
                  sigmaPint_ym_0=None, sigmaQint_ym=None, Cwt=np.inf, shared_model=False, device=0, max_iter=0,
-                 tol=0.0):
-        self.model, self.He = model, int(He)
+                 tol=0.0, direct=True):
+        self.model, self.He, self.direct = model, int(He), bool(direct)
         self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
         N, nx, nxh = model.N, model.nx, self.nxhat
         self.nym = len(self.i_ym)
@@ -70,10 +77,11 @@ class MovingHorizonEstimator:
         NM = 1 if shared_model else N
         sl = slice(0, NM)
         E, G, J, B, EX, GX, JX, BX = init_predmat_mhe(self.Ahat[sl], self.Buhat[sl], self.Cmhat[sl], self.Bdhat[sl],
-                                                      self.Ddmhat[sl], (self.fophat - self.xophat)[sl], self.He)
+                                                      self.Ddmhat[sl], (self.fophat - self.xophat)[sl], self.He,
+                                                      self.direct)
         self._h = C.c_void_p()
         dims = _lib.MheDims(N=N, nu=model.nu, nym=self.nym, nd=model.nd, nxhat=nxh, He=self.He, neps=self.neps,
-                            direct=1, shared_model=int(shared_model), max_iter=max_iter, device=device, tol=tol)
+                            direct=int(self.direct), shared_model=int(shared_model), max_iter=max_iter, device=device, tol=tol)
         L = _lib.lib()
         check(L.bmhe_create(C.byref(self._h), C.byref(dims)))
         nd = model.nd
@@ -135,20 +143,38 @@ class MovingHorizonEstimator:
         check(_lib.lib().bmhe_set_constraints(self._h, *[dptr(x) for x in a], *[dptr(x) for x in sv]))
         return self
 
-    def preparestate(self, ym, d=None):
+    def _io(self):
+        p32 = lambda a: a.ctypes.data_as(_lib.c_int32_p)
+        return [dptr(self.xhat0), dptr(self.Ztilde), dptr(self.J), p32(self.status), p32(self.iters), dptr(self.Vhat),
+                dptr(self.X0)]
+
+    def _dev(self, ym, d):
         m, N = self.model, self.model.N
         y0m = np.ascontiguousarray(_b(ym, N, (self.nym,)) - m.yop[:, self.i_ym])
         d0 = np.ascontiguousarray(_b(d, N, (m.nd,)) - m.dop) if m.nd else None
-        p32 = lambda a: a.ctypes.data_as(_lib.c_int32_p)
-        check(_lib.lib().bmhe_correct(self._h, dptr(y0m), dptr(d0) if d0 is not None else None, dptr(self.xhat0),
-                                      dptr(self.Ztilde), dptr(self.J), p32(self.status), p32(self.iters),
-                                      dptr(self.Vhat), dptr(self.X0)))
-        self._solved = True
+        return y0m, d0
+
+    def preparestate(self, ym, d=None):
+        """preparestate! (src/estimator/execute.jl:334-352): solves the window when direct=true; with direct=false
+        correct_estimate! is empty (mhe/execute.jl:44-55) and the current estimate is returned."""
+        y0m, d0 = self._dev(ym, d)
+        check(_lib.lib().bmhe_correct(self._h, dptr(y0m), dptr(d0) if d0 is not None else None, *self._io()))
+        if self.direct:
+            self._solved = True
         return self.xhat0 + self.xophat
 
     def updatestate(self, u, ym=None, d=None):
+        """updatestate! (src/estimator/execute.jl:371-386 -> update_estimate!, mhe/execute.jl:71-84)."""
         u0 = np.ascontiguousarray(_b(u, self.model.N, (self.model.nu,)) - self.model.uop)
-        check(_lib.lib().bmhe_update(self._h, dptr(u0)))
+        if self.direct:
+            check(_lib.lib().bmhe_update(self._h, dptr(u0)))
+        else:
+            if ym is None:
+                raise ValueError("updatestate needs ym (and d) when direct=false")
+            y0m, d0 = self._dev(ym, d)
+            check(_lib.lib().bmhe_update_solve(self._h, dptr(u0), dptr(y0m), dptr(d0) if d0 is not None else None,
+                                               *self._io()))
+            self._solved = True
         return self.xhat0 + self.xophat
 
     def reset(self):

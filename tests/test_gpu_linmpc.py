@@ -247,9 +247,9 @@ def test_all_features_vs_oracle(team):
             m.estim.xhat0 = xh[i].copy()
         b.lastu0[:] = np.stack([m.lastu0 for m in mpcs])
         b.step(xh, ry=ry, Rhat_y=Ry, Rhat_u=Ru,
-               d0=d - 0.3, Dhat0=Dh - 0.3)
+               d0=d - 0.3, Dhat0=None if k == 6 else Dh - 0.3)  # k = 6: default D̂ = repeat(d, Hp)
         for i, m in enumerate(mpcs):
-            u = m.moveinput(ry[i], d=d[i], Dhat=Dh[i], Rhat_y=None if Ry is None else Ry[i], Rhat_u=Ru[i])
+            u = m.moveinput(ry[i], d=d[i], Dhat=None if k == 6 else Dh[i], Rhat_y=None if Ry is None else Ry[i], Rhat_u=Ru[i])
             assert b.status[i] == 0 and m.last_status == qp.OPTIMAL, (k, i, b.status[i], b.iters[i])
             ez = np.abs(b.Ztilde[i] - m.Ztilde).max() / (1 + np.abs(m.Ztilde).max())
             tz = TOL_Z if b.iters[i] > 0 else 1e-9
@@ -257,5 +257,13 @@ def test_all_features_vs_oracle(team):
             assert np.abs(b.u[i] - u).max() < tz * (1 + np.abs(u).max())
             n_active += b.iters[i] > 0
             worst = max(worst, ez)
+        if k % 3 == 0:  # getinfo with nd > 0: x̂end carries gx̂ d0 + jx̂ D̂0, Ŷ carries G d0 + J D̂0
+            gi = b.getinfo()
+            for i, m in enumerate(mpcs):
+                oi = m.getinfo()
+                tz = 10 * (TOL_Z if b.iters[i] > 0 else 1e-9)
+                xe = gi["xhat0end"][i] + m.estim.xophat
+                assert np.abs(xe - oi["xhatend"]).max() < tz * (1 + np.abs(oi["xhatend"]).max()), (k, i)
+                assert np.abs(gi["Yhat0"][i] + m.Yop - oi["Yhat"]).max() < tz * (1 + np.abs(oi["Yhat"]).max()), (k, i)
     assert n_active > 10
     print("all features worst", worst, "active", n_active, b.launch_info())

@@ -28,6 +28,8 @@ def run_both(gmhe, omhes, rng, steps, nd, ny, nu, tol_active=1e-6):
     N = len(omhes)
     worst = 0.0
     nact = 0
+    if not gmhe.direct:
+        return run_both_prediction_form(gmhe, omhes, rng, steps, nd, ny, nu, tol_active)
     for k in range(steps):
         y = np.array([5.0, 3.0])[:ny] + rng.standard_normal((N, ny))
         d = 0.5 + 0.3 * rng.standard_normal((N, nd))
@@ -46,6 +48,77 @@ def run_both(gmhe, omhes, rng, steps, nd, ny, nu, tol_active=1e-6):
             o.updatestate(u[i], y[i], d[i] if nd else ())
         gmhe.updatestate(u, y, d if nd else None)
     return worst, nact
+
+
+def run_both_prediction_form(gmhe, omhes, rng, steps, nd, ny, nu, tol_active):
+    """direct=false: preparestate! returns the current estimate unchanged, the window is solved in updatestate!
+    (update_estimate!, src/estimator/mhe/execute.jl:71-84)."""
+    N = len(omhes)
+    worst, nact = 0.0, 0
+    for k in range(steps):
+        y = np.array([5.0, 3.0])[:ny] + rng.standard_normal((N, ny))
+        d = 0.5 + 0.3 * rng.standard_normal((N, nd))
+        u = np.array([1.0, -2.0])[:nu] + rng.standard_normal((N, nu))
+        xp = gmhe.preparestate(y, d if nd else None).copy()
+        for i, o in enumerate(omhes):
+            xo = o.preparestate(y[i], d[i] if nd else ())
+            assert np.abs(xp[i] - xo).max() <= 2e-6 * (1 + np.abs(xo).max()), (k, i)
+        xg = gmhe.updatestate(u, y, d if nd else None)
+        for i, o in enumerate(omhes):
+            xo = o.updatestate(u[i], y[i], d[i] if nd else ())
+            assert gmhe.status[i] == o.last_qp["status"], (k, i, gmhe.status[i], o.last_qp["status"], gmhe.iters[i])
+            tol = tol_active if gmhe.iters[i] > 0 else 1e-9
+            nact += gmhe.iters[i] > 0
+            e = np.abs(xg[i] - xo).max() / (1 + np.abs(xo).max())
+            ez = np.abs(gmhe.Ztilde[i] - o.Ztilde).max() / (1 + np.abs(o.Ztilde).max())
+            ej = abs(gmhe.J[i] - o.Jval) / (1 + abs(o.Jval))
+            assert e < tol and ez < tol and ej < 1e-8, (k, i, e, ez, ej, gmhe.iters[i])
+            worst = max(worst, e, ez)
+    return worst, nact
+
+
+@pytest.mark.parametrize("He,nd", [(3, 1), (5, 0), (1, 1)])
+def test_mhe_prediction_form_matches_oracle_and_kalman(He, nd):
+    """test/2_test_state_estim.jl:1750-1766 through the GPU: MHE (direct=false) == oracle MHE == KalmanFilter
+    (direct=false); covers the growing window, the first full window and the moving window with the
+    correct+predict covariance update."""
+    import mpc_b200
+    N = 6
+    gm, oms, rng = make(N, 4, nd=nd)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0], direct=False)
+    os_ = [OMHE(m, He=He, nint_ym=0, direct=False) for m in oms]
+    kfs = [OKF(m, nint_ym=0, direct=False) for m in oms]
+    worst, nact = run_both(g, os_, rng, 2 * He + 4, nd, 2, 2)
+    assert nact == 0
+    # the same data through the time-varying KalmanFilter (oracle side already asserted equal in
+    # tests/test_oracle_mhe.py); here: GPU MHE state == KF state after the same sequence
+    rng2 = np.random.default_rng(4)
+    gm2, oms2, rng2 = make(N, 4, nd=nd)
+    for k in range(2 * He + 4):
+        y = np.array([5.0, 3.0]) + rng2.standard_normal((N, 2))
+        d = 0.5 + 0.3 * rng2.standard_normal((N, nd))
+        u = np.array([1.0, -2.0]) + rng2.standard_normal((N, 2))
+        for i, kf in enumerate(kfs):
+            kf.preparestate(y[i], d[i] if nd else ())
+            kf.updatestate(u[i], y[i], d[i] if nd else ())
+    xk = np.stack([kf.xhat0 + kf.xophat for kf in kfs])
+    xg = g.xhat0 + g.xophat
+    assert np.abs(xg - xk).max() < 1e-6 * (1 + np.abs(xk).max()), np.abs(xg - xk).max()
+    print("MHE direct=false worst", worst)
+
+
+def test_mhe_prediction_form_bounds_match_oracle():
+    """direct=false with state / process-noise / sensor-noise bounds, hard."""
+    import mpc_b200
+    N, He = 5, 4
+    gm, oms, rng = make(N, 6, nd=1)
+    kw = dict(xhatmin=[-0.6] * 3, xhatmax=[0.6] * 3, whatmin=[-0.3] * 3, whatmax=[0.3] * 3,
+              vhatmin=[-2.5] * 2, vhatmax=[2.5] * 2)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0], direct=False).setconstraint(**kw)
+    os_ = [OMHE(m, He=He, nint_ym=0, direct=False).setconstraint(**kw) for m in oms]
+    worst, nact = run_both(g, os_, rng, 2 * He + 3, 1, 2, 2, tol_active=2e-6)
+    assert nact > 10
+    print("MHE direct=false constrained worst", worst, "active solves", nact)
 
 
 @pytest.mark.parametrize("He,nd", [(3, 1), (5, 0)])
