@@ -157,6 +157,7 @@ int configure(bmpc_handle* h) {
     if (const char* e = getenv("BMPC_PD_LIMIT")) pd_limit = (size_t)atol(e);  // tuning override (bytes)
     bool in_smem = h->rt.nDb > 0 && pd_bytes <= pd_limit;
     bool hv_smem = true;
+    if (const char* e = getenv("BMPC_HV_SMEM")) hv_smem = atoi(e) != 0;  // tuning override
     for (int attempt = 0; attempt < 3; ++attempt) {
         layout_smem(h, in_smem, hv_smem);
         h->smem_bytes = h->sm.total * 8 * h->teams_per_cta;

@@ -1001,7 +1001,7 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
 }
 
 template <int TEAM>
-__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM, TEAM == 128 ? 6 : 1)
+__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM, TEAM == 128 ? 6 : (TEAM == 64 ? 8 : 1))
     step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) double smem[];
     constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
