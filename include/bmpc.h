@@ -178,6 +178,15 @@ int bmpc_getinfo(bmpc_handle *h, const bmpc_info *info);
 int bmpc_set_estimator(bmpc_handle *h, const double *Ahat, const double *Buhat, const double *Bdhat,
                        const double *Cmhat, const double *Ddmhat, const double *Khat,
                        const double *fop_minus_xop, int32_t nym);
+/* Time-varying KalmanFilter (reference src/estimator/kalman.jl:311-525) as the fused observer: after bmpc_set_estimator
+ * (whose Khat may then be NULL) give the covariances cov.P̂_0, Q̂, R̂ (column-major, N x len or 1 x len when
+ * dims.shared_model = 1).  Every bmpc_step with io.y0m then runs, around the step kernel,
+ *   before:  K̂(k) = P̂ Ĉm' (Ĉm P̂ Ĉm' + R̂)^-1,  P̂ <- Hermitian((I - K̂ Ĉm) P̂, :L)   (correct_estimate_kf!, :1235-1268)
+ *   after:   P̂ <- Hermitian(Â P̂ Â' + Q̂, :L)                                        (predict_estimate_kf!, :1270-1290)
+ * in one small kernel each (one CTA per model; the recursion does not depend on the data), while the state update
+ * x̂ += K̂ v̂, x̂ <- Â x̂ + ... stays inside the step kernel.  bmpc_get_cov reads P̂ back (N or 1 x nxhat x nxhat). */
+int bmpc_set_estimator_cov(bmpc_handle *h, const double *P0, const double *Qhat, const double *Rhat);
+int bmpc_get_cov(bmpc_handle *h, double *Phat);
 /* setstate! / read-back of the observer state: x̂0 (prediction for the next period) and the corrected estimate the
  * last step used; either output may be NULL. */
 int bmpc_set_state(bmpc_handle *h, const double *xhat0);

@@ -56,7 +56,7 @@ _lib = None
 # every symbol include/bmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bmpc_set_stream", "bmpc_set_model",
            "bmpc_set_predmat", "bmpc_set_weights", "bmpc_set_oppoints", "bmpc_set_constraints", "bmpc_step",
-           "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
+           "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_estimator_cov", "bmpc_get_cov", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_launch_count"]
 
@@ -85,6 +85,8 @@ def lib():
     L.bmpc_getinfo.argtypes = [C.c_void_p, C.POINTER(Info)]
     L.bmpc_launch_info.argtypes = [C.c_void_p, c_int32_p]
     L.bmpc_set_estimator.argtypes = [C.c_void_p] + [c_double_p] * 7 + [C.c_int32]
+    L.bmpc_set_estimator_cov.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    L.bmpc_get_cov.argtypes = [C.c_void_p, c_double_p]
     L.bmpc_set_state.argtypes = [C.c_void_p, c_double_p]
     L.bmpc_get_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.bmpc_set_gather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]

@@ -145,9 +145,22 @@ class BatchLinMPC:
         fx = None if fop_minus_xop is None else _vec(fop_minus_xop, self.NM, nx, "fop_minus_xop")
         args = [self._mat(Ahat, nx, nx, "Ahat"), self._mat(Buhat, nx, nu, "Buhat"),
                 self._mat(Bdhat, nx, nd, "Bdhat") if nd else None, self._mat(Cmhat, nym, nx, "Cmhat"),
-                self._mat(Ddmhat, nym, nd, "Ddmhat") if nd else None, self._mat(Khat, nx, nym, "Khat"), fx]
+                self._mat(Ddmhat, nym, nd, "Ddmhat") if nd else None,
+                None if Khat is None else self._mat(Khat, nx, nym, "Khat"), fx]
         check(_lib.lib().bmpc_set_estimator(self._h, *[dptr(a) for a in args], int(nym)))
         self.nym = nym
+
+    def set_estimator_cov(self, P0, Qhat, Rhat):
+        """Time-varying KalmanFilter as the fused observer (bmpc_set_estimator_cov): P̂_0, Q̂, R̂ per model; the gain is
+        recomputed every period by the covariance recursion around the step kernel."""
+        nx, nym = self.nxhat, self.nym
+        self._kf = [self._mat(P0, nx, nx, "P0"), self._mat(Qhat, nx, nx, "Qhat"), self._mat(Rhat, nym, nym, "Rhat")]
+        check(_lib.lib().bmpc_set_estimator_cov(self._h, *[dptr(a) for a in self._kf]))
+
+    def get_cov(self):
+        P = np.zeros((self.NM, self.nxhat, self.nxhat))
+        check(_lib.lib().bmpc_get_cov(self._h, dptr(P)))
+        return np.swapaxes(P, 1, 2)  # column-major on the device
 
     def set_state(self, xhat0):
         check(_lib.lib().bmpc_set_state(self._h, dptr(_vec(xhat0, self.N, self.nxhat, "xhat0"))))

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "bmpc_device.cuh"
+#include "bmpc_kf.cuh"
 #include "bmpc_setup.cuh"
 #include "bmpc_model.cuh"
 #include "bmpc_warp_registry.h"
@@ -78,6 +79,8 @@ struct bmpc_handle {
     bool have_estimator = false;
     int nym = 0;
     DevBuf<double> eA, eBu, eBd, eCm, eDdm, eK, efx, xstate, xcorr, y0m;
+    DevBuf<double> kfP, kfQ, kfR;  // time-varying KalmanFilter: P̂, Q̂, R̂ per model (bmpc_set_estimator_cov)
+    bool kf_on = false;
     bool e_has_fx = false;
     double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather)
     int zg_world = 0, zg_rank = 0;
@@ -413,7 +416,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
     DevBuf<double>* bufs[] = {&h->E, &h->ex, &h->Ht, &h->Ev, &h->exv, &h->Hv, &h->Lv, &h->Hee, &h->K, &h->V, &h->B,
-                              &h->G, &h->J, &h->kx, &h->vx, &h->bx, &h->gx, &h->jx, &h->Mw, &h->Lw, &h->uop,
+                              &h->G, &h->J, &h->kx, &h->vx, &h->bx, &h->gx, &h->jx, &h->Mw, &h->Lw, &h->uop, &h->kfP, &h->kfQ, &h->kfR,
                               &h->yop, &h->t_sig, &h->t_c, &h->sbase, &h->dbound, &h->Pd, &h->xhat0, &h->lastu0,
                               &h->ry, &h->Rhat_y, &h->Rhat_u, &h->d0, &h->Dhat0, &h->Z, &h->u, &h->Jv, &h->F,
                               &h->qt, &h->r, &h->lastu_prev};
@@ -865,6 +868,18 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.zg_world = h->zg_world;
     P.zg_rank = h->zg_rank;
     cudaError_t le;
+    const bool kf = fused_est && h->kf_on;
+    int kf_smem = 0;
+    if (kf) {  // preparestate! of the time-varying KalmanFilter: gain K̂(k) and corrected covariance, before the step
+        const size_t nq = std::max<size_t>(nx, (size_t)h->nym), nym = (size_t)h->nym;
+        kf_smem = (int)((2 * nx * nx + 2 * nq * nq + 2 * nx * nym + nym * nym + nq * nq) * 8);
+        CK(bmpc_host::raise_dyn_smem(reinterpret_cast<const void*>(bmpc::k_kf_cov), kf_smem));
+        bmpc::k_kf_cov<<<(unsigned)h->NM, 64, kf_smem, s>>>((int)h->NM, (int)nx, h->nym, 1, h->eA.p, h->kfQ.p, h->eCm.p, h->kfR.p,
+                                                           h->kfP.p, h->eK.p);
+        le = cudaGetLastError();
+        if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "KalmanFilter covariance kernel launch failed: %s", cudaGetErrorString(le));
+        h->launches++;
+    }
     if (h->warp) {
         bmpc::WarpParams Q = h->wp;
         Q.order = h->order_valid ? h->order[h->order_cur].p : nullptr;
@@ -884,6 +899,13 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     }
     if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(le));
     h->launches++;
+    if (kf) {  // updatestate!: P̂(k+1) = Â P̂(k) Â' + Q̂ (the state prediction ran inside the step kernel)
+        bmpc::k_kf_cov<<<(unsigned)h->NM, 64, kf_smem, s>>>((int)h->NM, (int)nx, h->nym, 2, h->eA.p, h->kfQ.p, h->eCm.p, h->kfR.p,
+                                                           h->kfP.p, h->eK.p);
+        le = cudaGetLastError();
+        if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "KalmanFilter covariance kernel launch failed: %s", cudaGetErrorString(le));
+        h->launches++;
+    }
     h->stepped = true;
     h->last_Z = P.Z;
     h->last_xhat0 = fused_est ? h->xcorr.p : P.xhat0;
@@ -937,7 +959,7 @@ int bmpc_getinfo(bmpc_handle* h, const bmpc_info* info) {
 
 int bmpc_set_estimator(bmpc_handle* h, const double* Ahat, const double* Buhat, const double* Bdhat, const double* Cmhat,
                        const double* Ddmhat, const double* Khat, const double* fop_minus_xop, int32_t nym) {
-    if (!h || !Ahat || !Buhat || !Cmhat || !Khat) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h || !Ahat || !Buhat || !Cmhat) return fail(BMPC_ERR_ARG, "null argument");
     const bmpc_dims& d = h->d;
     if (nym < 1 || nym > d.ny) return fail(BMPC_ERR_ARG, "nym must be 1..ny");
     if (d.nd > 0 && (!Bdhat || !Ddmhat)) return fail(BMPC_ERR_ARG, "Bdhat and Ddmhat are required when nd > 0");
@@ -951,7 +973,13 @@ int bmpc_set_estimator(bmpc_handle* h, const double* Ahat, const double* Buhat, 
         CK(h->eDdm.upload(Ddmhat, NM * nym * nd, s));
     }
     CK(h->eCm.upload(Cmhat, NM * nym * nx, s));
-    CK(h->eK.upload(Khat, NM * nx * nym, s));
+    if (Khat) {
+        CK(h->eK.upload(Khat, NM * nx * nym, s));
+    } else {  // the gain will come from the covariance recursion (bmpc_set_estimator_cov)
+        CK(h->eK.alloc(NM * nx * nym));
+        CK(cudaMemsetAsync(h->eK.p, 0, NM * nx * nym * 8, s));
+    }
+    h->kf_on = false;
     h->e_has_fx = fop_minus_xop != nullptr;
     if (fop_minus_xop) CK(h->efx.upload(fop_minus_xop, NM * nx, s));
     CK(h->xstate.alloc(N * nx));
@@ -961,6 +989,30 @@ int bmpc_set_estimator(bmpc_handle* h, const double* Ahat, const double* Buhat, 
     CK(cudaStreamSynchronize(s));
     h->nym = nym;
     h->have_estimator = true;
+    return BMPC_OK;
+}
+
+int bmpc_set_estimator_cov(bmpc_handle* h, const double* P0, const double* Qhat, const double* Rhat) {
+    if (!h || !P0 || !Qhat || !Rhat) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->have_estimator) return fail(BMPC_ERR_STATE, "bmpc_set_estimator_cov needs bmpc_set_estimator");
+    if (h->d.nxhat > 32 || h->nym > 32) return fail(BMPC_ERR_UNSUPPORTED, "nxhat <= 32 and nym <= 32 are supported");
+    CK(cudaSetDevice(h->d.device));
+    cudaStream_t s = h->stream;
+    const size_t NM = (size_t)h->NM, nx = h->d.nxhat, nym = h->nym;
+    CK(h->kfP.upload(P0, NM * nx * nx, s));
+    CK(h->kfQ.upload(Qhat, NM * nx * nx, s));
+    CK(h->kfR.upload(Rhat, NM * nym * nym, s));
+    CK(cudaStreamSynchronize(s));
+    h->kf_on = true;
+    return BMPC_OK;
+}
+
+int bmpc_get_cov(bmpc_handle* h, double* Phat) {
+    if (!h || !Phat) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->kf_on) return fail(BMPC_ERR_STATE, "bmpc_get_cov needs bmpc_set_estimator_cov");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaMemcpyAsync(Phat, h->kfP.p, (size_t)h->NM * h->d.nxhat * h->d.nxhat * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return BMPC_OK;
 }
 

@@ -13,6 +13,7 @@
 // only the leading Nk blocks of every matrix are used, as in trunc_predmat (:658-681).
 #pragma once
 #include "bmpc_device.cuh"
+#include "bmpc_kf.cuh"
 
 namespace bmpc {
 
@@ -36,82 +37,6 @@ struct MheParams {
     int *status, *iters;
     MheLayout L;
 };
-
-// lower-triangular in-place Cholesky + inverse of a small SPD matrix (n <= 32) by one thread.
-__device__ inline bool small_spd_inverse(const double* A, double* inv, double* L, int n) {
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double a = A[i + n * j];
-            for (int p = 0; p < j; ++p) a -= L[i + n * p] * L[j + n * p];
-            if (i == j) {
-                if (!(a > 0.0) || !isfinite(a)) return false;
-                L[i + n * i] = sqrt(a);
-            } else {
-                L[i + n * j] = a / L[j + n * j];
-            }
-        }
-    // inv = L^-T L^-1, column by column
-    for (int c = 0; c < n; ++c) {
-        double y[32];
-        for (int i = 0; i < n; ++i) {
-            double a = (i == c) ? 1.0 : 0.0;
-            for (int p = 0; p < i; ++p) a -= L[i + n * p] * y[p];
-            y[i] = a / L[i + n * i];
-        }
-        for (int i = n - 1; i >= 0; --i) {
-            double a = y[i];
-            for (int p = i + 1; p < n; ++p) a -= L[p + n * i] * inv[p + n * c];
-            inv[i + n * c] = a / L[i + n * i];
-        }
-    }
-    return true;
-}
-
-
-// Kalman correction of a covariance (correct_estimate_kf!, kalman.jl:1235-1268): out[0:nx*nx] <- (I - K Cm) P with
-// K = P Cm' (Cm P Cm' + R)^-1, raw (not symmetrised).  P (nx x nx, symmetric) in shared memory; scratch: K nx*nym,
-// M nym*nym + max(nx,nym)^2, out 2*max(nx,nym)^2 + nx*nym doubles.  Called by every thread of the CTA.
-template <class Sync>
-__device__ inline void kf_correct_cov(int tid, int nth, Sync sync, int nx, int nym, const double* __restrict__ gCm,
-                                      const double* __restrict__ gRm, const double* sP, double* sK, double* sM,
-                                      double* out) {
-    for (int e = tid; e < nx * nym; e += nth) {  // K <- P Cm'   (nx x nym)
-        const int i = e % nx, j = e / nx;
-        double a = 0.0;
-        for (int k = 0; k < nx; ++k) a = fma(sP[i + nx * k], gCm[j + nym * k], a);
-        sK[e] = a;
-    }
-    sync();
-    for (int e = tid; e < nym * nym; e += nth) {  // M <- Cm P Cm' + R
-        const int i = e % nym, j = e / nym;
-        double a = gRm[e];
-        for (int k = 0; k < nx; ++k) a = fma(gCm[i + nym * k], sK[k + nx * j], a);
-        sM[e] = a;
-    }
-    sync();
-    if (tid == 0) small_spd_inverse(sM, out, sM + nym * nym, nym);  // out[0:nym^2] = M^-1
-    sync();
-    for (int e = tid; e < nym * nym; e += nth) sM[e] = out[e];
-    sync();
-    for (int e = tid; e < nx * nym; e += nth) {  // Kg <- (P Cm') M^-1 into out[nx*nx ...]
-        const int i = e % nx, j = e / nx;
-        double a = 0.0;
-        for (int k = 0; k < nym; ++k) a = fma(sK[i + nx * k], sM[k + nym * j], a);
-        out[nx * nx + e] = a;
-    }
-    sync();
-    for (int e = tid; e < nx * nx; e += nth) {  // Pnew = P - Kg (Cm P) ; (Cm P) = (P Cm')' for symmetric P
-        const int i = e % nx, j = e / nx;
-        double a = sP[e];
-        for (int k = 0; k < nym; ++k) {
-            double cp = 0.0;  // (Cm P)[k, j]
-            for (int l = 0; l < nx; ++l) cp = fma(gCm[k + nym * l], sP[l + nx * j], cp);
-            a = fma(-out[nx * nx + i + nx * k], cp, a);
-        }
-        out[e] = a;
-    }
-    sync();
-}
 
 template <int TEAM>
 __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ StepParams P,

@@ -205,6 +205,47 @@ class SteadyKalmanFilter:
                 + self.model.yop)
 
 
+class KalmanFilter(SteadyKalmanFilter):
+    """Batched time-varying ``KalmanFilter`` (reference src/estimator/kalman.jl:311-525, direct=true):
+    ``preparestate`` = correct_estimate_kf! (:1235-1268, gain from the current P̂, P̂ <- Hermitian((I - K̂ Ĉm) P̂, :L)),
+    ``updatestate`` = predict_estimate_kf! (:1270-1290, P̂ <- Hermitian(Â P̂ Â' + Q̂, :L)).  Host-side numpy version for
+    the x̂0-input seam; ``LinMPC(KalmanFilter(model), fused_estimator=True)`` runs the same recursion on the GPU."""
+
+    def __init__(self, model, nint_u=0, nint_ym=None, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None,
+                 sigmaPint_ym_0=None, sigmaQint_ym=None):
+        self.model = model
+        self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
+        N, nx = model.N, model.nx
+        nym = len(self.i_ym)
+        one = lambda v, n, d: np.full(n, d) if v is None else np.asarray(v, float).reshape(n)
+        sP = np.concatenate([one(sigmaP_0, nx, 1.0 / nx), one(sigmaPint_ym_0, self.nxs, 1.0)])
+        sQ = np.concatenate([one(sigmaQ, nx, 1.0 / nx), one(sigmaQint_ym, self.nxs, 1.0)])
+        self.P0hat, self.Qhat, self.Rhat = np.diag(sP ** 2), np.diag(sQ ** 2), np.diag(one(sigmaR, nym, 1.0) ** 2)
+        self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]
+        self.Phat = np.broadcast_to(self.P0hat, (N, self.nxhat, self.nxhat)).copy()
+        self.Khat = np.zeros((N, self.nxhat, nym))
+        self.xhat0 = np.zeros((N, self.nxhat))
+
+    @staticmethod
+    def _herm_lower(P):
+        L = np.tril(P)
+        return L + np.swapaxes(np.tril(P, -1), 1, 2)
+
+    def preparestate(self, ym, d=None):
+        Cm, P = self.Cmhat, self.Phat
+        PCt = P @ np.swapaxes(Cm, 1, 2)
+        M = Cm @ PCt + self.Rhat
+        self.Khat = np.swapaxes(np.linalg.solve(np.swapaxes(M, 1, 2), np.swapaxes(PCt, 1, 2)), 1, 2)
+        out = SteadyKalmanFilter.preparestate(self, ym, d)
+        self.Phat = self._herm_lower((np.eye(self.nxhat) - self.Khat @ Cm) @ P)
+        return out
+
+    def updatestate(self, u, ym, d=None):
+        out = SteadyKalmanFilter.updatestate(self, u, ym, d)
+        self.Phat = self._herm_lower(self.Ahat @ self.Phat @ np.swapaxes(self.Ahat, 1, 2) + self.Qhat)
+        return out
+
+
 class ManualEstimator(SteadyKalmanFilter):
     """``ManualEstimator`` (reference src/estimator/manual.jl:60-64,150-154): the caller sets x̂ with
     ``setstate``; prepare/update do nothing."""

@@ -51,9 +51,13 @@ class LinMPC:
         self.fused_estimator = bool(fused_estimator)
         if self.fused_estimator:
             if not hasattr(estim, "Khat"):
-                raise ValueError("fused_estimator needs a SteadyKalmanFilter")
-            b.set_estimator(estim.Ahat, estim.Buhat, estim.Cmhat, estim.Khat, estim.Bdhat if nd else None,
+                raise ValueError("fused_estimator needs a SteadyKalmanFilter or a KalmanFilter")
+            tv = hasattr(estim, "P0hat")  # time-varying KalmanFilter: the gain comes from the covariance recursion
+            b.set_estimator(estim.Ahat, estim.Buhat, estim.Cmhat, None if tv else estim.Khat, estim.Bdhat if nd else None,
                             estim.Ddmhat if nd else None, estim.fophat - estim.xophat)
+            if tv:
+                rep = lambda M: np.broadcast_to(M, (N,) + M.shape)
+                b.set_estimator_cov(estim.Phat, rep(estim.Qhat), rep(estim.Rhat))
             b.set_state(estim.xhat0)
             self._y0m = None
         self._push()

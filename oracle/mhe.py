@@ -345,10 +345,13 @@ class KalmanFilter(StateEstimator):
         M = Cm @ P @ Cm.T + self.Rhat
         K = np.linalg.solve(M.T, (P @ Cm.T).T).T
         self.xhat0 = self.xhat0 + K @ (y0m - (Cm @ self.xhat0 + self.Ddmhat @ d0))
-        self.Phat = (np.eye(self.nxhat) - K @ Cm) @ P
+        self.Khat = K
+        Pc = (np.eye(self.nxhat) - K @ Cm) @ P
+        self.Phat = np.tril(Pc) + np.tril(Pc, -1).T           # Hermitian(P̂corr, :L), kalman.jl:1266
 
     def update_estimate(self, u0, y0m, d0):
         if not self.direct:
             self.correct_estimate(y0m, d0)
         self.xhat0 = self.Ahat @ self.xhat0 + self.Buhat @ u0 + self.Bdhat @ d0 + self.fophat - self.xophat
-        self.Phat = self.Ahat @ self.Phat @ self.Ahat.T + self.Qhat
+        Pn = self.Ahat @ self.Phat @ self.Ahat.T + self.Qhat
+        self.Phat = np.tril(Pn) + np.tril(Pn, -1).T           # Hermitian(P̂next, :L), kalman.jl:1288

@@ -233,3 +233,48 @@ def test_host_mapped_zero_copy_equals_staged_copies():
         bM.step_mapped(xh, ry, u, st, resident=k > 0)
         assert (st == bS.status).all() and (st == 0).all()
         assert np.array_equal(uS, u), k
+
+
+@pytest.mark.parametrize("team", [0, 128])
+def test_fused_kalman_filter_equals_host_and_oracle(team):
+    """SURVEY 8f-1, time-varying KalmanFilter (src/estimator/kalman.jl:1235-1290): covariance recursion + gain in
+    k_kf_cov around the step kernel, state update inside it, against the host-side mirror driving the same controller
+    and against the oracle's KalmanFilter (x̂, P̂) on the same data.  Tolerances: u 2e-6 (two interior-point solves of problems that differ by rounding agree to the
+    solver's accuracy, not bitwise), x̂ 1e-6 (the closed loop feeds those u differences back), P̂ 1e-10 (data-independent)."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    from oracle.linmpc import LinModel as OLinModel
+    from oracle.mhe import KalmanFilter as OKF
+    N = 12
+    model, rng = workloads.random_plants(N, 4, 2, 2, seed=78)
+    mk = lambda fused: mpc_b200.LinMPC(mpc_b200.KalmanFilter(model, sigmaP_0=[0.5, 0.4, 0.3, 0.2], sigmaR=[0.7, 1.3]),
+                                       Hp=20, Hc=5, Cwt=1e5, team=team, fused_estimator=fused).setconstraint(
+        umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+    mF, mH = mk(True), mk(False)
+    okf = [OKF(OLinModel(model.A[i], model.Bu[i], model.C[i]), sigmaP_0=[0.5, 0.4, 0.3, 0.2], sigmaR=[0.7, 1.3])
+           for i in range(N)]
+    plantF = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N)
+    plantH = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N)
+    ry = workloads.setpoints(rng, N, 2, 24, period=8)
+    noise = 0.05 * rng.standard_normal((24, N, 2))
+    for k in range(24):
+        yF, yH = plantF.evaloutput() + noise[k], plantH.evaloutput() + noise[k]
+        mF.preparestate(yF)
+        mH.preparestate(yH)
+        uF, uH = mF.moveinput(ry[k]), mH.moveinput(ry[k])
+        assert (mF.batch.status == 0).all() and (mH.batch.status == 0).all()
+        assert np.abs(uF - uH).max() < 2e-6, (k, np.abs(uF - uH).max())
+        xnext, xcorr = mF.batch.get_state()
+        assert np.abs(xcorr - mH.estim.xhat0).max() < 1e-6
+        for i, o in enumerate(okf):
+            o.preparestate(yH[i])
+            assert np.abs(xcorr[i] - o.xhat0).max() < 1e-6 * (1 + np.abs(o.xhat0).max()), (k, i)
+            o.updatestate(uH[i], yH[i])
+        plantF.updatestate(uF)
+        plantH.updatestate(uH)
+        mF.updatestate(uF, yF)
+        mH.updatestate(uH, yH)
+        assert np.abs(xnext - mH.estim.xhat0).max() < 1e-6
+        P = mF.batch.get_cov()
+        assert np.abs(P - mH.estim.Phat).max() < 1e-10 * (1 + np.abs(P).max())
+        assert np.abs(P - np.stack([o.Phat for o in okf])).max() < 1e-10 * (1 + np.abs(P).max())

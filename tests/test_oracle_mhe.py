@@ -99,3 +99,29 @@ def test_mhe_constraint_violation(Cwt):
     mhe.setconstraint(vhatmin=[-100, -100], vhatmax=[-1, -1])
     step()
     assert mhe.Vhat == pytest.approx([-1, -1], abs=5e-2)
+
+
+def test_host_kalman_filter_mirror_equals_oracle():
+    """The batched host-side KalmanFilter of the Python mirror (modelpredictivecontrol.jl_b200/host.py) against the
+    oracle's restatement of src/estimator/kalman.jl:1235-1290 (correct + predict, Hermitian(:L)): x̂ and P̂ to 1e-12."""
+    import mpc_b200
+    from oracle.linmpc import LinModel as OLinModel
+    from oracle.mhe import KalmanFilter as OKF
+    N = 5
+    rng = np.random.default_rng(8)
+    A = 0.6 * rng.standard_normal((N, 3, 3)) / 2
+    Bu, C = rng.standard_normal((N, 3, 2)), rng.standard_normal((N, 2, 3))
+    Bd, Dd = rng.standard_normal((N, 3, 1)), 0.1 * rng.standard_normal((N, 2, 1))
+    op = dict(uop=[1.0, -2.0], yop=[5.0, 3.0], dop=[0.5])
+    g = mpc_b200.KalmanFilter(mpc_b200.LinModel(A, Bu, C, Bd=Bd, Dd=Dd, N=N, **op), sigmaR=[0.5, 2.0])
+    os_ = [OKF(OLinModel(A[i], Bu[i], C[i], Bd=Bd[i], Dd=Dd[i], **op), sigmaR=[0.5, 2.0]) for i in range(N)]
+    for k in range(12):
+        y = 5 + rng.standard_normal((N, 2)); d = 0.5 + rng.standard_normal((N, 1)); u = rng.standard_normal((N, 2))
+        xg = g.preparestate(y, d)
+        for i, o in enumerate(os_):
+            xo = o.preparestate(y[i], d[i])
+            assert np.abs(xg[i] - xo).max() < 1e-12 * (1 + np.abs(xo).max())
+            assert np.abs(g.Phat[i] - o.Phat).max() < 1e-12
+            o.updatestate(u[i], y[i], d[i])
+        g.updatestate(u, y, d)
+        assert np.abs(g.Phat - np.stack([o.Phat for o in os_])).max() < 1e-12
