@@ -148,7 +148,7 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
 
 template <int TEAM>
 int configure(bmpc_handle* h) {
-    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    constexpr int CTA = bmpc::CtaThreads<TEAM>::value;
     const size_t pd_bytes = (size_t)h->nPd2 * 8;
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->d.device));
@@ -235,6 +235,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, E.func, 32, h->smem_bytes));
     if (occ < 1) return BMPC_ERR_UNSUPPORTED;
+    if (const char* e = getenv("BMPC_WARP_OCC")) occ = std::max(1, std::min(occ, atoi(e)));  // tuning: resident warps per SM
     h->team = 32;
     h->teams_per_cta = 1;
     h->grid = std::max(1, std::min(h->d.N, occ * h->num_sms));
@@ -324,7 +325,7 @@ int finalize(bmpc_handle* h) {
 
 template <int TEAM>
 cudaError_t launch_step(bmpc_handle* h, const bmpc::StepParams& P) {
-    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    constexpr int CTA = bmpc::CtaThreads<TEAM>::value;
     bmpc::step_kernel<TEAM><<<h->grid, CTA, h->smem_bytes, h->stream>>>(P);
     return cudaGetLastError();
 }

@@ -1000,11 +1000,16 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
     if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
 }
 
+// threads per CTA: sub-warp teams share a 128-thread CTA; a one-warp team is its own CTA (many CTAs per SM, bounded by
+// the shared memory per instance); larger teams are one CTA each
 template <int TEAM>
-__global__ void __launch_bounds__(TEAM <= 32 ? 128 : TEAM, TEAM == 128 ? 6 : (TEAM == 64 ? 8 : 1))
+struct CtaThreads { static constexpr int value = TEAM < 32 ? 128 : TEAM; };
+
+template <int TEAM>
+__global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((TEAM == 64 || TEAM == 32) ? 8 : 1))
     step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int CTA = TEAM <= 32 ? 128 : TEAM;
+    constexpr int CTA = CtaThreads<TEAM>::value;
     constexpr int TEAMS = CTA / TEAM;
     const int team_id = threadIdx.x / TEAM;
     Team<TEAM> T;
