@@ -35,6 +35,7 @@ struct MheParams {
     const double *y0m, *d0;          // inputs of this period
     double *J_out, *Vhat_out, *X0_out;
     int *status, *iters;
+    unsigned int* counter;  // work queue of this launch (zeroed by the host): instances are handed out dynamically
     MheLayout L;
 };
 
@@ -66,7 +67,15 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
     const int nz = P.nz, n = P.n, m = rt.m, nS = rt.nS, nDr = rt.nDr, nDb = rt.nDb;
     const int nYk = nym * Nk, nXk = nx * Nk, ldE = Q.ldE, ldEX = Q.ldEX;
 
-    for (int inst = blockIdx.x; inst < Q.N; inst += gridDim.x) {
+    // dynamic work queue: the windows that need the interior-point solver (a quarter of them on the C3 workload, 15-40
+    // iterations each) would otherwise pile up on whichever CTA a static stride happens to give them
+    __shared__ int s_inst;
+    for (;;) {
+        if (T.tid == 0) s_inst = (int)atomicAdd(Q.counter, 1u);
+        T.sync();
+        const int inst = s_inst;
+        T.sync();
+        if (inst >= Q.N) break;
         double* Y0m = Q.Y0m + (long)inst * nym * He;
         double* U0 = Q.U0 + (long)inst * nu * He;
         double* D0 = Q.D0 + (long)inst * nd * (He + 1);

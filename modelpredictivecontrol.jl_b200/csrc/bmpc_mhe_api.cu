@@ -40,6 +40,7 @@ struct bmhe_handle {
     // io staging
     DevBuf<double> y0m, d0, u0, Jv, Vhat, X0;
     DevBuf<int> status, iters;
+    DevBuf<unsigned int> counter;
     int64_t launches = 0;
 };
 
@@ -223,6 +224,9 @@ static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, con
     Q.row_kind = h->t_kind.p; Q.row_bidx = h->t_bidx.p; Q.Pd = h->Pd.p; Q.sPd = sh * h->nPd;
     Q.y0m = h->y0m.p; Q.d0 = h->d0.p; Q.J_out = h->Jv.p; Q.Vhat_out = Vhat ? h->Vhat.p : nullptr; Q.X0_out = X0 ? h->X0.p : nullptr;
     Q.status = h->status.p; Q.iters = h->iters.p; Q.L = h->L;
+    if (!h->counter.p) CK(h->counter.alloc(1));
+    CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned int), s));
+    Q.counter = h->counter.p;
     bmpc::mhe_step_kernel<256><<<h->grid, 256, h->smem_bytes, s>>>(P, Q);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE kernel launch failed: %s", cudaGetErrorString(le));
@@ -300,6 +304,7 @@ int bmhe_destroy(bmhe_handle* h) {
     for (auto* b : ib) b->release();
     h->t_pi.release();
     h->t_pj.release();
+    h->counter.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BMPC_OK;
