@@ -35,12 +35,14 @@ struct MheParams {
     const double *y0m, *d0;          // inputs of this period
     double *J_out, *Vhat_out, *X0_out;
     int *status, *iters;
+    double* Hscratch;       // nullptr: the Hessian lives in shared memory
+    long sHs;
     unsigned int* counter;  // work queue of this launch (zeroed by the host): instances are handed out dynamically
     MheLayout L;
 };
 
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ StepParams P,
+template <int TEAM, int MINB = 1>
+__global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_constant__ StepParams P,
                                                          const __grid_constant__ MheParams Q) {
     extern __shared__ __align__(128) double smem[];
     Team<TEAM> T;
@@ -53,7 +55,9 @@ __global__ void __launch_bounds__(TEAM) mhe_step_kernel(const __grid_constant__ 
     c.x = smem + L.x; c.xb = smem + L.xb; c.q = smem + L.q; c.rd = smem + L.rd; c.rhs = smem + L.rhs; c.dx = smem + L.dx;
     c.invd = smem + L.invd; c.yb = smem + L.yb; c.ybd = smem + L.ybd; c.wd = smem + L.wd; c.s = smem + L.s;
     c.lam = smem + L.lam; c.h = smem + L.h; c.rp = smem + L.rp; c.t = smem + L.t; c.ds = smem + L.ds;
-    c.dl = smem + L.dl; c.Hv = smem + L.Hv; c.Phi = smem + L.Phi;
+    c.dl = smem + L.dl; c.Phi = smem + L.Phi;
+    // the rebuilt Hessian: shared memory, or (two CTAs per SM) a per-CTA scratch slice that stays in L2
+    c.Hv = Q.Hscratch ? Q.Hscratch + (long)blockIdx.x * Q.sHs : smem + L.Hv;
     c.F = nullptr; c.tY = nullptr; c.fx = nullptr;
     double* sF = smem + L.F;
     double* sFX = smem + L.FX;
