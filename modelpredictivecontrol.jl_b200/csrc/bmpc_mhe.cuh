@@ -35,6 +35,12 @@ struct MheParams {
     const double *y0m, *d0;          // inputs of this period
     double *J_out, *Vhat_out, *X0_out;
     int *status, *iters;
+    // IPM warm start (moving window only): multipliers of the previous period [N x ws_stride], 1/0 flag per instance,
+    // and the row map of the one-block window shift (new row r <- old row ws_map[r], -1: no predecessor)
+    double* lam_ws;
+    int* ws_flag;
+    const int* ws_map;
+    int ws_stride, use_ws;
     double* Hscratch;       // nullptr: the Hessian lives in shared memory
     long sHs;
     unsigned int* counter;  // work queue of this launch (zeroed by the host): instances are handed out dynamically
@@ -245,10 +251,39 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
         smin = (m > 0) ? T.min(smin) : 0.0;
         int status = ST_OPTIMAL, iters = 0;
         const bool feasible = (m == 0) || (bad == 0 && smin >= -1e-12 * hscale);
-        if (!feasible) ipm_solve(T, c, P, Hee, qs, hscale, status, iters);
+        double* gZ = Q.Z + (long)inst * (neps + nx + nx * He);
+        if (!feasible) {
+            // warm start from the previous window shifted by one block: Z̃s of set_warmstart_mhe! (arrival state =
+            // x̂0arr_old, Ŵ shifted, transcription.jl:967-1001) and the multipliers of the rows that stay in the window
+            const double* lam0 = nullptr;
+            if (Q.use_ws && Q.moving && Q.ws_flag[inst] != 0) {
+                const double* glw = Q.lam_ws + (long)inst * Q.ws_stride;
+                for (int r = T.tid; r < m; r += TEAM) {
+                    const int o = Q.ws_map[r];
+                    c.dl[r] = o >= 0 ? glw[o] : 0.0;
+                }
+                for (int j = T.tid; j < nz; j += TEAM)
+                    c.x[j] = j < nx ? x0arr[j] : ((j + nx < nx + nx * He) ? gZ[neps + j + nx] : 0.0);
+                if (neps && T.tid == 0) c.x[nz] = gZ[0];
+                T.sync();
+                dense_apply(T, c, c.x, c.yb);
+                T.sync();
+                for (int r = T.tid; r < m; r += TEAM) c.s[r] = c.h[r] - row_gx(c, r, c.x, c.yb);
+                T.sync();
+                lam0 = c.dl;
+            }
+            ipm_solve(T, c, P, Hee, qs, hscale, status, iters, lam0);
+            if (Q.use_ws) {
+                const bool keep = status == ST_OPTIMAL && iters > 0;
+                if (keep)
+                    for (int r = T.tid; r < m; r += TEAM) Q.lam_ws[(long)inst * Q.ws_stride + r] = c.lam[r];
+                if (T.tid == 0) Q.ws_flag[inst] = keep ? 1 : 0;
+            }
+        } else if (Q.use_ws && T.tid == 0) {
+            Q.ws_flag[inst] = 0;
+        }
         T.sync();
         // ---- outputs: Z̃ (reference order), getstate! ----
-        double* gZ = Q.Z + (long)inst * (neps + nx + nx * He);
         if (status == ST_INFEASIBLE) {
             // warm start Z̃s (set_warmstart_mhe!, transcription.jl:967-1001): arrival = x̂0arr_old, Ŵ shifted
             for (int j = T.tid; j < nz; j += TEAM) {

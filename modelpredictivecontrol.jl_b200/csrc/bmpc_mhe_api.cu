@@ -41,7 +41,9 @@ struct bmhe_handle {
     DevBuf<double> y0m, d0, u0, Jv, Vhat, X0;
     DevBuf<int> status, iters;
     DevBuf<unsigned int> counter;
-    DevBuf<double> Hscratch;
+    DevBuf<double> Hscratch, lam_ws;
+    DevBuf<int> ws_flag, t_wsmap;
+    bool warm_start = true;
     bool two_ctas = false;
     int64_t launches = 0;
 };
@@ -107,6 +109,22 @@ int compile_rows(bmhe_handle* h, int Nk) {
     const int nDr = (int)dr_base.size(), nDb = (int)pd_src.size();
     // no eps >= 0 row: the softness weights are non-negative, so eps < 0 is never optimal (see bmpc_set_constraints)
     const int m = nS + nDr;
+    // row map of the one-block window shift (moving window, Nk = He on both sides): the arrival rows take over the
+    // multipliers of the old X̂ block 0 (same bounds, same state), every Ŵ / X̂ / V̂ block b those of the old block b + 1
+    std::vector<int> ws_map(std::max(m, 1), -1);
+    {
+        int nA = 0, nWb = 0, nVb = 0;
+        for (int k = 0; k < nx; ++k) { nA += f[k] + f[nx + k]; nWb += f[2 * nx + k] + f[3 * nx + k]; }
+        for (int k = 0; k < nym; ++k) nVb += f[4 * nx + k] + f[4 * nx + nym + k];
+        const int nXb = nA, offW = nA, offX = offW + Nk * nWb, offV = offX + Nk * nXb;
+        for (int r = 0; r < nA; ++r) ws_map[r] = offX + r;
+        for (int b = 0; b + 1 < Nk; ++b) {
+            for (int r = 0; r < nWb; ++r) ws_map[offW + b * nWb + r] = offW + (b + 1) * nWb + r;
+            for (int r = 0; r < nXb; ++r) ws_map[offX + b * nXb + r] = offX + (b + 1) * nXb + r;
+            for (int r = 0; r < nVb; ++r) ws_map[offV + b * nVb + r] = offV + (b + 1) * nVb + r;
+        }
+        if (offV + Nk * nVb != m) return fail(BMPC_ERR_STATE, "internal: MHE row blocks do not add up (%d != %d)", offV + Nk * nVb, m);
+    }
     std::vector<int> var_ptr(nz + 1, 0), var_row(nS), var_sgn(nS, 1);
     for (int g = 0; g < nS; ++g) var_ptr[s_i1[g] + 1]++;
     for (int j = 0; j < nz; ++j) var_ptr[j + 1] += var_ptr[j];
@@ -131,6 +149,11 @@ int compile_rows(bmhe_handle* h, int Nk) {
     CK(h->t_dbrmin.upload(db_rmin, s)); CK(h->t_drbase.upload(dr_base, s)); CK(h->t_drsrc.upload(dr_src, s));
     CK(h->t_kind.upload(kind, s)); CK(h->t_bidx.upload(bidx, s)); CK(h->t_pdsrc.upload(pd_src, s));
     CK(h->t_pi.upload(pi, s)); CK(h->t_pj.upload(pj, s));
+    CK(h->t_wsmap.upload(ws_map, s));
+    CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(m, 1))));
+    CK(h->ws_flag.alloc((size_t)h->d.N));
+    CK(cudaMemsetAsync(h->ws_flag.p, 0, (size_t)h->d.N * sizeof(int), s));
+    if (const char* e = getenv("BMPC_WARM")) h->warm_start = atoi(e) != 0;
     bmpc::RowTables& rt = h->rt;
     rt.nS = nS; rt.nDr = nDr; rt.nDb = nDb; rt.m = m;
     rt.s_i1 = h->t_si1.p; rt.s_i2 = h->t_si2.p; rt.s_ch = h->t_sch.p; rt.row_sig = h->t_sig.p; rt.row_c = h->t_c.p;
@@ -241,6 +264,8 @@ static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, con
     if (!h->counter.p) CK(h->counter.alloc(1));
     CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned int), s));
     Q.counter = h->counter.p;
+    Q.lam_ws = h->lam_ws.p; Q.ws_flag = h->ws_flag.p; Q.ws_map = h->t_wsmap.p; Q.ws_stride = even(std::max(h->rt.m, 1));
+    Q.use_ws = h->warm_start ? 1 : 0;
     Q.Hscratch = h->two_ctas ? h->Hscratch.p : nullptr;
     Q.sHs = even(h->nz * (h->nz + 1) / 2);
     if (h->two_ctas)
@@ -325,6 +350,9 @@ int bmhe_destroy(bmhe_handle* h) {
     h->t_pj.release();
     h->counter.release();
     h->Hscratch.release();
+    h->lam_ws.release();
+    h->ws_flag.release();
+    h->t_wsmap.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BMPC_OK;
