@@ -974,13 +974,14 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         if (stall >= 2) break;
         // ... and before the collapse: an infeasible problem's iterates drift along a Farkas ray for 20-30 iterations
         // (primal residual on a plateau, complementarity GROWING by orders of magnitude, h'lam < 0) -- measured on
-        // infeasible MHE windows, tools/studies/mhe_infeas.py.  Checked every 8 iterations from the 16th on; all three
+        // infeasible MHE windows, tools/studies/mhe_infeas.py.  Checked every 4 iterations from the 8th on (every 8 from the
+        // 16th until tools/studies/mhe_infeas2.py showed the same false-positive set and 6 fewer iterations per infeasible window); all three
         // signs at TWO consecutive checkpoints end the solve, and only for problems without a slack variable (with one,
         // the dense rows can always be satisfied and a long plateau is just a hard but feasible problem).
         if (it == 0) mu_first = mu;
-        if (P.neps == 0 && (it & 7) == 0) {
+        if (P.neps == 0 && (it & 3) == 0) {
             bool ray = false;
-            if (it >= 16 && e_p > 0.5 * ep_chk && e_p > 1e-4 * hscale && mu > 100.0 * mu_first) {
+            if (it >= 8 && e_p > 0.5 * ep_chk && e_p > 1e-4 * hscale && mu > 100.0 * mu_first) {
                 double hl = 0.0;
                 for (int r = T.tid; r < m; r += TEAM) hl = fma(c.h[r], c.lam[r], hl);
                 ray = T.sum(hl) < 0.0;

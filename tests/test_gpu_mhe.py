@@ -161,3 +161,36 @@ def test_mhe_with_integrators_shared_model():
     os_ = [OMHE(oms[0], He=He) for _ in range(N)]
     worst, _ = run_both(g, os_, rng, 2 * He + 2, 0, 2, 2)
     print("MHE integrators worst", worst)
+
+
+def test_mhe_status_agreement_many_windows():
+    """Feasible / infeasible classification on many windows: hard bounds tight enough that a large share of the windows
+    is infeasible (sensor noise against |v̂| <= 2); the GPU status (two-collapsed-steps exit, Farkas-ray checkpoints)
+    must equal the exact oracle's on every window, and feasible windows must agree on x̂ (5e-6 / 1e-9)."""
+    import mpc_b200
+    N, He = 40, 6
+    gm, oms, rng = make(N, 31, nx=4, nd=0)
+    kw = dict(xhatmin=[-10] * 4, xhatmax=[10] * 4, whatmin=[-0.5] * 4, whatmax=[0.5] * 4, vhatmin=[-2.0] * 2,
+              vhatmax=[2.0] * 2)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0]).setconstraint(**kw)
+    os_ = [OMHE(m, He=He, nint_ym=0).setconstraint(**kw) for m in oms]
+    x = np.zeros((N, 4))
+    ninf = nfeas_active = 0
+    for k in range(14):
+        u = rng.choice([-1.0, 1.0], (N, 2))
+        x = np.einsum("nij,nj->ni", gm.A, x) + np.einsum("nij,nj->ni", gm.Bu, u - gm.uop) + rng.standard_normal((N, 4)) / 4
+        y = np.einsum("nij,nj->ni", gm.C, x) + gm.yop + rng.standard_normal((N, 2))
+        xg = g.preparestate(y).copy()
+        for i, o in enumerate(os_):
+            xo = o.preparestate(y[i])
+            assert g.status[i] == o.last_qp["status"], (k, i, g.status[i], o.last_qp["status"], g.iters[i])
+            if g.status[i] == 0:
+                tol = 5e-6 if g.iters[i] > 0 else 1e-9
+                assert np.abs(xg[i] - xo).max() < tol * (1 + np.abs(xo).max()), (k, i, g.iters[i])
+                nfeas_active += int(g.iters[i] > 0)
+            else:
+                ninf += 1
+            o.updatestate(u[i], y[i])
+        g.updatestate(u, y)
+    assert ninf > 40 and nfeas_active > 40, (ninf, nfeas_active)
+    print("MHE status agreement: infeasible windows", ninf, "feasible active windows", nfeas_active, "of", N * 14)
