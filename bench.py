@@ -364,7 +364,7 @@ def main():
         "gather": {"mode": gather_mode, "equals_ncclAllGather": gather_check},
         "solver": {"mean_ipm_iters_per_instance": mean_iters, "unconstrained_exit_fraction": frac_exit,
                    "non_optimal_statuses": n_nonopt, "tol": 1e-11, "launch": b.launch_info()},
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+        "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA; B200's FP64 tensor rate equals its FP64 vector rate)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                      "traffic": traffic, "peak_source": "profiles/fp64_peak_r01.json (cuBLAS DGEMM 8192^3 measured on this pool; "
                      "MEASURED_PEAKS.json has no fp64 entry)", "algorithmic_flops_per_instance_step": fl_step,
                      "cholesky_flops_per_instance_step": fl_chol, "achieved_cholesky_tflops": fl_chol * N / (ms_per_step * 1e-3) / 1e12,
