@@ -58,6 +58,15 @@ def test_argument_validation_without_device():
     assert L.bmpc_create(C.byref(h), C.byref(dims), nb) == _lib.ERR_ARG
     assert L.bmpc_step(None, None) == _lib.ERR_ARG
     assert L.bmpc_destroy(None) == _lib.OK
+    # entry points added for the prediction-form MHE and the time-varying KalmanFilter: null handles are refused
+    assert L.bmhe_update_solve(None, None, None, None, None, None, None, None, None, None, None) == _lib.ERR_ARG
+    assert L.bmpc_set_estimator_cov(None, None, None, None) == _lib.ERR_ARG
+    assert L.bmpc_get_cov(None, None) == _lib.ERR_ARG
+    mh = C.c_void_p()
+    md = _lib.MheDims(N=2, nu=1, nym=1, nd=0, nxhat=40, He=3, neps=0, direct=0)
+    assert L.bmhe_create(C.byref(mh), C.byref(md)) == _lib.ERR_UNSUPPORTED  # nxhat > 32
+    md.nxhat, md.He = 2, 0
+    assert L.bmhe_create(C.byref(mh), C.byref(md)) == _lib.ERR_ARG
 
 
 def test_host_mirror_constructors():
