@@ -344,7 +344,7 @@ def init_predmat(estim, Hp, Hc, nb):
 
 @dataclasses.dataclass
 class ControllerConstraint:
-    """Numeric content of ``ControllerConstraint`` (src/controller/construct.jl:126-199), nw = 0."""
+    """Numeric content of ``ControllerConstraint`` (src/controller/construct.jl:126-199)."""
     U0min: np.ndarray
     U0max: np.ndarray
     DUmin: np.ndarray
@@ -361,6 +361,11 @@ class ControllerConstraint:
     C_ymax: np.ndarray
     c_xmin: np.ndarray
     c_xmax: np.ndarray
+    Wmin: np.ndarray = None     # custom linear constraints (nw*(Hp+1),), construct.jl:158-159
+    Wmax: np.ndarray = None
+    C_wmin: np.ndarray = None
+    C_wmax: np.ndarray = None
+    Fw: np.ndarray = None
     A: np.ndarray = None
     b: np.ndarray = None
     i_b: np.ndarray = None
@@ -372,12 +377,15 @@ class ControllerConstraint:
 class LinMPC:
     """Restatement of ``LinMPC`` (src/controller/linmpc.jl:3-111, kw constructors :229-316).
 
-    Only the SingleShooting transcription, no custom ``W`` constraints (nw = 0): the scope
-    of SURVEY section 8(a).  ``estim`` is a SteadyKalmanFilter (default) or ManualEstimator.
+    Only the SingleShooting transcription: the scope of SURVEY section 8(a), plus the custom linear
+    constraints ``Wmin <= Wy Ŷe + Wu Ue + Wd D̂e + Wr R̂e <= Wmax`` of section 8(f-3) (validate_custom_lincon
+    construct.jl:666-695, relaxW :1086-1160, linconstraint_custom! execute.jl:337-366), restated here ahead of the
+    CUDA path and pinned by tests/test_oracle_linmpc.py to test/3_test_predictive_control.jl:466-496.
+    ``estim`` is a SteadyKalmanFilter (default) or ManualEstimator.
     """
 
     def __init__(self, model_or_estim, Hp=None, Hc=DEFAULT_HC, Mwt=None, Nwt=None, Lwt=None,
-                 M_Hp=None, N_Hc=None, L_Hp=None, Cwt=DEFAULT_CWT, **kwargs):
+                 M_Hp=None, N_Hc=None, L_Hp=None, Cwt=DEFAULT_CWT, Wy=None, Wu=None, Wd=None, Wr=None, **kwargs):
         estim = model_or_estim if isinstance(model_or_estim, StateEstimator) else SteadyKalmanFilter(model_or_estim, **kwargs)
         model = estim.model
         self.estim, self.model = estim, model
@@ -415,6 +423,17 @@ class LinMPC:
         else:
             self.Ptilde_u, self.Ptilde_Du, self.Etilde, self.etilde_x = self.Pu, PDu, self.E, self.ex
         inf = np.inf
+        # validate_custom_lincon (construct.jl:666-695): nw rows, missing matrices are zero
+        given = [np.atleast_2d(np.asarray(W, float)) for W in (Wy, Wu, Wd, Wr) if W is not None]
+        nw = given[0].shape[0] if given else 0
+        mat = lambda W, ncol: np.zeros((nw, ncol)) if W is None else np.atleast_2d(np.asarray(W, float)).reshape(nw, ncol)
+        self.Wy, self.Wu, self.Wd, self.Wr = mat(Wy, ny), mat(Wu, nu), mat(Wd, nd), mat(Wr, ny)
+        self.nw = nw
+        rd = lambda W: np.kron(np.eye(Hp + 1), W)                    # repeatdiag(W, Hp+1), construct.jl:922-925
+        self.Wbar_y, self.Wbar_u, self.Wbar_d, self.Wbar_r = rd(self.Wy), rd(self.Wu), rd(self.Wd), rd(self.Wr)
+        # relaxW (construct.jl:1138-1160): Ew = W̄y [0; E] + W̄u [Pu; pu], pu = last nu rows of Pu
+        self.Ew = (self.Wbar_y @ np.vstack([np.zeros((ny, nZ)), self.E])
+                   + self.Wbar_u @ np.vstack([self.Pu, self.Pu[-nu:]]))
         # init_defaultcon_mpc defaults, construct.jl:904-921
         self.con = ControllerConstraint(
             U0min=np.full(nu * Hp, -inf), U0max=np.full(nu * Hp, inf),
@@ -424,7 +443,9 @@ class LinMPC:
             C_umin=np.zeros(nu * Hp), C_umax=np.zeros(nu * Hp),
             C_dumin=np.zeros(nu * Hc), C_dumax=np.zeros(nu * Hc),
             C_ymin=np.ones(ny * Hp), C_ymax=np.ones(ny * Hp),
-            c_xmin=np.ones(nx), c_xmax=np.ones(nx))
+            c_xmin=np.ones(nx), c_xmax=np.ones(nx),
+            Wmin=np.full(nw * (Hp + 1), -inf), Wmax=np.full(nw * (Hp + 1), inf),
+            C_wmin=np.ones(nw * (Hp + 1)), C_wmax=np.ones(nw * (Hp + 1)), Fw=np.zeros(nw * (Hp + 1)))
         self.Uop, self.Yop, self.Dop = np.tile(model.uop, Hp), np.tile(model.yop, Hp), np.tile(model.dop, Hp)
         self._rebuild_constraints()
         # init_quadprog, construct.jl:837-845
@@ -456,7 +477,9 @@ class LinMPC:
             A_DUmin, A_DUmax = -np.hstack([PDu, col(c.C_dumin)]), np.hstack([PDu, -col(c.C_dumax)])
             A_Ymin, A_Ymax = -np.hstack([self.E, col(c.C_ymin)]), np.hstack([self.E, -col(c.C_ymax)])
             A_xmin, A_xmax = -np.hstack([self.ex, col(c.c_xmin)]), np.hstack([self.ex, -col(c.c_xmax)])
+            A_Wmin, A_Wmax = -np.hstack([self.Ew, col(c.C_wmin)]), np.hstack([self.Ew, -col(c.C_wmax)])
         else:
+            A_Wmin, A_Wmax = -self.Ew, self.Ew
             A_Umin, A_Umax = -self.Pu, self.Pu
             A_DUmin, A_DUmax = -PDu, PDu
             A_Ymin, A_Ymax = -self.E, self.E
@@ -474,15 +497,17 @@ class LinMPC:
         i_DUmin = fin(c.DUmin) & ~fin(Zmin[:nZ])
         i_DUmax = fin(c.DUmax) & ~fin(Zmax[:nZ])
         c.i_b = np.concatenate([fin(c.U0min), fin(c.U0max), i_DUmin, i_DUmax,
-                                fin(c.Y0min), fin(c.Y0max), fin(c.xhat0min), fin(c.xhat0max)])
-        c.A = np.vstack([A_Umin, A_Umax, A_DUmin, A_DUmax, A_Ymin, A_Ymax, A_xmin, A_xmax])
+                                fin(c.Y0min), fin(c.Y0max), fin(c.Wmin), fin(c.Wmax),
+                                fin(c.xhat0min), fin(c.xhat0max)])
+        c.A = np.vstack([A_Umin, A_Umax, A_DUmin, A_DUmax, A_Ymin, A_Ymax, A_Wmin, A_Wmax, A_xmin, A_xmax])
         c.Zmin, c.Zmax = Zmin, Zmax
 
     def setconstraint(self, umin=None, umax=None, dumin=None, dumax=None, ymin=None, ymax=None,
                       xhatmin=None, xhatmax=None, Umin=None, Umax=None, DUmin=None, DUmax=None,
                       Ymin=None, Ymax=None, c_umin=None, c_umax=None, c_dumin=None, c_dumax=None,
                       c_ymin=None, c_ymax=None, c_xhatmin=None, c_xhatmax=None,
-                      C_umin=None, C_umax=None, C_dumin=None, C_dumax=None, C_ymin=None, C_ymax=None):
+                      C_umin=None, C_umax=None, C_dumin=None, C_dumax=None, C_ymin=None, C_ymax=None,
+                      wmin=None, wmax=None, Wmin=None, Wmax=None, c_wmin=None, c_wmax=None, C_wmin=None, C_wmax=None):
         """src/controller/construct.jl:324-559 (same argument meaning; ASCII keyword names)."""
         c, Hp, Hc = self.con, self.Hp, self.Hc
         nu, ny, nx = self.model.nu, self.model.ny, self.estim.nxhat
@@ -506,10 +531,15 @@ class LinMPC:
         elif Ymin is not None: c.Y0min = chk(Ymin, ny * Hp, "Ymin") - self.Yop
         if Ymax is None and ymax is not None: c.Y0max = np.tile(chk(ymax, ny, "ymax"), Hp) - self.Yop
         elif Ymax is not None: c.Y0max = chk(Ymax, ny * Hp, "Ymax") - self.Yop
+        nw = self.nw
+        if Wmin is None and wmin is not None: c.Wmin = np.tile(chk(wmin, nw, "wmin"), Hp + 1)      # construct.jl:410-418
+        elif Wmin is not None: c.Wmin = chk(Wmin, nw * (Hp + 1), "Wmin").copy()
+        if Wmax is None and wmax is not None: c.Wmax = np.tile(chk(wmax, nw, "wmax"), Hp + 1)
+        elif Wmax is not None: c.Wmax = chk(Wmax, nw * (Hp + 1), "Wmax").copy()
         if xhatmin is not None: c.xhat0min = chk(xhatmin, nx, "xhatmin") - self.estim.xophat
         if xhatmax is not None: c.xhat0max = chk(xhatmax, nx, "xhatmax") - self.estim.xophat
         ecrs = [c_umin, c_umax, c_dumin, c_dumax, c_ymin, c_ymax, c_xhatmin, c_xhatmax,
-                C_umin, C_umax, C_dumin, C_dumax, C_ymin, C_ymax]
+                C_umin, C_umax, C_dumin, C_dumax, C_ymin, C_ymax, c_wmin, c_wmax, C_wmin, C_wmax]
         if any(e is not None for e in ecrs):
             if self.neps != 1:
                 raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
@@ -519,7 +549,8 @@ class LinMPC:
             rep = lambda small, big, k: np.tile(a(small), k) if (big is None and small is not None) else (None if big is None else a(big))
             for name, small, big, k in (("C_umin", c_umin, C_umin, Hp), ("C_umax", c_umax, C_umax, Hp),
                                         ("C_dumin", c_dumin, C_dumin, Hc), ("C_dumax", c_dumax, C_dumax, Hc),
-                                        ("C_ymin", c_ymin, C_ymin, Hp), ("C_ymax", c_ymax, C_ymax, Hp)):
+                                        ("C_ymin", c_ymin, C_ymin, Hp), ("C_ymax", c_ymax, C_ymax, Hp),
+                                        ("C_wmin", c_wmin, C_wmin, Hp + 1), ("C_wmax", c_wmax, C_wmax, Hp + 1)):
                 v = rep(small, big, k)
                 if v is not None:
                     if (v < 0).any():
@@ -546,6 +577,7 @@ class LinMPC:
             self.d0 = np.asarray(d, float) - m.dop
             self.Dhat0 = np.asarray(Dhat, float) - self.Dop
         self.Rhat_y, self.Rhat_u = np.asarray(Rhat_y, float), np.asarray(Rhat_u, float)
+        self.ry = np.asarray(ry, float).reshape(-1)
         F = self.B + self.K @ self.estim.xhat0 + self.V @ self.lastu0
         if m.nd > 0:
             F = F + self.G @ self.d0 + self.J @ self.Dhat0
@@ -569,9 +601,21 @@ class LinMPC:
         if self.model.nd > 0:
             fx = fx + self.gx @ self.d0 + self.jx @ self.Dhat0
         c.fx = fx
+        # linconstraint_custom! + linconstraint_custom_outputs! (execute.jl:337-366): Fw in ABSOLUTE units
+        m = self.model
+        Fw = np.zeros(self.nw * (self.Hp + 1))
+        if self.nw:
+            Ue = np.concatenate([self.Tu_lastu0 + self.Uop, self.lastu0 + m.uop])
+            Fw = Fw + self.Wbar_u @ Ue
+            if m.nd > 0:
+                Fw = Fw + self.Wbar_d @ np.concatenate([self.d0 + m.dop, self.Dhat0 + self.Dop])
+            Fw = Fw + self.Wbar_r @ np.concatenate([self.ry, self.Rhat_y])
+            Fw = Fw + self.Wbar_y @ np.concatenate([self.yhat, self.F + self.Yop])
+        c.Fw = Fw
         c.b = np.concatenate([-c.U0min + self.Tu_lastu0, c.U0max - self.Tu_lastu0,
                               -c.DUmin, c.DUmax,
                               -c.Y0min + self.F, c.Y0max - self.F,
+                              -c.Wmin + Fw, c.Wmax - Fw,
                               -c.xhat0min + fx, c.xhat0max - fx])
 
     def warmstart(self):

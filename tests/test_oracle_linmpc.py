@@ -236,3 +236,53 @@ def test_qp_solver_against_bruteforce():
         sol = qp.solve_qp(H, q, G, h)
         assert sol["status"] == qp.OPTIMAL
         assert sol["z"] == pytest.approx(bz, abs=1e-9)
+
+
+def _model2_with_disturbance():
+    # test/3_test_predictive_control.jl:466-467: LinModel([tf(2,[10,1]) tf(0.1,[7,1])], 3.0, i_d=[2]) with
+    # uop=25, dop=30, yop=50, realised as two first-order ZOH states (SURVEY App. D-3 for the (b, c) split)
+    A1, B1, C1 = zoh_first_order(2, 10, 3.0)
+    A2, B2, C2 = zoh_first_order(0.1, 7, 3.0)
+    A = np.diag([A1[0, 0], A2[0, 0]])
+    Bu, Bd = np.array([[B1[0, 0]], [0.0]]), np.array([[0.0], [B2[0, 0]]])
+    C = np.array([[C1[0, 0], C2[0, 0]]])
+    return LinModel(A, Bu, C, Bd=Bd, Dd=np.zeros((1, 1)), Ts=3.0, uop=[25], dop=[30], yop=[50])
+
+
+@pytest.mark.parametrize("kw,wmin,wmax,steps", [
+    (dict(Wy=[[1]]), 36, 75, [(0, "Yhat", 36), (100, "Yhat", 75)]),
+    (dict(Wu=[[1]]), 4, 20, [(0, "U", 4), (100, "U", 20)]),
+    (dict(Wd=[[1]], Wy=[[1]]), 56, 95, [(0, "Yhat", 56 - 30), (100, "Yhat", 95 - 30)]),
+    (dict(Wr=[[1]], Wy=[[1]]), 52, 175, [(21, "Yhat", 52 - 21), (100, "Yhat", 175 - 100)]),
+])
+def test_custom_linear_constraints_known_answers(kw, wmin, wmax, steps):
+    """test/3_test_predictive_control.jl:468-496: custom linear constraints Wy/Wu/Wd/Wr (hard, Cwt = Inf): the whole
+    predicted trajectory sits on the active custom bound (the reference's own atol = 1e-1)."""
+    mpc = LinMPC(_model2_with_disturbance(), Nwt=[0], Cwt=np.inf, Hp=50, Hc=50, **kw)
+    mpc.setconstraint(wmin=[wmin], wmax=[wmax])
+    mpc.preparestate([50], [30])
+    for ry, key, expect in steps:
+        mpc.moveinput([ry], [30])
+        assert mpc.last_status == qp.OPTIMAL
+        assert np.allclose(mpc.getinfo()[key], expect, atol=1e-1), (kw, ry, mpc.getinfo()[key][:5])
+
+
+def test_custom_linear_constraints_matrices():
+    """test/3_test_predictive_control.jl:53-64: W̄y = repeatdiag(Wy, Hp+1) and friends; relaxW's Ew (construct.jl:1138-1160)
+    reproduces W = Ew Z + Fw for a random Z."""
+    rng = np.random.default_rng(0)
+    m = _model2_with_disturbance()
+    Wy, Wu, Wd, Wr = rng.standard_normal((2, 1)), rng.standard_normal((2, 1)), rng.standard_normal((2, 1)), rng.standard_normal((2, 1))
+    mpc = LinMPC(m, Hp=7, Hc=3, Wy=Wy, Wu=Wu, Wd=Wd, Wr=Wr)
+    assert np.allclose(mpc.Wbar_y, np.kron(np.eye(8), Wy)) and mpc.Wbar_y.shape == (16, 8)
+    mpc.preparestate([52], [31])
+    mpc.setconstraint(wmin=[-1e3, -1e3], wmax=[1e3, 1e3])
+    mpc.moveinput([55], [31])
+    Z = mpc.Ztilde
+    info = mpc.getinfo()
+    Ye = np.concatenate([info["yhat"], info["Yhat"]])
+    Ue = np.concatenate([info["U"], info["U"][-1:]])
+    De = np.full(8, 31.0)
+    Re = np.full(8, 55.0)
+    W = mpc.Wbar_y @ Ye + mpc.Wbar_u @ Ue + mpc.Wbar_d @ De + mpc.Wbar_r @ Re
+    assert np.allclose(W, mpc.Ew @ Z[:3] + mpc.con.Fw, atol=1e-9)
