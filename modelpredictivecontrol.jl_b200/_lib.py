@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbmpc.so")
+# BMPC_LIB: another build of the same library (instrumented study builds, tools/studies); never a CPU implementation
+LIB_PATH = os.environ.get("BMPC_LIB") or os.path.join(HERE, "libbmpc.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 STATUS_OPTIMAL, STATUS_ITERATION_LIMIT, STATUS_INFEASIBLE = 0, 1, 2

@@ -3,6 +3,7 @@ The translation units (API + general kernel, and one unit per warp-kernel specia
 compiled in parallel and linked into one shared object."""
 import concurrent.futures
 import glob
+import zlib
 import os
 import subprocess
 import sys
@@ -18,6 +19,13 @@ OUT = os.path.join(HERE, "libbmpc.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--expt-extended-lambda", "-Xcompiler", "-fPIC"]
+
+
+EXTRA = os.environ.get("BMPC_NVCC_EXTRA", "").split()  # study builds: e.g. -DBMPC_PHASE_CLK (with BMPC_OUT / TMPDIR set)
+if EXTRA:
+    FLAGS = FLAGS + EXTRA
+    OBJDIR = OBJDIR + "_%08x" % zlib.crc32(" ".join(EXTRA).encode())
+OUT = os.environ.get("BMPC_OUT", OUT)
 
 
 def _obj(src):

@@ -75,6 +75,9 @@ struct bmpc_handle {
     DevBuf<double> Gw, HLw;
     DevBuf<int> order[2];
     DevBuf<unsigned int> ocnt;
+#ifdef BMPC_PHASE_CLK
+    DevBuf<long long> clk;  // study builds: per-phase cycle accumulators of step_warp
+#endif
     // fused observer (bmpc_set_estimator): model matrices, state x̂0 (handle-owned), corrected estimate of the last step
     bool have_estimator = false;
     int nym = 0;
@@ -205,7 +208,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     L.G = take(MP * E.ldg);
     L.H = take(NT * E.ldh);
     L.L = take(NT * E.ldh);
-    L.phi = take(std::max(8 * ((NT + 7) / 8) * E.ldp, NT * E.ldn));
+    L.phi = take(std::max((8 * ((NT + 7) / 8) + 1) * E.ldp, NT * E.ldn));  // DMMA C tiles + the rhs row, then the factor's columns
     L.vx = take(16);
     L.w1 = take(MP);
     L.w2 = take(MP);
@@ -265,6 +268,11 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     h->wp.HL = h->HLw.p;
     h->wp.sHL = h->d.shared_model ? 0 : sHL;
     h->wp.m = m;
+#ifdef BMPC_PHASE_CLK
+    CK(h->clk.alloc(32));
+    CK(cudaMemsetAsync(h->clk.p, 0, 32 * sizeof(long long), h->stream));
+    h->wp.clk = h->clk.p;
+#endif
     h->wp.long_thresh = 9;
     if (const char* e = getenv("BMPC_LONG")) h->wp.long_thresh = atoi(e);
     return BMPC_OK;
@@ -416,19 +424,7 @@ int bmpc_destroy(bmpc_handle* h) {
     if (!h) return BMPC_OK;
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
-    DevBuf<double>* bufs[] = {&h->E, &h->ex, &h->Ht, &h->Ev, &h->exv, &h->Hv, &h->Lv, &h->Hee, &h->K, &h->V, &h->B,
-                              &h->G, &h->J, &h->kx, &h->vx, &h->bx, &h->gx, &h->jx, &h->Mw, &h->Lw, &h->uop, &h->kfP, &h->kfQ, &h->kfR,
-                              &h->yop, &h->t_sig, &h->t_c, &h->sbase, &h->dbound, &h->Pd, &h->xhat0, &h->lastu0,
-                              &h->ry, &h->Rhat_y, &h->Rhat_u, &h->d0, &h->Dhat0, &h->Z, &h->u, &h->Jv, &h->F,
-                              &h->qt, &h->r, &h->lastu_prev};
-    for (auto* b : bufs) b->release();
-    DevBuf<int>* ibufs[] = {&h->lv_ok, &h->t_si1, &h->t_si2, &h->t_sch, &h->t_varptr, &h->t_varrow, &h->t_varsgn,
-                            &h->t_dbrmax, &h->t_dbrmin, &h->t_drbase, &h->t_drsrc, &h->t_blk, &h->t_blkstart,
-                            &h->t_pdsrc, &h->status, &h->iters};
-    for (auto* b : ibufs) b->release();
-    h->t_pi.release();
-    h->t_pj.release();
-    h->counters.release();
+    // every DevBuf member frees its allocation in its destructor (delete h below)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return BMPC_OK;
@@ -1068,6 +1064,17 @@ int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {
 }
 
 int64_t bmpc_launch_count(bmpc_handle* h) { return h ? h->launches : 0; }
+
+#ifdef BMPC_PHASE_CLK
+// study builds only (tools/studies/phase_clk.py): read and reset the per-phase cycle accumulators
+int bmpc_debug_phase_clk(bmpc_handle* h, long long out[32]) {
+    if (!h || !h->clk.p) return BMPC_ERR_STATE;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->clk.p, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->clk.p, 0, 32 * sizeof(long long)));
+    return BMPC_OK;
+}
+#endif
 
 int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, const double* Chat, const double* Bdhat,
                    const double* Ddhat, const double* fop_minus_xop, const double* M_diag, const double* N_diag,

@@ -897,6 +897,9 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         // the normal equations lose accuracy as lam/s spreads over > 1e24 and the dual residual
         // starts to grow again.
         if (best_merit <= 1e3 && merit >= best_merit) {
+            T.sync();
+            for (int j = T.tid; j < n; j += TEAM) c.x[j] = c.xb[j];  // the best iterate, not the current (worse) one
+            T.sync();
             status = ST_OPTIMAL;
             break;
         }
@@ -915,7 +918,14 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         }
         best_merit = fmin(best_merit, merit);
         if (it == P.max_iter) {
+            // iteration cap (the reference's time limit): keep the best iterate, status ITERATION_LIMIT unless it is
+            // already acceptable -- the reference keeps the solver's value with a warning (execute.jl:482-503)
             if (merit <= 1e3) status = ST_OPTIMAL;
+            else if (merit > best_merit) {
+                T.sync();
+                for (int j = T.tid; j < n; j += TEAM) c.x[j] = c.xb[j];
+                T.sync();
+            }
             break;
         }
         iters = it + 1;
@@ -971,7 +981,10 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         // collapses (1e-9, 1e-15, ...) while the primal residual stays where it is; two such steps end the solve
         // (status INFEASIBLE below) instead of running to the iteration cap.  Feasible problems never step below 1e-3.
         stall = (a < 1e-8 && e_p > 1e-6 * hscale) ? stall + 1 : 0;
-        if (stall >= 2) break;
+        if (stall >= 2) {
+            status = ST_INFEASIBLE;
+            break;
+        }
         // ... and before the collapse: an infeasible problem's iterates drift along a Farkas ray for 20-30 iterations
         // (primal residual on a plateau, complementarity GROWING by orders of magnitude, h'lam < 0) -- measured on
         // infeasible MHE windows, tools/studies/mhe_infeas.py.  Checked every 4 iterations from the 8th on (every 8 from the
@@ -986,7 +999,10 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
                 for (int r = T.tid; r < m; r += TEAM) hl = fma(c.h[r], c.lam[r], hl);
                 ray = T.sum(hl) < 0.0;
             }
-            if (ray && ray_prev) break;
+            if (ray && ray_prev) {
+                status = ST_INFEASIBLE;
+                break;
+            }
             ray_prev = ray;
             ep_chk = e_p;
         }
@@ -998,7 +1014,9 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         }
         T.sync();
     }
-    if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+    // status INFEASIBLE is reserved for the certified exits above (collapsed steps, Farkas ray, NaN): an iteration-limit
+    // exit keeps its iterate (general.jl `iserror`: only INFEASIBLE / NUMERICAL_ERROR ... discard the solver's value)
+    (void)rp_inf;
 }
 
 // threads per CTA: sub-warp teams share a 128-thread CTA; a one-warp team is its own CTA (many CTAs per SM, bounded by

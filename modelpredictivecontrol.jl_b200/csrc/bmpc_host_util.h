@@ -44,9 +44,13 @@ inline cudaError_t raise_dyn_smem(const void* func, int bytes) {
 }
 
 template <class T>
-struct DevBuf {
+struct DevBuf {  // owning device allocation: freed by the destructor (handles are destroyed with the device current)
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t alloc(size_t count) {
         if (count <= n && p) return cudaSuccess;
         if (p) cudaFree(p);

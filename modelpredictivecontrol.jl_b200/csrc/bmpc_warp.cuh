@@ -39,6 +39,7 @@ struct WarpParams {
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
     int long_thresh;    // iterations from which an instance counts as slow
     int m;              // inequality rows (without the eps >= 0 row)
+    long long* clk;     // BMPC_PHASE_CLK study builds only: [32] accumulated cycles per phase (nullptr otherwise)
 };
 
 template <int NT>
@@ -46,11 +47,23 @@ struct WarpDims {
     static constexpr int NB = (NT + 7) / 8;            // 8-wide variable blocks (DMMA tiles)
     static constexpr int LDG = NT <= 12 ? 12 : 20;     // == 4 (mod 8): conflict-free DMMA fragment loads
     static constexpr int LDH = (NT + 1) & ~1;
-    static constexpr int LDN = NT | 1;
+    static constexpr int LDN0 = (NT + 1) & ~1;
+    static constexpr int LDN = (LDN0 % 4 == 0) ? LDN0 + 2 : LDN0;  // factor columns: even (16-byte rows), == 2 (mod 4): conflict-free LDS.128
     static constexpr int LDP = 8 * NB + 2;
 };
 
 constexpr unsigned WFULL = 0xffffffffu;
+
+// Study builds (-DBMPC_PHASE_CLK, tools/studies/phase_clk.py): lane 0 accumulates the cycles spent between marks.
+#ifdef BMPC_PHASE_CLK
+#define PCLK_DECL long long pclk_t = clock64(); long long pclk_acc[24] = {0}
+#define PCLK(i) do { const long long t_ = clock64(); pclk_acc[i] += t_ - pclk_t; pclk_t = t_; } while (0)
+#define PCLK_FLUSH() do { if (lane == 0 && Q.clk) { for (int i_ = 0; i_ < 24; ++i_) if (pclk_acc[i_]) atomicAdd((unsigned long long*)&Q.clk[i_], (unsigned long long)pclk_acc[i_]); } for (int i_ = 0; i_ < 24; ++i_) pclk_acc[i_] = 0; } while (0)
+#else
+#define PCLK_DECL
+#define PCLK(i)
+#define PCLK_FLUSH()
+#endif
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -141,10 +154,20 @@ __global__ void __launch_bounds__(32, 16)
     const int KS = (m + 3) / 4;             // DMMA k-steps
     const double minv = 1.0 / (double)max(m, 1);
 
+    PCLK_DECL;
+    bool first_pass = true;
     for (;;) {
+        PCLK(23);
+        // work queue: the first instance of every CTA is its block index (no 2368-way atomic storm at launch), the
+        // rest come from the shared counter
         int slot = 0;
-        if (lane == 0) slot = (int)atomicAdd(&P.counters[0], 1u);
-        slot = __shfl_sync(WFULL, slot, 0);
+        if (first_pass) {
+            slot = (int)blockIdx.x;
+            first_pass = false;
+        } else {
+            if (lane == 0) slot = (int)gridDim.x + (int)atomicAdd(&P.counters[0], 1u);
+            slot = __shfl_sync(WFULL, slot, 0);
+        }
         if (__all_sync(WFULL, slot >= P.N)) break;  // vote: provably warp-uniform branch (no divergent-shuffle paths)
         const int inst = Q.order ? Q.order[slot] : slot;
 
@@ -158,9 +181,50 @@ __global__ void __launch_bounds__(32, 16)
             tma_bulk_g2s(sG, Q.Gw + (long)inst * Q.sGw, bG, bar);
         }
         // ---- stage 1: initpred!  (execute.jl:247-277) ----
+        // Every global read of the prologue is ISSUED before the first one is consumed (one DRAM round trip instead of a
+        // dozen dependent ones: with the L2 cold, the old row-by-row loops took ~19 k cycles per instance): the state, the
+        // previous solution and multipliers (warm start), this lane's bounds, and the first 8 x 4 columns of K / V for
+        // the lane's two prediction rows.
         const double* gxh = P.est_on ? P.xstate : P.xhat0;
-        for (int k = lane; k < nx; k += 32) sxh[k] = gxh[(long)inst * nx + k];
-        for (int k = lane; k < nu; k += 32) slu[k] = P.lastu0[(long)inst * nu + k];
+        const double* gK = P.K + (long)inst * P.sK;
+        const double* gV = P.V + (long)inst * P.sV;
+        const double* gB = P.B + (long)inst * P.sB;
+        const double* gyop = P.yop + (long)inst * P.syop;
+        const double* guop = P.uop + (long)inst * P.suop;
+        const double* gM = P.Mw + (long)inst * P.sM;
+        const double* gdb = P.dbound + (long)inst * nDr;
+        const double* gsb = P.sbase + (long)inst * nS;
+        const double* glw0 = P.lam_ws + (long)inst * P.ws_stride;
+        const double pxh = lane < nx ? gxh[(long)inst * nx + lane] : 0.0;
+        const double plu = lane < nu ? P.lastu0[(long)inst * nu + lane] : 0.0;
+        const double pz = lane < nr ? P.Z[(long)inst * nr + lane] : 0.0;  // previous period's Z̃ (warm start, shifted solution)
+        const int ws_on = P.use_ws ? P.ws_flag[inst] : 0;
+        double plam[RPL], pbnd[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int r = lane + 32 * t;
+            plam[t] = (P.use_ws && r < m) ? glw0[r] : 0.0;
+            pbnd[t] = r < nS ? gsb[r] : (r < m ? gdb[r - nS] : 0.0);
+        }
+        constexpr int KC = 8, VC = 4;
+        double kpre[2][KC], vpre[2][VC], bpre[2], mpre[2], rypre[2], yoppre[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = lane + 32 * h;
+            const bool okt = t < nY;
+            const int tc = okt ? t : 0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) kpre[h][k] = (okt && k < nx) ? gK[tc + (long)nY * k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < VC; ++k) vpre[h][k] = (okt && k < nu) ? gV[tc + (long)nY * k] : 0.0;
+            bpre[h] = okt ? gB[tc] : 0.0;
+            mpre[h] = okt ? gM[tc] : 0.0;
+            rypre[h] = okt ? (P.Rhat_y ? P.Rhat_y[(long)inst * nY + tc] : P.ry[(long)inst * ny + (tc % ny)]) : 0.0;
+            yoppre[h] = okt ? gyop[tc % ny] : 0.0;
+        }
+        if (lane < nx) sxh[lane] = pxh;
+        for (int k = lane + 32; k < nx; k += 32) sxh[k] = gxh[(long)inst * nx + k];
+        if (lane < nu) slu[lane] = plu;
         if (nd > 0) {
             for (int k = lane; k < nd; k += 32) sd0[k] = P.d0[(long)inst * nd + k];
             for (int k = lane; k < nd * P.Hp; k += 32)
@@ -168,20 +232,9 @@ __global__ void __launch_bounds__(32, 16)
         }
         __syncwarp();
         if (__any_sync(WFULL, P.est_on != 0)) skf_correct(P, inst, lane, 32, sxh, sd0, smem + L.ev, [] { __syncwarp(); });
-        const double* gK = P.K + (long)inst * P.sK;
-        const double* gV = P.V + (long)inst * P.sV;
-        const double* gB = P.B + (long)inst * P.sB;
-        const double* gyop = P.yop + (long)inst * P.syop;
-        const double* guop = P.uop + (long)inst * P.suop;
-        const double* gM = P.Mw + (long)inst * P.sM;
         double racc = 0.0;
-#pragma unroll 1
-        for (int t = lane; t < nY; t += 32) {
-            double f = gB[t];
-#pragma unroll 2
-            for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
-#pragma unroll 1
-            for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
+        // measured-disturbance terms and the bookkeeping every prediction row shares
+        auto finish_row = [&](int t, double f, double mt, double ryt, double yopt) {
             if (nd > 0) {
                 const double* gG = P.G + (long)inst * P.sG;
                 const double* gJ = P.J + (long)inst * P.sJ;
@@ -191,12 +244,36 @@ __global__ void __launch_bounds__(32, 16)
                 for (int k = 0; k < nd * P.Hp; ++k) f = fma(gJ[t + (long)nY * k], sDh[k], f);
             }
             sF[t] = f;
-            const double ryt = P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)];
-            const double cy = f + gyop[t % ny] - ryt;
-            const double ty = gM[t] * cy;
+            const double cy = f + yopt - ryt;
+            const double ty = mt * cy;
             stY[t] = ty;
             racc = fma(cy, ty, racc);
             P.F_out[(long)inst * nY + t] = f;
+        };
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = lane + 32 * h;
+            if (t < nY) {
+                double f = bpre[h];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) f = fma(kpre[h][k], sxh[k < nx ? k : 0], f);
+#pragma unroll 1
+                for (int k = KC; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
+#pragma unroll
+                for (int k = 0; k < VC; ++k) f = fma(vpre[h][k], slu[k < nu ? k : 0], f);
+#pragma unroll 1
+                for (int k = VC; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
+                finish_row(t, f, mpre[h], rypre[h], yoppre[h]);
+            }
+        }
+#pragma unroll 1
+        for (int t = lane + 64; t < nY; t += 32) {
+            double f = gB[t];
+#pragma unroll 2
+            for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
+#pragma unroll 1
+            for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
+            finish_row(t, f, gM[t], P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)], gyop[t % ny]);
         }
         if (P.has_terminal) {
             const double* gkx = P.kx + (long)inst * P.skx;
@@ -225,8 +302,6 @@ __global__ void __launch_bounds__(32, 16)
         double hR[RPL], sR[RPL], lamR[RPL];
         bool okR[RPL];
         double hmax = 0.0;
-        const double* gdb = P.dbound + (long)inst * nDr;
-        const double* gsb = P.sbase + (long)inst * nS;
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int r = lane + 32 * t;
@@ -234,11 +309,11 @@ __global__ void __launch_bounds__(32, 16)
             double hv = 0.0, wq = 0.0;
             if (r < nS) {
                 const int ch = rt.s_ch[r];
-                hv = gsb[r] - (ch >= 0 ? rt.row_sig[r] * slu[ch] : 0.0);
+                hv = pbnd[t] - (ch >= 0 ? rt.row_sig[r] * slu[ch] : 0.0);
             } else if (r < m) {
                 const int src = rt.dr_src[r - nS];
                 const double fsrc = src < nY ? sF[src] : sfx[src - nY];
-                hv = rt.row_sig[r] * (gdb[r - nS] - fsrc);
+                hv = rt.row_sig[r] * (pbnd[t] - fsrc);
                 if (P.pd_is_ev) {
                     // q = 2 Ev' tY = Gt' w with w = 2 sigma tY on ONE row per prediction (the max-side row if present)
                     const int kb = rt.dr_base[r - nS];
@@ -250,8 +325,10 @@ __global__ void __launch_bounds__(32, 16)
             hmax = fmax(hmax, fabs(hv));
             w1[r] = wq;
         }
+        PCLK(12);
         mbar_wait(bar, phase);
         phase ^= 1u;
+        PCLK(13);
 
         // helpers -------------------------------------------------------------------------
         // out[t] = Gt[r,:] . v   for this lane's rows, v in vx
@@ -407,6 +484,7 @@ __global__ void __launch_bounds__(32, 16)
         }
         smin = (m > 0) ? wmin(smin) : 0.0;
         const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
+        PCLK(14);
         int status = ST_OPTIMAL, iters = 0;
         if (__any_sync(WFULL, !feasible)) {
             // ---- stage 3: Mehrotra predictor-corrector ----
@@ -417,24 +495,25 @@ __global__ void __launch_bounds__(32, 16)
                 lamR[t] = okR[t] ? mu0 / sR[t] : 0.0;
             }
             // ---- warm start (set_warmstart_mpc! analogue): previous period's solution and multipliers ----
-            if (__any_sync(WFULL, P.use_ws && P.ws_flag[inst] != 0)) {
-                const double* gZp = P.Z + (long)inst * nr;
+            if (__any_sync(WFULL, ws_on != 0)) {
+                // level coordinates of the previous Z̃: v_l = sum of the moves up to block l of the same input (pz holds Z̃_lane)
                 double xw = 0.0;
-                if (isreal)
-                    for (int l = lane % nu; l <= lane; l += nu) xw += gZp[l];
-                if (iseps) xw = gZp[nz];
+                for (int k = 0; k * nu < NT; ++k) {  // (uniform trip count)
+                    const int src = lane - k * nu;
+                    const double zl = __shfl_sync(WFULL, pz, src >= 0 ? src : 0);
+                    if (isreal && src >= 0) xw += zl;
+                }
+                if (iseps) xw = pz;
                 __syncwarp();
                 if (lane < 16) vx[lane] = xw;
                 __syncwarp();
                 x = xw;
                 row_products(gx);
-                const double* glw = P.lam_ws + (long)inst * P.ws_stride;
                 const double lmin = 1e-4 * qs / hscale;
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    const int r = lane + 32 * t;
                     sR[t] = fmax(hR[t] - gx[t], 1e-2 * hscale);
-                    lamR[t] = okR[t] ? fmax(glw[r], lmin) : 0.0;
+                    lamR[t] = okR[t] ? fmax(plam[t], lmin) : 0.0;
                 }
             }
             status = ST_ITERATION_LIMIT;
@@ -446,7 +525,9 @@ __global__ void __launch_bounds__(32, 16)
 #pragma unroll
             for (int t = 0; t < RPL; ++t) rpR[t] = okR[t] ? gx[t] + sR[t] - hR[t] : 0.0;
             const double inv_tol_p = 1.0 / (P.tol * hscale), inv_tol_mu = 1.0 / (P.tol_mu * qs * hscale);
+            PCLK(15);
             for (int it = 0; it <= P.max_iter; ++it) {
+                PCLK(11);
                 double dR[RPL], isR[RPL];
                 double e_p = 0.0, musum = 0.0;
 #pragma unroll
@@ -461,6 +542,7 @@ __global__ void __launch_bounds__(32, 16)
                     musum = fma(sR[t], lamR[t], musum);
                 }
                 __syncwarp();
+                PCLK(0);
                 // residuals: rd = Hx + q + G'lam; the predictor's right-hand side needs G'(d rp) -- one pass for both
                 const double Hxq = hess_apply() + q;
                 double Gtl, Gdr;
@@ -469,6 +551,7 @@ __global__ void __launch_bounds__(32, 16)
                     Gtl = 0.0;
                     Gdr = 0.0;
                 }
+                PCLK(1);
                 const double rd = Hxq + Gtl;
                 double e_d = fabs(rd), dsc = fmax(fabs(Hxq), fabs(Gtl));
                 wred_mmms(e_d, dsc, e_p, musum);
@@ -489,6 +572,7 @@ __global__ void __launch_bounds__(32, 16)
                 best_merit = fmin(best_merit, merit);
                 if (it == P.max_iter) break;
                 iters = it + 1;
+                PCLK(2);
                 // ---- Phi = H + Gt' D Gt on the FP64 tensor pipe (lower block-triangle) ----
                 double c00a, c00b, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
                 {
@@ -515,19 +599,35 @@ __global__ void __launch_bounds__(32, 16)
                     const double* ga = sG + ft * LDG + fg;
                     const double* gb = sG + ft * LDG + (ok1 ? 8 + fg : 0);
                     const double* wdp = wd + ft;
-#pragma unroll 3
-                    for (int ks = 0; ks < KS; ++ks) {
+                    // two accumulator sets (even / odd k-steps) halve the dependent DMMA chain
+                    double e00a = 0.0, e00b = 0.0, e10a = 0.0, e10b = 0.0, e11a = 0.0, e11b = 0.0;
+                    auto kstep = [&](int ks, double& x00a, double& x00b, double& x10a, double& x10b, double& x11a, double& x11b) {
                         const double a0 = ga[ks * 4 * LDG];
                         const double dk = wdp[ks * 4];
                         const double b0 = dk * a0;
-                        dmma884(c00a, c00b, a0, b0);
+                        dmma884(x00a, x00b, a0, b0);
                         if (NB == 2) {
                             double a1 = gb[ks * 4 * LDG];
                             if (pred1) a1 = ok1 ? a1 : 0.0;
                             const double b1 = dk * a1;
-                            dmma884(c10a, c10b, a1, b0);
-                            dmma884(c11a, c11b, a1, b1);
+                            dmma884(x10a, x10b, a1, b0);
+                            dmma884(x11a, x11b, a1, b1);
                         }
+                    };
+                    int ks = 0;
+#pragma unroll 2
+                    for (; ks + 1 < KS; ks += 2) {
+                        kstep(ks, c00a, c00b, c10a, c10b, c11a, c11b);
+                        kstep(ks + 1, e00a, e00b, e10a, e10b, e11a, e11b);
+                    }
+                    if (ks < KS) kstep(ks, c00a, c00b, c10a, c10b, c11a, c11b);
+                    c00a += e00a;
+                    c00b += e00b;
+                    if (NB == 2) {
+                        c10a += e10a;
+                        c10b += e10b;
+                        c11a += e11a;
+                        c11b += e11b;
                     }
                 }
                 __syncwarp();
@@ -536,10 +636,14 @@ __global__ void __launch_bounds__(32, 16)
                     *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 2 * ft) = make_double2(c10a, c10b);
                     *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 8 + 2 * ft) = make_double2(c11a, c11b);
                 }
+                // the predictor's right-hand side rides along as row NT of the matrix being factored: the factorisation
+                // then leaves D^-2 M^-1 rhs in that row -- the predictor's forward substitution costs nothing extra
+                const double rhs0 = isvar ? -(Hxq + Gdr) : 0.0;
+                if (lane < LDP) sPhi[8 * NB * LDP + lane] = rhs0;  // (row 8 NB: past the C tiles)
                 __syncwarp();
                 double phi[2 * NV2];
                 {
-                    const double2* prow = reinterpret_cast<const double2*>(sPhi + iv * LDP);
+                    const double2* prow = reinterpret_cast<const double2*>(sPhi + (lane < NT ? lane : (lane == NT ? 8 * NB : 0)) * LDP);
 #pragma unroll
                     for (int jj = 0; jj < NV2; ++jj) {
                         const double2 p2 = prow[jj];
@@ -552,8 +656,12 @@ __global__ void __launch_bounds__(32, 16)
                 for (int j = 0; j < NT; ++j)
                     if (j == lane) pdiag = phi[j];
                 __syncwarp();
-                // ---- Cholesky: right-looking, rows in registers, columns exchanged by shuffles ----
+                PCLK(3);
+                // ---- Cholesky: right-looking, rows in registers; column k goes through shared memory (one store, then
+                // broadcast LDS.128 reads of the entries below the diagonal) -- a quarter of the shuffle traffic of a
+                // per-entry broadcast, and the factor ends up column-major for the backward substitutions ----
                 double invd = 1.0;
+                double* colbuf = sPhi;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) {
                     const double dk = bcast(pdiag, k);
@@ -565,33 +673,50 @@ __global__ void __launch_bounds__(32, 16)
                     const double lik = phi[k] * rs;
                     if (lane == k) invd = rs;
                     pdiag = fma(-lik, lik, pdiag);
+                    if (k + 1 < NT) {
+                        if (lane < NT) colbuf[k * LDN + lane] = lik;
+                        __syncwarp();
 #pragma unroll
-                    for (int j = k + 1; j < NT; ++j) {
-                        const double ljk = bcast(lik, j);
-                        phi[j] = fma(-lik, ljk, phi[j]);
+                        for (int jp = (k + 1) / 2; jp <= (NT - 1) / 2; ++jp) {
+                            const double2 c2 = *reinterpret_cast<const double2*>(colbuf + k * LDN + 2 * jp);
+                            if (2 * jp > k) phi[2 * jp] = fma(-lik, c2.x, phi[2 * jp]);
+                            if (2 * jp + 1 < NT) phi[2 * jp + 1] = fma(-lik, c2.y, phi[2 * jp + 1]);
+                        }
                     }
                     // keep the COLUMN-SCALED factor M = L diag(L)^-1 (unit diagonal): both substitutions then run on
                     // raw broadcasts, without a multiply by 1/L_jj on their dependent chains
                     phi[k] = lik * rs;
                 }
-                // rows of M to shared memory for the backward substitutions
-                if (isvar) {
+                PCLK(4);
+                // lane NT now holds z = D^-2 M^-1 rhs0: hand z_i to lane i through vx (x is not read again before the
+                // end of the iteration rewrites it)
+                if (lane == NT) {
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) sPhi[lane * LDN + j] = phi[j];
+                    for (int jj = 0; jj < NV2; ++jj) *reinterpret_cast<double2*>(vx + 2 * jj) = make_double2(phi[2 * jj], phi[2 * jj + 1]);
                 }
                 __syncwarp();
-                double lcol[NT];  // column `lane` of L (entries below the diagonal)
+                const double z0 = isvar ? vx[iv] : 0.0;
+                double lcol[NT];  // column `lane` of M (entries below the diagonal): L[j][lane] / L[lane][lane]
+                {
+                    const double2* ccol = reinterpret_cast<const double2*>(colbuf + iv * LDN);
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    lcol[j] = (lane < j) ? sPhi[j * LDN + iv] : 0.0;
-                    phi[j] = (lane > j && isvar) ? phi[j] : 0.0;  // row `lane` of L, strictly lower part, for the forward sweeps
+                    for (int jp = 0; jp <= (NT - 1) / 2; ++jp) {
+                        const double2 c2 = ccol[jp];
+                        lcol[2 * jp] = (lane < 2 * jp) ? c2.x * invd : 0.0;
+                        if (2 * jp + 1 < NT) lcol[2 * jp + 1] = (lane < 2 * jp + 1) ? c2.y * invd : 0.0;
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) phi[j] = (lane > j && isvar) ? phi[j] : 0.0;  // row `lane` of M, strictly lower part
+                PCLK(5);
                 // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b
                 const double invd2 = invd * invd;
-                auto solve = [&](double b) -> double {
+                auto solve_fwd = [&](double b) -> double {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) b = fma(-phi[j], bcast(b, j), b);  // M^-1 (unit lower)
-                    b *= invd2;
+                    return b * invd2;
+                };
+                auto solve_back = [&](double b) -> double {
 #pragma unroll
                     for (int j = NT - 1; j >= 0; --j) b = fma(-lcol[j], bcast(b, j), b);  // M'^-1 (unit upper)
                     return isvar ? b : 0.0;
@@ -600,11 +725,14 @@ __global__ void __launch_bounds__(32, 16)
                 double dsR[RPL], dlR[RPL], rcR[RPL];
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) rcR[t] = 0.0;
-                double rhs = isvar ? -(Hxq + Gdr) : 0.0;
+                double rhs = 0.0;
                 double dx = 0.0, rho = 0.0, ratio = 1.0;
 #pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
-                    dx = solve(rhs);
+                    double zz = z0;
+                    if (pass) zz = solve_fwd(rhs);
+                    dx = solve_back(zz);
+                    PCLK(6 + 3 * pass);
                     __syncwarp();
                     if (lane < 16) vx[lane] = dx;
                     __syncwarp();
@@ -627,6 +755,7 @@ __global__ void __launch_bounds__(32, 16)
                         sdd = fma(dsR[t], dlR[t], sdd);
                     }
                     wred_ms(rho, sdd);
+                    PCLK(7 + 3 * pass);
                     if (pass == 0) {
                         // affine step: s*dl + lam*ds = -s*lam exactly, so
                         //   sum (s + a ds)(lam + a dl) = (1 - a) sum s*lam + a^2 sum ds*dl   -- no second reduction
@@ -643,6 +772,7 @@ __global__ void __launch_bounds__(32, 16)
                         __syncwarp();
                         const double Gw = gt_apply1(w1);
                         rhs = isvar ? -(rd + Gw) : 0.0;
+                        PCLK(8);
                     }
                 }
                 // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
@@ -651,7 +781,10 @@ __global__ void __launch_bounds__(32, 16)
                 // infeasibility: two collapsed steps with the primal residual still open end the solve (ipm_solve,
                 // bmpc_device.cuh)
                 stall = (a < 1e-8 && rp_inf > 1e-6 * hscale) ? stall + 1 : 0;
-                if (__any_sync(WFULL, stall >= 2)) break;
+                if (__any_sync(WFULL, stall >= 2)) {
+                    status = ST_INFEASIBLE;
+                    break;
+                }
                 x = fma(a, dx, x);
                 const double oma = 1.0 - a;
 #pragma unroll
@@ -664,8 +797,9 @@ __global__ void __launch_bounds__(32, 16)
                 if (lane < 16) vx[lane] = x;
                 __syncwarp();
             }
-            if (status == ST_ITERATION_LIMIT && rp_inf > 1e-6 * hscale) status = ST_INFEASIBLE;
+            // (status INFEASIBLE only from the certified exits: collapsed steps or NaN; an iteration-limit exit keeps its iterate)
         }
+        PCLK(16);
         // ---- stage 4: getinput!  (execute.jl:536-546) ----
         double* gZ = P.Z + (long)inst * nr;
         __syncwarp();
@@ -734,6 +868,11 @@ __global__ void __launch_bounds__(32, 16)
         }
         fence_proxy_async();  // generic-proxy accesses to the TMA destinations precede the next bulk copy
         __syncwarp();
+        PCLK(17);
+#ifdef BMPC_PHASE_CLK
+        if (lane == 0 && Q.clk) { atomicAdd((unsigned long long*)&Q.clk[24], 1ull); atomicAdd((unsigned long long*)&Q.clk[25], (unsigned long long)iters); }
+#endif
+        PCLK_FLUSH();
     }
     // ---- reset the work counters for the next launch (last CTA out) ----
     if (lane == 0) {

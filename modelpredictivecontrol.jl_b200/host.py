@@ -123,7 +123,7 @@ def augment_model(model, nint_u=0, nint_ym=None, i_ym=None):
     xop = np.concatenate([model.xop, np.zeros((N, nxs))], axis=1)
     fop = np.concatenate([model.fop, np.zeros((N, nxs))], axis=1)
     return dict(Ahat=Ahat, Buhat=Buhat, Chat=Chat, Bdhat=Bdhat, Ddhat=model.Dd.copy(), xophat=xop, fophat=fop,
-                nxhat=nxh, nxs=nxs, i_ym=i_ym, nint_ym=list(nint_ym))
+                nxhat=nxh, nxs=nxs, nsu=nsu, i_ym=i_ym, nint_ym=list(nint_ym))
 
 
 def dare_filter_sda(A, C, Q, R, iters=60, tol=1e-13):
@@ -167,7 +167,7 @@ class SteadyKalmanFilter:
         nym = len(self.i_ym)
         sQ = np.full(nx, 1.0 / nx) if sigmaQ is None else np.asarray(sigmaQ, float)
         sR = np.ones(nym) if sigmaR is None else np.asarray(sigmaR, float)
-        nsu = int(np.sum(nint_u)) if not np.isscalar(nint_u) else int(nint_u) * 0
+        nsu = self.nsu  # integrator states on the manipulated inputs (init_integrators)
         sQu = np.ones(nsu) if sigmaQint_u is None else np.asarray(sigmaQint_u, float)
         sQy = np.ones(self.nxs - nsu) if sigmaQint_ym is None else np.asarray(sigmaQint_ym, float)
         self.Qhat = np.diag(np.concatenate([sQ, sQu, sQy]) ** 2)

@@ -21,7 +21,12 @@ class LinMPC:
         self.estim, self.model = estim, model
         N, nu, ny, nd = model.N, model.nu, model.ny, model.nd
         if Hp is None:
-            Hp = DEFAULT_HP0  # default_Hp adds the estimated delays (construct.jl:569-591); batch plants: none assumed
+            # default_Hp (construct.jl:569-591): 10 + the number of (near-)zero poles, the estimate of the plant's
+            # dead time; one horizon for the whole batch, so the estimate must agree across the instances
+            nk = np.sum(np.abs(np.linalg.eigvals(model.A)) < 1e-3, axis=-1)
+            if nk.min() != nk.max():
+                raise ValueError("default Hp: the instances have different delay estimates; pass Hp explicitly")
+            Hp = DEFAULT_HP0 + int(nk.max())
         self.nb = move_blocking(Hp, Hc)
         self.Hp, self.Hc = Hp, len(self.nb)
         w = lambda v, dflt, n: np.full(n, dflt) if v is None else np.asarray(v, dtype=np.float64).reshape(n)
