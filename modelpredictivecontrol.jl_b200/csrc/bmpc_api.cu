@@ -57,6 +57,9 @@ struct bmpc_handle {
         t_blkstart, t_pdsrc;
     DevBuf<short> t_pi, t_pj;
     DevBuf<double> t_sig, t_c, sbase, dbound, Pd;
+    // host copies of the row tables (the warp kernel's position tables are derived from them)
+    std::vector<int> hs_i1, hs_i2, hs_ch, hdr_src, hdr_base, hdb_rmax, hdb_rmin;
+    std::vector<double> hsig, hcc;
     std::vector<unsigned char> pattern;  // finiteness pattern of the bounds (frozen after first step)
     int nPd2 = 0;
     bool pd_is_ev = false, pd_in_smem = false, has_terminal_rows = false, hv_in_smem = true;
@@ -73,6 +76,8 @@ struct bmpc_handle {
     const bmpc::WarpEntry* warp = nullptr;
     bmpc::WarpParams wp{};
     DevBuf<double> Gw, HLw;
+    DevBuf<int4> w_pinfo;   // per position: row, flags, bound source / shift channel, unit variable
+    DevBuf<int> w_upos, w_posrow;
     DevBuf<int> order[2];
     DevBuf<unsigned int> ocnt;
 #ifdef BMPC_PHASE_CLK
@@ -85,8 +90,13 @@ struct bmpc_handle {
     DevBuf<double> kfP, kfQ, kfR;  // time-varying KalmanFilter: P̂, Q̂, R̂ per model (bmpc_set_estimator_cov)
     bool kf_on = false;
     bool e_has_fx = false;
-    double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather)
+    double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather / bmpc_set_gather_flags)
     int zg_world = 0, zg_rank = 0;
+    unsigned long long* zg_flag[8] = {nullptr};  // epoch-flag protocol: every peer's flag array [world]
+    long zg_row_offset = 0, zg_rows_total = 0;
+    int zg_slots = 1;
+    int64_t zg_epoch = 0;   // periods published so far
+    DevBuf<int> zg_timeout;
     int order_cur = 0;       // order[order_cur] drives the next launch
     bool order_valid = false;
     int warm_start = 1;
@@ -198,21 +208,69 @@ const std::vector<bmpc::WarpEntry>& warp_registry() {
     return reg;
 }
 
-// warp-per-controller kernel: all rows dense, one TMA copy per instance, DMMA Hessian build
+// warp-per-controller kernel: unit rows (hard bounds on one variable) handled lane-locally, every other row dense;
+// one TMA copy per instance, DMMA Hessian build
 int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
-    const int NT = E.nt, MP = 32 * E.rpl, nY = h->nY, nx = h->d.nxhat;
+    const int NT = E.nt, MP = 32 * E.rpl, nY = h->nY, nx = h->d.nxhat, nS = h->rt.nS;
     const int m = h->rt.nS + h->rt.nDr;  // without the (redundant) eps >= 0 row
+    // ---- positions: dense rows first (original order), then the unit rows ----
+    std::vector<int> upos(32, MP);       // [0..15] max-side, [16..31] min-side unit row of each variable
+    std::vector<char> is_unit(std::max(m, 1), 0);
+    for (int r = 0; r < nS; ++r) {
+        const int i1 = h->hs_i1[r];
+        if (h->hs_i2[r] >= 0 || h->hcc[r] != 0.0 || i1 >= 16) continue;  // 2-variable or soft rows stay dense
+        const int side = h->hsig[r] > 0 ? 0 : 16;
+        if (upos[side + i1] != MP) continue;  // a second row of the same kind stays dense
+        upos[side + i1] = -2 - r;             // marked; the position follows below
+        is_unit[r] = 1;
+    }
+    std::vector<int> pos_row;  // dense positions -> row
+    for (int r = 0; r < m; ++r)
+        if (!is_unit[r]) pos_row.push_back(r);
+    const int mD = (int)pos_row.size();
+    const int mh = ((mD + 1) / 2 + 3) & ~3, KS = (mD + 3) / 4;
+    const int GR = std::max(2 * mh, 4 * KS);
+    if (GR > MP) return BMPC_ERR_UNSUPPORTED;
+    std::vector<int4> pinfo(MP, make_int4(-1, 0, -1, 0));
+    auto dense_info = [&](int r) {
+        int4 pi = make_int4(r, bmpc::PI_VALID, -1, 0);
+        if (h->hsig[r] < 0) pi.y |= bmpc::PI_NEG;
+        if (r < nS) {
+            pi.y |= bmpc::PI_SPARSE;
+            pi.z = h->hs_ch[r];
+        } else {
+            pi.z = h->hdr_src[r - nS];
+            if (h->pd_is_ev) {
+                const int kb = h->hdr_base[r - nS];
+                const int rmax = h->hdb_rmax[kb];
+                if (rmax == r || (rmax < 0 && h->hdb_rmin[kb] == r)) pi.y |= bmpc::PI_ISQ;
+            }
+        }
+        return pi;
+    };
+    for (int p = 0; p < mD; ++p) pinfo[p] = dense_info(pos_row[p]);
+    int pu = mD;
+    for (int r = 0; r < nS; ++r) {
+        if (!is_unit[r]) continue;
+        int4 pi = dense_info(r);
+        pi.y |= bmpc::PI_UNIT;
+        pi.w = h->hs_i1[r];
+        pinfo[pu] = pi;
+        upos[(h->hsig[r] > 0 ? 0 : 16) + h->hs_i1[r]] = pu;
+        ++pu;
+    }
     bmpc::WarpLayout& L = h->wp.L;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += even(std::max(cnt, 1)); return at; };
-    L.G = take(MP * E.ldg);
+    L.G = take(GR * E.ldg);
     L.H = take(NT * E.ldh);
     L.L = take(NT * E.ldh);
-    L.phi = take(std::max((8 * ((NT + 7) / 8) + 1) * E.ldp, NT * E.ldn));  // DMMA C tiles + the rhs row, then the factor's columns
+    L.phi = take(std::max((8 * ((NT + 7) / 8) + 1) * E.ldp, 2 * NT * E.ldn));  // DMMA C tiles + the rhs row, then the columns of L and of M
     L.vx = take(16);
-    L.w1 = take(MP);
-    L.w2 = take(MP);
-    L.wd = take(MP);
+    L.vy = take(16);
+    L.w1 = take(MP + 2);  // (+ the "no unit row" slot that reads as zero)
+    L.w2 = take(MP + 2);
+    L.wd = take(MP + 2);
     // F and M*Cy are dead before the interior-point loop first writes wd / w2: share the storage when they fit
     if (nY <= MP) {
         L.F = L.wd;
@@ -245,13 +303,18 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     h->warp = &E;
     h->pd_in_smem = true;
     const long NM = h->NM;
-    const long sG = (long)MP * E.ldg, sHL = 2L * NT * E.ldh;
+    const long sG = (long)std::max(GR, 1) * E.ldg, sHL = 2L * NT * E.ldh;
     CK(h->Gw.alloc((size_t)NM * sG));
     CK(h->HLw.alloc((size_t)NM * sHL));
+    CK(h->w_pinfo.upload(pinfo, h->stream));
+    CK(h->w_upos.upload(upos, h->stream));
+    if (pos_row.empty()) pos_row.push_back(0);
+    CK(h->w_posrow.upload(pos_row, h->stream));
     const double* pdsrc = h->pd_is_ev ? h->Ev.p : h->Pd.p;
     const long spd = h->pd_is_ev ? h->nEv2 : h->nPd2;
-    bmpc::k_make_warp<<<(unsigned)NM, 128, 0, h->stream>>>(pdsrc, spd, h->rt.nDb, h->Hv.p, h->Lv.p, h->nHp2, h->Hee.p, h->rt, m,
-                                                         h->nz, h->d.neps, NT, E.ldg, E.ldh, MP, h->Gw.p, sG, h->HLw.p, sHL);
+    bmpc::k_make_warp<<<(unsigned)NM, 128, 0, h->stream>>>(pdsrc, spd, h->rt.nDb, h->Hv.p, h->Lv.p, h->nHp2, h->Hee.p, h->rt,
+                                                         h->w_posrow.p, mD, h->nz, h->d.neps, NT, E.ldg, E.ldh, GR, h->Gw.p, sG,
+                                                         h->HLw.p, sHL);
     h->launches++;
     CK(cudaGetLastError());
     CK(h->lam_ws.alloc((size_t)h->d.N * even(std::max(h->rt.m, 1))));
@@ -267,7 +330,11 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     h->wp.sGw = h->d.shared_model ? 0 : sG;
     h->wp.HL = h->HLw.p;
     h->wp.sHL = h->d.shared_model ? 0 : sHL;
+    h->wp.pinfo = h->w_pinfo.p;
+    h->wp.upos = h->w_upos.p;
     h->wp.m = m;
+    h->wp.mD = mD;
+    h->wp.GR = GR;
 #ifdef BMPC_PHASE_CLK
     CK(h->clk.alloc(32));
     CK(cudaMemsetAsync(h->clk.p, 0, 32 * sizeof(long long), h->stream));
@@ -275,6 +342,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
 #endif
     h->wp.long_thresh = 9;
     if (const char* e = getenv("BMPC_LONG")) h->wp.long_thresh = atoi(e);
+    CK(cudaStreamSynchronize(h->stream));  // (the host vectors uploaded above go out of scope)
     return BMPC_OK;
 }
 
@@ -371,6 +439,7 @@ int bmpc_create(bmpc_handle** out, const bmpc_dims* dims, const int32_t* nb) {
     h->d = d;
     if (h->d.max_iter <= 0) h->d.max_iter = 50;
     if (!(h->d.tol > 0)) h->d.tol = 1e-11;
+    if (const char* e = getenv("BMPC_TOL")) h->d.tol = atof(e);  // diagnostic override (tools/studies)
     h->nb.assign(nb, nb + d.Hc);
     h->blk_start.assign(d.Hc + 1, 0);
     for (int l = 0; l < d.Hc; ++l) {
@@ -708,6 +777,8 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
         }
         for (int r = 0; r < nDr; ++r) dbound[(size_t)i * nDr + r] = arrs[dsrc[r].arr][(size_t)i * lens[dsrc[r].arr] + dsrc[r].k];
     }
+    h->hs_i1 = s_i1; h->hs_i2 = s_i2; h->hs_ch = s_ch; h->hdr_src = dr_src; h->hdr_base = dr_base;
+    h->hdb_rmax = db_rmax; h->hdb_rmin = db_rmin; h->hsig = sig; h->hcc = cc;
     cudaStream_t s = h->stream;
     CK(h->t_si1.upload(s_i1, s));
     CK(h->t_si2.upload(s_i2, s));
@@ -861,9 +932,17 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
     P.use_ws = (h->warm_start && h->lam_ws.p) ? 1 : 0;
-    for (int pr = 0; pr < 8; ++pr) P.zg[pr] = h->zg[pr];
+    for (int pr = 0; pr < 8; ++pr) {
+        P.zg[pr] = h->zg[pr];
+        P.zg_flag[pr] = h->zg_flag[pr];
+    }
     P.zg_world = h->zg_world;
     P.zg_rank = h->zg_rank;
+    if (h->zg_world > 0) {
+        h->zg_epoch++;
+        P.zg_epoch = (unsigned long long)h->zg_epoch;
+        P.zg_base = ((long)(h->zg_epoch % h->zg_slots) * h->zg_rows_total + h->zg_row_offset) * (long)n;
+    }
     cudaError_t le;
     const bool kf = fused_est && h->kf_on;
     int kf_smem = 0;
@@ -1033,20 +1112,64 @@ int bmpc_get_state(bmpc_handle* h, double* xhat0, double* xhat0_corrected) {
     return BMPC_OK;
 }
 
-int bmpc_set_gather(bmpc_handle* h, void* const* peer_bufs, int32_t world, int32_t rank) {
+int bmpc_set_gather_flags(bmpc_handle* h, void* const* peer_bufs, void* const* peer_flags, int32_t world, int32_t rank,
+                          int32_t row_offset, int32_t rows_total, int32_t slots) {
     if (!h) return fail(BMPC_ERR_ARG, "null handle");
     if (world == 0 || !peer_bufs) {
         h->zg_world = 0;
         return BMPC_OK;
     }
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BMPC_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
+    if (row_offset < 0 || rows_total < 1 || (long)row_offset + h->d.N > rows_total)
+        return fail(BMPC_ERR_ARG, "rows [row_offset, row_offset + N) must lie inside [0, rows_total)");
+    if (slots < 1 || (peer_flags && slots < 3))
+        return fail(BMPC_ERR_ARG, "slots must be >= 1 (>= 3 with epoch flags: a peer may run one period ahead of a reader one period behind)");
     for (int pr = 0; pr < world; ++pr) {
-        if (!peer_bufs[pr]) return fail(BMPC_ERR_ARG, "null peer buffer");
+        if (!peer_bufs[pr] || (peer_flags && !peer_flags[pr])) return fail(BMPC_ERR_ARG, "null peer buffer");
         h->zg[pr] = static_cast<double*>(peer_bufs[pr]);
+        h->zg_flag[pr] = peer_flags ? static_cast<unsigned long long*>(peer_flags[pr]) : nullptr;
     }
+    for (int pr = world; pr < 8; ++pr) { h->zg[pr] = nullptr; h->zg_flag[pr] = nullptr; }
+    CK(cudaSetDevice(h->d.device));
+    CK(h->zg_timeout.alloc(1));
+    CK(cudaMemsetAsync(h->zg_timeout.p, 0, sizeof(int), h->stream));
     h->zg_world = world;
     h->zg_rank = rank;
+    h->zg_row_offset = row_offset;
+    h->zg_rows_total = rows_total;
+    h->zg_slots = slots;
+    h->zg_epoch = 0;
     return BMPC_OK;
+}
+
+int bmpc_set_gather(bmpc_handle* h, void* const* peer_bufs, int32_t world, int32_t rank) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    // barrier protocol, one slot, EQUAL shard sizes on every rank (row block `rank` of [world x N x n])
+    return bmpc_set_gather_flags(h, peer_bufs, nullptr, world, rank, rank * h->d.N, (world > 0 ? world : 1) * h->d.N, 1);
+}
+
+int64_t bmpc_gather_epoch(bmpc_handle* h) { return h ? h->zg_epoch : 0; }
+
+int bmpc_gather_wait(bmpc_handle* h, int64_t epoch, int32_t* slot) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    if (h->zg_world <= 0 || !h->zg_flag[h->zg_rank]) return fail(BMPC_ERR_STATE, "bmpc_gather_wait needs bmpc_set_gather_flags");
+    if (epoch < 1 || epoch > h->zg_epoch) return fail(BMPC_ERR_ARG, "epoch must be 1..bmpc_gather_epoch()");
+    CK(cudaSetDevice(h->d.device));
+    // ~2 s at 2 GHz: a peer that never publishes must not hang the device
+    bmpc::k_gather_wait<<<1, 32, 0, h->stream>>>(h->zg_flag[h->zg_rank], h->zg_world, (unsigned long long)epoch, 4000000000LL,
+                                               h->zg_timeout.p);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (slot) *slot = (int32_t)(epoch % h->zg_slots);
+    return BMPC_OK;
+}
+
+int bmpc_gather_timed_out(bmpc_handle* h) {
+    if (!h || !h->zg_timeout.p) return 0;
+    int v = 0;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, h->zg_timeout.p, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
 }
 
 int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {

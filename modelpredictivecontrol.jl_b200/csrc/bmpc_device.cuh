@@ -73,6 +73,9 @@ struct StepParams {
     // epilogue stores this instance's Z̃ straight into slot (rank, inst) of EVERY peer's buffer (world = 0: off)
     double* zg[8];
     int zg_world, zg_rank;
+    long zg_base;                    // offset (doubles) of this rank's first row in the current slot: (slot * rows_total + row_offset) * n
+    unsigned long long* zg_flag[8];  // epoch-flag protocol (bmpc_set_gather_flags): peer p's flag array [world]; nullptr: barrier protocol
+    unsigned long long zg_epoch;     // period number this launch publishes (st.release.sys by the last CTA out, after every peer store)
     // fused observer (SteadyKalmanFilter, kalman.jl:284-309): correct before the step, predict after it.
     // est_on: x̂0 is STATE OF THE HANDLE (xstate, in/out); the corrected estimate used by the step goes to xcorr.
     int est_on, nym;
@@ -114,6 +117,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Fused all-gather, epoch-flag protocol: called by ONE thread of the last CTA out, after it has observed every other
+// CTA's arrival (each preceded by a system-scope fence after that CTA's peer stores).  The release store of the period
+// number into slot `rank` of every peer's flag array makes this launch's rows visible to a consumer that acquires it.
+__device__ __forceinline__ void publish_epoch(const StepParams& P) {
+    if (P.zg_world <= 0 || !P.zg_flag[0]) return;
+    __threadfence_system();
+    for (int pr = 0; pr < P.zg_world; ++pr) {
+        unsigned long long* f = P.zg_flag[pr] + P.zg_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.zg_epoch) : "memory");
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Team: 8/16/32 lanes inside a warp (independent thread scheduling + masked sync), or a CTA.
@@ -1318,7 +1333,7 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
         for (int j = T.tid; j < nz; j += TEAM) gZ[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
         if (neps && T.tid == 0) gZ[nz] = c.x[nz];
         if (P.zg_world > 0) {  // fused all-gather: peer stores over NVLink
-            const long off = ((long)P.zg_rank * P.N + inst) * n;
+            const long off = P.zg_base + (long)inst * n;
             for (int pr = 0; pr < P.zg_world; ++pr) {
                 double* dst = P.zg[pr] + off;
                 for (int j = T.tid; j < nz; j += TEAM) dst[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
@@ -1352,12 +1367,13 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
     // ---- reset the work counters for the next launch (last CTA out) ----
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (P.zg_world > 0) __threadfence_system(); else __threadfence();  // this CTA's peer stores before its arrival
         const unsigned done = atomicAdd(&P.counters[1], 1u);
         if (done == gridDim.x - 1) {
             P.counters[0] = 0u;
             P.counters[1] = 0u;
             __threadfence();
+            publish_epoch(P);
         }
     }
     (void)TEAMS;

@@ -146,18 +146,20 @@ __global__ void k_getinfo(const double* __restrict__ Ev, long sE, const double* 
 }
 
 // Setup: dense row matrix Gt and extended Hessian / factor for the warp kernel (one CTA per instance).
-//   Gt[r, :] = [sigma_r * p_r, -c_r]:  sparse rows p_r = e_i1 - e_i2, dense rows p_r = Pd[base_r, :]
+//   Gt[p, :] = [sigma_r * p_r, -c_r] for the row r = pos_row[p] of dense position p < mD (zero rows up to GR):
+//   sparse rows p_r = e_i1 - e_i2, dense rows p_r = Pd[base_r, :]  (the unit rows never enter the matrix)
 //   H_ext = blockdiag(Hv, Hee, I_dummy);  L_ext = its Cholesky factor with 1/L_ii on the diagonal
 __global__ void k_make_warp(const double* __restrict__ Pd, long sPd, int nDb, const double* __restrict__ Hv,
-                            const double* __restrict__ Lv, int nHp2, const double* __restrict__ Hee, RowTables rt, int m,
-                            int nz, int neps, int NT, int LDG, int LDH, int MP, double* __restrict__ Gw, long sGw,
-                            double* __restrict__ HL, long sHL) {
+                            const double* __restrict__ Lv, int nHp2, const double* __restrict__ Hee, RowTables rt,
+                            const int* __restrict__ pos_row, int mD, int nz, int neps, int NT, int LDG, int LDH, int GR,
+                            double* __restrict__ Gw, long sGw, double* __restrict__ HL, long sHL) {
     const long inst = blockIdx.x;
     double* G = Gw + inst * sGw;
-    for (int e = threadIdx.x; e < MP * LDG; e += blockDim.x) {
-        const int r = e / LDG, j = e % LDG;
+    for (int e = threadIdx.x; e < GR * LDG; e += blockDim.x) {
+        const int p = e / LDG, j = e % LDG;
         double v = 0.0;
-        if (r < m) {
+        if (p < mD) {
+            const int r = pos_row[p];
             const double sg = rt.row_sig[r], c = rt.row_c[r];
             if (j < nz) {
                 if (r < rt.nS)
@@ -190,6 +192,25 @@ __global__ void k_make_warp(const double* __restrict__ Pd, long sPd, int nDb, co
         }
         H[e] = h;
         L[e] = l;
+    }
+}
+
+// Consumer side: one warp spins (acquire loads) until every rank's flag has reached `epoch`; gives up after `limit`
+// cycles (a rank that died must not hang the device) and reports it in *timed_out.
+__global__ void k_gather_wait(const unsigned long long* flags, int world, unsigned long long epoch, long long limit,
+                              int* timed_out) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > limit) {
+            *timed_out = 1;
+            break;
+        }
+        __nanosleep(64);
     }
 }
 

@@ -2,16 +2,24 @@
 // shape of BASELINE.json's headline config (C1: n = 11, 60 rows).
 //
 // One warp owns one controller instance for the whole moveinput!:
-//   * ALL inequality rows are kept as one dense matrix Gt = [sigma*p_r, -c_r] (m x n, row-major, zero
-//     padded), loaded per instance by ONE TMA bulk copy (cp.async.bulk + mbarrier) together with the
-//     Hessian and its cached Cholesky factor;
-//   * lane l owns rows l, l+32, ... (s, lambda, h, r_p in registers) and, for l < n, decision variable l
-//     (row l of Phi = H + Gt' D Gt and then of its Cholesky factor in registers);
-//   * Phi is formed on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) tiles A = Gt' (8 variables x 4
+//   * rows come in two classes.  UNIT rows -- hard bounds on ONE variable, +-x_i <= h, at most a max- and a min-side
+//     row per variable (C1: the 20 merged input-box rows) -- never enter a matrix: their row product is +-x_i, their
+//     contribution to G'w is +-w_r on lane i and to Phi a diagonal term.  Every other row (predicted outputs,
+//     terminal states, 2-variable increment rows, soft rows) is a DENSE row of Gt = [sigma*p_r, -c_r] (mD x n,
+//     row-major, zero padded), loaded per instance by ONE TMA bulk copy (cp.async.bulk + mbarrier) together with the
+//     Hessian and its cached Cholesky factor.  Rows are addressed by POSITION p: dense rows first, then the unit rows;
+//   * lane l owns positions l, l+32, ... (s, lambda, h, r_p in registers) and, for l < n, decision variable l;
+//   * Phi = H + Gt' D Gt is formed on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) tiles A = Gt' (8 variables x 4
 //     rows), B = D*Gt, accumulators initialised with H; only the lower block-triangle is computed;
-//   * Cholesky and both triangular solves run on registers + warp shuffles; G'w products read Gt
-//     columns from shared memory with the row range split between the two half-warps;
-//   * the redundant  eps >= 0  row of the reference QP is NOT part of Gt: every softness weight is
+//   * Cholesky: right-looking, one row per lane in registers, column k broadcast through shared memory.  The matrix
+//     is BORDERED by the predictor's right-hand side (lane NT): the same column updates leave D^-2 M^-1 rhs there, so
+//     the predictor's forward substitution costs no extra instruction.  The column-scaled factor M = L diag(L)^-1 stays
+//     in shared memory (column-major); each substitution sweep re-reads its row / column of M with independent loads
+//     and then runs n dependent shuffle + FMA steps.  (An explicit W = D^-1 L^-1 from identity border rows, solves as
+//     two mat-vecs, was measured: 7 % shorter iterations but the late, ill-conditioned iterations of the degenerate
+//     instances lose accuracy -- per-period maximum 27 instead of 21 iterations, non-optimal exits -- rejected);
+//   * G'w products read Gt columns from shared memory with the row range split between the two half-warps;
+//   * the redundant  eps >= 0  row of the reference QP is NOT compiled: every softness weight is
 //     non-negative (construct.jl:456-506), so any point with eps < 0 is dominated by the same point with
 //     eps = 0 and the optimum is unchanged -- while the row's vanishing multiplier (no strict
 //     complementarity whenever no soft constraint is active) is what slows interior-point convergence.
@@ -25,20 +33,28 @@
 namespace bmpc {
 
 struct WarpLayout {  // per-warp shared-memory offsets (doubles)
-    int G, H, L, phi, vx, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, ev, total;
+    int G, H, L, phi, vx, vy, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, ev, total;
 };
 
+// per-position row descriptor (built on the host, bmpc_api.cu configure_warp)
+constexpr int PI_VALID = 1, PI_SPARSE = 2, PI_UNIT = 4, PI_ISQ = 8, PI_NEG = 16;
 struct WarpParams {
     WarpLayout L;
-    const double* Gw;  // [MP x LDG] per instance: all rows, zero padded
+    const double* Gw;   // [GR x LDG] per instance: the DENSE rows, zero padded
     long sGw;
-    const double* HL;  // [2 x NT x LDH] per instance: extended Hessian, then its factor (1/L_ii on the diagonal)
+    const double* HL;   // [2 x NT x LDH] per instance: extended Hessian, then its factor (1/L_ii on the diagonal)
     long sHL;
+    const int4* pinfo;  // [32 RPL] per position: x = row index r in the row tables, y = PI_* flags,
+                        //   z = dense: source of the bound (t < nY: F[t], else fx) / sparse: input channel shifting it or -1,
+                        //   w = unit rows: the variable
+    const int* upos;    // [2 x 16] position of the max-side / min-side unit row of each variable (32 RPL = none)
     const int* order;   // processing order of this launch (nullptr: 0..N-1)
     int* order_next;    // written by this launch: slow instances first
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
     int long_thresh;    // iterations from which an instance counts as slow
     int m;              // inequality rows (without the eps >= 0 row)
+    int mD;             // dense rows = positions 0..mD-1; the unit rows follow
+    int GR;             // rows of Gw (mD rounded up for the half-warp split and the DMMA k-steps)
     long long* clk;     // BMPC_PHASE_CLK study builds only: [32] accumulated cycles per phase (nullptr otherwise)
 };
 
@@ -107,26 +123,29 @@ __device__ __forceinline__ void wred_ms(double& a, double& s) {
     a = (double)fa;
 }
 
+#ifndef BMPC_WARP_MINB
+#define BMPC_WARP_MINB 16  // resident warps (one-warp CTAs) per SM the register allocation is capped for
+#endif
 template <int NT, int RPL>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32, BMPC_WARP_MINB)
     step_warp(const __grid_constant__ StepParams P, const __grid_constant__ WarpParams Q) {
     using D = WarpDims<NT>;
     constexpr int NB = D::NB, LDG = D::LDG, LDH = D::LDH, LDN = D::LDN, LDP = D::LDP;
     constexpr int MP = 32 * RPL, NV2 = LDH / 2;
     extern __shared__ __align__(128) double smem[];
     const WarpLayout& L = Q.L;
-    const RowTables& rt = P.rt;
     const int lane = threadIdx.x;
     const int fg = lane >> 2, ft = lane & 3;  // DMMA fragment coordinates
     const int half = lane >> 4, i16 = lane & 15;
     const int nz = P.nz, nr = P.n;  // real sizes: move variables, move variables + slack
     const int nY = P.nY, nu = P.nu, ny = P.ny, nx = P.nx, nd = P.nd;
-    const int nS = rt.nS, nDr = rt.nDr, m = Q.m;
+    const int nS = P.rt.nS, nDr = P.rt.nDr, m = Q.m, mD = Q.mD;
     double* sG = smem + L.G;
     double* sH = smem + L.H;
     double* sL = smem + L.L;
-    double* sPhi = smem + L.phi;  // C tiles of Phi, then the rows of its factor (stride LDN)
+    double* sPhi = smem + L.phi;  // C tiles of Phi (+ the rhs row), then the factor's columns, then W = D^-1 L^-1
     double* vx = smem + L.vx;
+    double* vy = smem + L.vy;
     double* w1 = smem + L.w1;
     double* w2 = smem + L.w2;
     double* wd = smem + L.wd;
@@ -141,7 +160,15 @@ __global__ void __launch_bounds__(32, 16)
 
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (lane < 16) vx[lane] = 0.0;
+    if (lane < 16) {
+        vx[lane] = 0.0;
+        vy[lane] = 0.0;
+    }
+    if (lane < 2) {  // the "no unit row" position MP reads as zero in every row-weight array
+        w1[MP + lane] = 0.0;
+        w2[MP + lane] = 0.0;
+        wd[MP + lane] = 0.0;
+    }
     __syncwarp();
     uint32_t phase = 0;
     const bool isvar = lane < NT;   // lane owns a (real or dummy) variable
@@ -150,9 +177,24 @@ __global__ void __launch_bounds__(32, 16)
     const int iv = isvar ? lane : 0;
     const double2* vx2 = reinterpret_cast<const double2*>(vx);
     const double2* hrow = reinterpret_cast<const double2*>(sH + iv * LDH);
-    const int mh = ((m + 1) / 2 + 3) & ~3;  // rows per half-warp in the G'w products (multiple of 4)
-    const int KS = (m + 3) / 4;             // DMMA k-steps
+    const int mh = ((mD + 1) / 2 + 3) & ~3;  // dense rows per half-warp in the G'w products (multiple of 4)
+    const int KS = (mD + 3) / 4;              // DMMA k-steps
     const double minv = 1.0 / (double)max(m, 1);
+    // per-CTA constants: this lane's positions and, for a variable lane, its unit rows
+    int pflag[RPL], prow[RPL], pz3[RPL], pvar[RPL];
+    double psig[RPL];
+    bool okR[RPL];
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) {
+        const int4 pi = Q.pinfo[lane + 32 * t];
+        prow[t] = pi.x;
+        pflag[t] = pi.y;
+        pz3[t] = pi.z;
+        pvar[t] = pi.w;
+        okR[t] = (pi.y & PI_VALID) != 0;
+        psig[t] = (pi.y & PI_NEG) ? -1.0 : 1.0;
+    }
+    const int up0 = isvar ? Q.upos[lane] : MP, up1 = isvar ? Q.upos[16 + lane] : MP;
 
     PCLK_DECL;
     bool first_pass = true;
@@ -175,16 +217,15 @@ __global__ void __launch_bounds__(32, 16)
         const int lv_ok = P.lv_ok[P.sH ? inst : 0];
         if (lane == 0) {
             fence_proxy_async();
-            const uint32_t bG = (uint32_t)(MP * LDG) * 8u, bH = (uint32_t)(2 * NT * LDH) * 8u;
+            const uint32_t bG = (uint32_t)(Q.GR * LDG) * 8u, bH = (uint32_t)(2 * NT * LDH) * 8u;
             mbar_arrive_expect_tx(bar, bG + bH);
             tma_bulk_g2s(sH, Q.HL + (long)inst * Q.sHL, bH, bar);
-            tma_bulk_g2s(sG, Q.Gw + (long)inst * Q.sGw, bG, bar);
+            if (bG) tma_bulk_g2s(sG, Q.Gw + (long)inst * Q.sGw, bG, bar);
         }
         // ---- stage 1: initpred!  (execute.jl:247-277) ----
         // Every global read of the prologue is ISSUED before the first one is consumed (one DRAM round trip instead of a
-        // dozen dependent ones: with the L2 cold, the old row-by-row loops took ~19 k cycles per instance): the state, the
-        // previous solution and multipliers (warm start), this lane's bounds, and the first 8 x 4 columns of K / V for
-        // the lane's two prediction rows.
+        // dozen dependent ones): the state, the previous solution and multipliers (warm start), this lane's bounds, and
+        // the first 8 / 4 columns of K / V for the lane's two prediction rows.
         const double* gxh = P.est_on ? P.xstate : P.xhat0;
         const double* gK = P.K + (long)inst * P.sK;
         const double* gV = P.V + (long)inst * P.sV;
@@ -202,9 +243,8 @@ __global__ void __launch_bounds__(32, 16)
         double plam[RPL], pbnd[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
-            const int r = lane + 32 * t;
-            plam[t] = (P.use_ws && r < m) ? glw0[r] : 0.0;
-            pbnd[t] = r < nS ? gsb[r] : (r < m ? gdb[r - nS] : 0.0);
+            plam[t] = (P.use_ws && okR[t]) ? glw0[lane + 32 * t] : 0.0;  // (multipliers are kept by position)
+            pbnd[t] = okR[t] ? ((pflag[t] & PI_SPARSE) ? gsb[prow[t]] : gdb[prow[t] - nS]) : 0.0;
         }
         constexpr int KC = 8, VC = 4;
         double kpre[2][KC], vpre[2][VC], bpre[2], mpre[2], rypre[2], yoppre[2];
@@ -300,30 +340,25 @@ __global__ void __launch_bounds__(32, 16)
         __syncwarp();
         // ---- linconstraint!  (transcription.jl:811-848): right-hand sides of this lane's rows ----
         double hR[RPL], sR[RPL], lamR[RPL];
-        bool okR[RPL];
         double hmax = 0.0;
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
-            const int r = lane + 32 * t;
-            okR[t] = r < m;
             double hv = 0.0, wq = 0.0;
-            if (r < nS) {
-                const int ch = rt.s_ch[r];
-                hv = pbnd[t] - (ch >= 0 ? rt.row_sig[r] * slu[ch] : 0.0);
-            } else if (r < m) {
-                const int src = rt.dr_src[r - nS];
-                const double fsrc = src < nY ? sF[src] : sfx[src - nY];
-                hv = rt.row_sig[r] * (pbnd[t] - fsrc);
-                if (P.pd_is_ev) {
+            if (okR[t]) {
+                if (pflag[t] & PI_SPARSE) {
+                    const int ch = pz3[t];
+                    hv = pbnd[t] - (ch >= 0 ? psig[t] * slu[ch] : 0.0);
+                } else {
+                    const int src = pz3[t];
+                    const double fsrc = src < nY ? sF[src] : sfx[src - nY];
+                    hv = psig[t] * (pbnd[t] - fsrc);
                     // q = 2 Ev' tY = Gt' w with w = 2 sigma tY on ONE row per prediction (the max-side row if present)
-                    const int kb = rt.dr_base[r - nS];
-                    const int rmax = rt.db_rmax[kb];
-                    if (rmax == r || (rmax < 0 && rt.db_rmin[kb] == r)) wq = 2.0 * rt.row_sig[r] * stY[src];
+                    if (pflag[t] & PI_ISQ) wq = 2.0 * psig[t] * stY[src];
                 }
             }
             hR[t] = hv;
             hmax = fmax(hmax, fabs(hv));
-            w1[r] = wq;
+            w1[lane + 32 * t] = wq;
         }
         PCLK(12);
         mbar_wait(bar, phase);
@@ -331,23 +366,34 @@ __global__ void __launch_bounds__(32, 16)
         PCLK(13);
 
         // helpers -------------------------------------------------------------------------
-        // out[t] = Gt[r,:] . v   for this lane's rows, v in vx
+        // out[t] = (row at this lane's position t) . v   with v in vx: dense rows from Gt, unit rows +-v_i
         auto row_products = [&](double (&out)[RPL]) {
 #pragma unroll
             for (int t = 0; t < RPL; ++t) {
-                const double2* row = reinterpret_cast<const double2*>(sG + (lane + 32 * t) * LDG);
-                double a = 0.0, b = 0.0;
+                const int p = lane + 32 * t;
+                double r = 0.0;
+                if (p < mD) {
+                    const double2* row = reinterpret_cast<const double2*>(sG + p * LDG);
+                    double2 g2[NV2], v2[NV2];
 #pragma unroll
-                for (int jj = 0; jj < NV2; ++jj) {
-                    const double2 g2 = row[jj];
-                    const double2 v2 = vx2[jj];
-                    a = fma(g2.x, v2.x, a);
-                    b = fma(g2.y, v2.y, b);
+                    for (int jj = 0; jj < NV2; ++jj) {  // (all loads first: one shared-memory latency per row, not twelve)
+                        g2[jj] = row[jj];
+                        v2[jj] = vx2[jj];
+                    }
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < NV2; ++jj) {
+                        a = fma(g2[jj].x, v2[jj].x, a);
+                        b = fma(g2[jj].y, v2[jj].y, b);
+                    }
+                    r = a + b;
+                } else if (pflag[t] & PI_UNIT) {
+                    r = psig[t] * vx[pvar[t]];
                 }
-                out[t] = a + b;
+                out[t] = r;
             }
         };
-        // (Gt' w)_i for lane i < NT; w in shared memory (zero on padding rows)
+        // (Gt' w)_i for lane i < NT; w in shared memory by position (zero on padding positions)
         const double* gcol = sG + (long)half * mh * LDG + (i16 < NT ? i16 : 0);
         auto gt_apply1 = [&](const double* w) -> double {
             const double2* wv = reinterpret_cast<const double2*>(w + half * mh);
@@ -355,20 +401,21 @@ __global__ void __launch_bounds__(32, 16)
 #pragma unroll 2
             for (int r = 0; r < mh; r += 4) {
                 const double2 wa = wv[r >> 1], wb = wv[(r >> 1) + 1];
-                a0 = fma(gcol[r * LDG], wa.x, a0);
-                a1 = fma(gcol[(r + 1) * LDG], wa.y, a1);
-                a2 = fma(gcol[(r + 2) * LDG], wb.x, a2);
-                a3 = fma(gcol[(r + 3) * LDG], wb.y, a3);
+                const double g0 = gcol[r * LDG], g1 = gcol[(r + 1) * LDG], g2 = gcol[(r + 2) * LDG], g3 = gcol[(r + 3) * LDG];
+                a0 = fma(g0, wa.x, a0);
+                a1 = fma(g1, wa.y, a1);
+                a2 = fma(g2, wb.x, a2);
+                a3 = fma(g3, wb.y, a3);
             }
             double a = (a0 + a1) + (a2 + a3);
             a += __shfl_xor_sync(WFULL, a, 16);
-            return a;
+            return a + (w[up0] - w[up1]);  // unit rows of this lane's variable (position MP reads as zero)
         };
         auto gt_apply2 = [&](const double* wa_, const double* wb_, double& outa, double& outb) {
             const double2* wva = reinterpret_cast<const double2*>(wa_ + half * mh);
             const double2* wvb = reinterpret_cast<const double2*>(wb_ + half * mh);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-#pragma unroll 1
+#pragma unroll 2
             for (int r = 0; r < mh; r += 4) {  // mh is a multiple of 4
                 const double2 wa = wva[r >> 1], wa2 = wva[(r >> 1) + 1], wb = wvb[r >> 1], wb2 = wvb[(r >> 1) + 1];
                 const double g0 = gcol[r * LDG], g1 = gcol[(r + 1) * LDG], g2 = gcol[(r + 2) * LDG], g3 = gcol[(r + 3) * LDG];
@@ -384,18 +431,22 @@ __global__ void __launch_bounds__(32, 16)
             double a = (a0 + a1) + (a2 + a3), b = (b0 + b1) + (b2 + b3);
             a += __shfl_xor_sync(WFULL, a, 16);
             b += __shfl_xor_sync(WFULL, b, 16);
-            outa = a;
-            outb = b;
+            outa = a + (wa_[up0] - wa_[up1]);
+            outb = b + (wb_[up0] - wb_[up1]);
         };
         // (H x)_i with x in vx
         auto hess_apply = [&]() -> double {
+            double2 h2[NV2], v2[NV2];
+#pragma unroll
+            for (int jj = 0; jj < NV2; ++jj) {
+                h2[jj] = hrow[jj];
+                v2[jj] = vx2[jj];
+            }
             double a = 0.0, b = 0.0;
 #pragma unroll
             for (int jj = 0; jj < NV2; ++jj) {
-                const double2 h2 = hrow[jj];
-                const double2 v2 = vx2[jj];
-                a = fma(h2.x, v2.x, a);
-                b = fma(h2.y, v2.y, b);
+                a = fma(h2[jj].x, v2[jj].x, a);
+                b = fma(h2[jj].y, v2[jj].y, b);
             }
             return isvar ? a + b : 0.0;
         };
@@ -532,12 +583,12 @@ __global__ void __launch_bounds__(32, 16)
                 double e_p = 0.0, musum = 0.0;
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    const int r = lane + 32 * t;
+                    const int p = lane + 32 * t;
                     isR[t] = okR[t] ? __drcp_rn(sR[t]) : 0.0;
                     dR[t] = lamR[t] * isR[t];
-                    w1[r] = lamR[t];
-                    w2[r] = dR[t] * rpR[t];
-                    wd[r] = dR[t];
+                    w1[p] = lamR[t];
+                    w2[p] = dR[t] * rpR[t];
+                    wd[p] = dR[t];
                     e_p = fmax(e_p, fabs(rpR[t]));
                     musum = fma(sR[t], lamR[t], musum);
                 }
@@ -599,35 +650,31 @@ __global__ void __launch_bounds__(32, 16)
                     const double* ga = sG + ft * LDG + fg;
                     const double* gb = sG + ft * LDG + (ok1 ? 8 + fg : 0);
                     const double* wdp = wd + ft;
-                    // two accumulator sets (even / odd k-steps) halve the dependent DMMA chain
-                    double e00a = 0.0, e00b = 0.0, e10a = 0.0, e10b = 0.0, e11a = 0.0, e11b = 0.0;
-                    auto kstep = [&](int ks, double& x00a, double& x00b, double& x10a, double& x10b, double& x11a, double& x11b) {
-                        const double a0 = ga[ks * 4 * LDG];
-                        const double dk = wdp[ks * 4];
+                    // software pipeline: the fragments of k-step ks+1 are loaded before the DMMAs of k-step ks issue
+                    double a0 = 0.0, a1 = 0.0, dk = 0.0;
+                    if (KS > 0) {
+                        a0 = ga[0];
+                        dk = wdp[0];
+                        if (NB == 2) a1 = gb[0];
+                    }
+#pragma unroll 2
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int kn = ks + 1 < KS ? ks + 1 : ks;
+                        const double a0n = ga[kn * 4 * LDG];
+                        const double dkn = wdp[kn * 4];
+                        double a1n = 0.0;
+                        if (NB == 2) a1n = gb[kn * 4 * LDG];
                         const double b0 = dk * a0;
-                        dmma884(x00a, x00b, a0, b0);
+                        dmma884(c00a, c00b, a0, b0);
                         if (NB == 2) {
-                            double a1 = gb[ks * 4 * LDG];
                             if (pred1) a1 = ok1 ? a1 : 0.0;
                             const double b1 = dk * a1;
-                            dmma884(x10a, x10b, a1, b0);
-                            dmma884(x11a, x11b, a1, b1);
+                            dmma884(c10a, c10b, a1, b0);
+                            dmma884(c11a, c11b, a1, b1);
                         }
-                    };
-                    int ks = 0;
-#pragma unroll 2
-                    for (; ks + 1 < KS; ks += 2) {
-                        kstep(ks, c00a, c00b, c10a, c10b, c11a, c11b);
-                        kstep(ks + 1, e00a, e00b, e10a, e10b, e11a, e11b);
-                    }
-                    if (ks < KS) kstep(ks, c00a, c00b, c10a, c10b, c11a, c11b);
-                    c00a += e00a;
-                    c00b += e00b;
-                    if (NB == 2) {
-                        c10a += e10a;
-                        c10b += e10b;
-                        c11a += e11a;
-                        c11b += e11b;
+                        a0 = a0n;
+                        a1 = a1n;
+                        dk = dkn;
                     }
                 }
                 __syncwarp();
@@ -636,32 +683,40 @@ __global__ void __launch_bounds__(32, 16)
                     *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 2 * ft) = make_double2(c10a, c10b);
                     *reinterpret_cast<double2*>(sPhi + (8 + fg) * LDP + 8 + 2 * ft) = make_double2(c11a, c11b);
                 }
-                // the predictor's right-hand side rides along as row NT of the matrix being factored: the factorisation
-                // then leaves D^-2 M^-1 rhs in that row -- the predictor's forward substitution costs nothing extra
+                // the predictor's right-hand side rides along as an extra row of the matrix being factored
                 const double rhs0 = isvar ? -(Hxq + Gdr) : 0.0;
                 if (lane < LDP) sPhi[8 * NB * LDP + lane] = rhs0;  // (row 8 NB: past the C tiles)
+                const double dunit = wd[up0] + wd[up1];  // unit rows: a diagonal term of Phi
                 __syncwarp();
+                // rows of the bordered matrix: lane < NT row `lane` of Phi, lane NT the predictor's right-hand side
                 double phi[2 * NV2];
                 {
-                    const double2* prow = reinterpret_cast<const double2*>(sPhi + (lane < NT ? lane : (lane == NT ? 8 * NB : 0)) * LDP);
+                    const double2* prw = reinterpret_cast<const double2*>(sPhi + (lane < NT ? lane : 8 * NB) * LDP);
 #pragma unroll
                     for (int jj = 0; jj < NV2; ++jj) {
-                        const double2 p2 = prow[jj];
+                        const double2 p2 = prw[jj];
                         phi[2 * jj] = p2.x;
                         phi[2 * jj + 1] = p2.y;
                     }
                 }
                 double pdiag = 0.0;
 #pragma unroll
-                for (int j = 0; j < NT; ++j)
-                    if (j == lane) pdiag = phi[j];
+                for (int j = 0; j < NT; ++j) {
+                    if (j == lane) {
+                        phi[j] += dunit;
+                        pdiag = phi[j];
+                    }
+                }
                 __syncwarp();
                 PCLK(3);
                 // ---- Cholesky: right-looking, rows in registers; column k goes through shared memory (one store, then
-                // broadcast LDS.128 reads of the entries below the diagonal) -- a quarter of the shuffle traffic of a
-                // per-entry broadcast, and the factor ends up column-major for the backward substitutions ----
+                // broadcast LDS.128 reads of the entries below the diagonal).  The COLUMN-SCALED factor M = L diag(L)^-1
+                // (unit diagonal) is kept in shared memory, column k contiguous, for the substitutions: they then run on
+                // raw broadcasts, without a multiply by 1/L_jj on their dependent chains, and nothing of the factor stays
+                // in registers during the row phases ----
                 double invd = 1.0;
                 double* colbuf = sPhi;
+                double* mbuf = sPhi + NT * LDN;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) {
                     const double dk = bcast(pdiag, k);
@@ -673,8 +728,12 @@ __global__ void __launch_bounds__(32, 16)
                     const double lik = phi[k] * rs;
                     if (lane == k) invd = rs;
                     pdiag = fma(-lik, lik, pdiag);
+                    const double mik = lik * rs;
+                    if (lane < NT) {
+                        if (k + 1 < NT) colbuf[k * LDN + lane] = lik;
+                        mbuf[k * LDN + lane] = mik;
+                    }
                     if (k + 1 < NT) {
-                        if (lane < NT) colbuf[k * LDN + lane] = lik;
                         __syncwarp();
 #pragma unroll
                         for (int jp = (k + 1) / 2; jp <= (NT - 1) / 2; ++jp) {
@@ -683,42 +742,38 @@ __global__ void __launch_bounds__(32, 16)
                             if (2 * jp + 1 < NT) phi[2 * jp + 1] = fma(-lik, c2.y, phi[2 * jp + 1]);
                         }
                     }
-                    // keep the COLUMN-SCALED factor M = L diag(L)^-1 (unit diagonal): both substitutions then run on
-                    // raw broadcasts, without a multiply by 1/L_jj on their dependent chains
-                    phi[k] = lik * rs;
+                    phi[k] = mik;  // (the rhs lane ends up with z = D^-2 M^-1 rhs: its forward substitution came for free)
                 }
                 PCLK(4);
-                // lane NT now holds z = D^-2 M^-1 rhs0: hand z_i to lane i through vx (x is not read again before the
-                // end of the iteration rewrites it)
                 if (lane == NT) {
 #pragma unroll
-                    for (int jj = 0; jj < NV2; ++jj) *reinterpret_cast<double2*>(vx + 2 * jj) = make_double2(phi[2 * jj], phi[2 * jj + 1]);
+                    for (int jj = 0; jj < NV2; ++jj) *reinterpret_cast<double2*>(vy + 2 * jj) = make_double2(phi[2 * jj], 2 * jj + 1 < NT ? phi[2 * jj + 1] : 0.0);
                 }
                 __syncwarp();
-                const double z0 = isvar ? vx[iv] : 0.0;
-                double lcol[NT];  // column `lane` of M (entries below the diagonal): L[j][lane] / L[lane][lane]
-                {
-                    const double2* ccol = reinterpret_cast<const double2*>(colbuf + iv * LDN);
-#pragma unroll
-                    for (int jp = 0; jp <= (NT - 1) / 2; ++jp) {
-                        const double2 c2 = ccol[jp];
-                        lcol[2 * jp] = (lane < 2 * jp) ? c2.x * invd : 0.0;
-                        if (2 * jp + 1 < NT) lcol[2 * jp + 1] = (lane < 2 * jp + 1) ? c2.y * invd : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < NT; ++j) phi[j] = (lane > j && isvar) ? phi[j] : 0.0;  // row `lane` of M, strictly lower part
+                const double z0 = isvar ? vy[iv] : 0.0;
                 PCLK(5);
-                // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b
+                // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b.  Row `lane` / column `lane` of M are re-read from
+                // shared memory at every sweep (independent loads, issued ahead of the dependent shuffle + FMA chain)
                 const double invd2 = invd * invd;
                 auto solve_fwd = [&](double b) -> double {
+                    double mr[NT];
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) b = fma(-phi[j], bcast(b, j), b);  // M^-1 (unit lower)
+                    for (int j = 0; j < NT; ++j) mr[j] = (lane > j && isvar) ? mbuf[j * LDN + iv] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) b = fma(-mr[j], bcast(b, j), b);  // M^-1 (unit lower)
                     return b * invd2;
                 };
                 auto solve_back = [&](double b) -> double {
+                    double mc[2 * NV2];
+                    const double2* ccol = reinterpret_cast<const double2*>(mbuf + iv * LDN);
 #pragma unroll
-                    for (int j = NT - 1; j >= 0; --j) b = fma(-lcol[j], bcast(b, j), b);  // M'^-1 (unit upper)
+                    for (int jp = 0; jp < NV2; ++jp) {
+                        const double2 c2 = ccol[jp];
+                        mc[2 * jp] = (lane < 2 * jp) ? c2.x : 0.0;
+                        mc[2 * jp + 1] = (lane < 2 * jp + 1) ? c2.y : 0.0;
+                    }
+#pragma unroll
+                    for (int j = NT - 1; j >= 0; --j) b = fma(-mc[j], bcast(b, j), b);  // M'^-1 (unit upper)
                     return isvar ? b : 0.0;
                 };
                 // ---- predictor (pass 0) and corrector (pass 1) share one copy of the code ----
@@ -754,7 +809,11 @@ __global__ void __launch_bounds__(32, 16)
                         rho = fmax(rho, fmax(rs_, rl));
                         sdd = fma(dsR[t], dlR[t], sdd);
                     }
-                    wred_ms(rho, sdd);
+                    if (pass == 0) {
+                        wred_ms(rho, sdd);
+                    } else {
+                        rho = (double)wmax_nonneg_f32(f32_up(rho));  // (the sum is only needed after the affine step)
+                    }
                     PCLK(7 + 3 * pass);
                     if (pass == 0) {
                         // affine step: s*dl + lam*ds = -s*lam exactly, so
@@ -765,9 +824,8 @@ __global__ void __launch_bounds__(32, 16)
                         const double sig = ratio * ratio * ratio;
 #pragma unroll
                         for (int t = 0; t < RPL; ++t) {
-                            const int r = lane + 32 * t;
                             rcR[t] = sR[t] * lamR[t] + dsR[t] * dlR[t] - sig * mu;
-                            w1[r] = (lamR[t] * rpR[t] - rcR[t]) * isR[t];
+                            w1[lane + 32 * t] = (lamR[t] * rpR[t] - rcR[t]) * isR[t];
                         }
                         __syncwarp();
                         const double Gw = gt_apply1(w1);
@@ -821,7 +879,7 @@ __global__ void __launch_bounds__(32, 16)
         __syncwarp();
         if (P.zg_world > 0 && lane < nr) {  // fused all-gather of Z̃: peer stores over NVLink (slot (rank, inst) of every peer)
             const double zv = isreal ? x - (lane >= nu ? vx[lane - nu] : 0.0) : x;
-            const long off = ((long)P.zg_rank * P.N + inst) * nr + lane;
+            const long off = P.zg_base + (long)inst * nr + lane;
             for (int pr = 0; pr < P.zg_world; ++pr) P.zg[pr][off] = zv;
         }
         if (isreal) {
@@ -843,7 +901,7 @@ __global__ void __launch_bounds__(32, 16)
             P.u[(long)inst * nu + lane] = lu + du + guop[lane];
         }
         if (P.use_ws) {
-            // multipliers for the next period's warm start (valid only after a converged IPM solve)
+            // multipliers for the next period's warm start (valid only after a converged IPM solve), by position
             const bool keep = status == ST_OPTIMAL && iters > 0;
             double* glw = P.lam_ws + (long)inst * P.ws_stride;
             if (keep) {
@@ -875,8 +933,9 @@ __global__ void __launch_bounds__(32, 16)
         PCLK_FLUSH();
     }
     // ---- reset the work counters for the next launch (last CTA out) ----
+    __syncwarp();  // the other lanes' (peer) stores are ordered before lane 0's fence
     if (lane == 0) {
-        __threadfence();
+        if (P.zg_world > 0) __threadfence_system(); else __threadfence();
         const unsigned done = atomicAdd(&P.counters[1], 1u);
         if (done == gridDim.x - 1) {
             P.counters[0] = 0u;
@@ -886,6 +945,7 @@ __global__ void __launch_bounds__(32, 16)
                 Q.ocnt[1] = 0u;
             }
             __threadfence();
+            publish_epoch(P);
         }
     }
 }
