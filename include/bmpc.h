@@ -272,6 +272,10 @@ int bmhe_update(bmhe_handle *h, const double *u0);
  * bmhe_correct (preparestate!) only returns the current x̂0, as correct_estimate! is empty in that mode. */
 int bmhe_update_solve(bmhe_handle *h, const double *u0, const double *y0m, const double *d0, double *xhat0,
                       double *Ztilde, double *J, int32_t *status, int32_t *iters, double *Vhat, double *X0);
+/* Run the per-period calls on the caller's stream (NULL = the handle's own); with sync = 0 they return without
+ * synchronising it and their array arguments may be DEVICE pointers (the copies are cudaMemcpyDefault): the form a
+ * device-resident caller (or a CUDA-event timed loop) uses.  Default: own stream, sync = 1, host pointers. */
+int bmhe_set_stream(bmhe_handle *h, void *stream, int32_t sync);
 int64_t bmhe_launch_count(bmhe_handle *h);
 
 #ifdef __cplusplus

@@ -19,7 +19,8 @@ struct bmhe_handle {
     bmhe_dims d;
     long NM;
     int nx, nu, nym, nd, He, neps, nZfull;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    bool io_async = false;  // bmhe_set_stream(..., sync = 0): no stream synchronisation after a period (device-resident callers)
     int num_sms = 148;
     bool have_predmat = false, have_cov = false, have_con = false;
     int Nk = 0, compiled_Nk = -1;
@@ -240,8 +241,8 @@ static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, con
     }
     cudaStream_t s = h->stream;
     const size_t N = h->d.N, nx = h->nx, nym = h->nym, nd = h->nd, He = h->He;
-    CK(cudaMemcpyAsync(h->y0m.p, y0m, N * nym * 8, cudaMemcpyHostToDevice, s));
-    if (nd) CK(cudaMemcpyAsync(h->d0.p, d0, N * nd * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->y0m.p, y0m, N * nym * 8, cudaMemcpyDefault, s));
+    if (nd) CK(cudaMemcpyAsync(h->d0.p, d0, N * nd * 8, cudaMemcpyDefault, s));
     bmpc::StepParams P{};
     P.N = h->d.N; P.nz = h->nz; P.n = h->n; P.neps = h->neps; P.max_iter = h->d.max_iter; P.tol = h->d.tol;
     P.tol_mu = h->d.tol * 1e-3; P.rt = h->rt;
@@ -276,14 +277,14 @@ static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, con
     if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE kernel launch failed: %s", cudaGetErrorString(le));
     h->launches++;
     h->Nk = Nk;
-    CK(cudaMemcpyAsync(xhat0, h->xhat0.p, N * nx * 8, cudaMemcpyDeviceToHost, s));
-    if (Ztilde) CK(cudaMemcpyAsync(Ztilde, h->Z.p, N * (h->neps + nx * (1 + He)) * 8, cudaMemcpyDeviceToHost, s));
-    if (J) CK(cudaMemcpyAsync(J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
-    if (Vhat) CK(cudaMemcpyAsync(Vhat, h->Vhat.p, N * nym * He * 8, cudaMemcpyDeviceToHost, s));
-    if (X0) CK(cudaMemcpyAsync(X0, h->X0.p, N * nx * He * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(xhat0, h->xhat0.p, N * nx * 8, cudaMemcpyDefault, s));
+    if (Ztilde) CK(cudaMemcpyAsync(Ztilde, h->Z.p, N * (h->neps + nx * (1 + He)) * 8, cudaMemcpyDefault, s));
+    if (J) CK(cudaMemcpyAsync(J, h->Jv.p, N * 8, cudaMemcpyDefault, s));
+    if (Vhat) CK(cudaMemcpyAsync(Vhat, h->Vhat.p, N * nym * He * 8, cudaMemcpyDefault, s));
+    if (X0) CK(cudaMemcpyAsync(X0, h->X0.p, N * nx * He * 8, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(status, h->status.p, N * 4, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(iters, h->iters.p, N * 4, cudaMemcpyDefault, s));
+    if (!h->io_async) CK(cudaStreamSynchronize(s));
     return BMPC_OK;
 }
 
@@ -310,10 +311,11 @@ int bmhe_create(bmhe_handle** out, const bmhe_dims* dims) {
     h->nZfull = d.nxhat * (1 + d.He);
     h->NM = d.shared_model ? 1 : d.N;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, d.device);
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(BMPC_ERR_CUDA, "cudaStreamCreate failed");
     }
+    h->stream = h->own_stream;
     const size_t N = d.N, nx = d.nxhat, He = d.He;
     cudaError_t a = cudaSuccess;
     auto A = [&](cudaError_t r) { if (a == cudaSuccess) a = r; };
@@ -353,7 +355,7 @@ int bmhe_destroy(bmhe_handle* h) {
     h->lam_ws.release();
     h->ws_flag.release();
     h->t_wsmap.release();
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return BMPC_OK;
 }
@@ -534,7 +536,7 @@ static int launch_update(bmhe_handle* h) {
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(BMPC_ERR_CUDA, "MHE update kernel launch failed: %s", cudaGetErrorString(le));
     h->launches++;
-    CK(cudaStreamSynchronize(s));
+    if (!h->io_async) CK(cudaStreamSynchronize(s));
     return BMPC_OK;
 }
 
@@ -543,7 +545,7 @@ int bmhe_update(bmhe_handle* h, const double* u0) {
     if (!h->d.direct) return fail(BMPC_ERR_STATE, "direct = false: updatestate! needs ym and d, call bmhe_update_solve");
     if (h->Nk < 1) return fail(BMPC_ERR_STATE, "bmhe_correct (preparestate!) must be called before bmhe_update");
     CK(cudaSetDevice(h->d.device));
-    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyDefault, h->stream));
     return launch_update(h);
 }
 
@@ -552,10 +554,17 @@ int bmhe_update_solve(bmhe_handle* h, const double* u0, const double* y0m, const
     if (!h || !u0) return fail(BMPC_ERR_ARG, "null argument");
     if (h->d.direct) return fail(BMPC_ERR_STATE, "direct = true: the window is solved in bmhe_correct; call bmhe_update");
     CK(cudaSetDevice(h->d.device));
-    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->u0.p, u0, (size_t)h->d.N * h->nu * 8, cudaMemcpyDefault, h->stream));
     int rc = solve_window(h, y0m, d0, h->u0.p, xhat0, Ztilde, J, status, iters, Vhat, X0);
     if (rc != BMPC_OK) return rc;
     return launch_update(h);
+}
+
+int bmhe_set_stream(bmhe_handle* h, void* stream, int32_t sync) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    h->io_async = sync == 0;
+    return BMPC_OK;
 }
 
 int64_t bmhe_launch_count(bmhe_handle* h) { return h ? h->launches : 0; }

@@ -124,7 +124,11 @@ __device__ __forceinline__ void wred_ms(double& a, double& s) {
 }
 
 #ifndef BMPC_WARP_MINB
-#define BMPC_WARP_MINB 16  // resident warps (one-warp CTAs) per SM the register allocation is capped for
+// resident warps (one-warp CTAs) per SM the register allocation is capped for.  Measured on C1 (tools/studies/nscale.py):
+// 16 warps x 128 registers 0.181 ms, 12 x 168 registers 0.172 ms, 8 x 228 registers 0.200 ms -- the iteration is a
+// dependent chain whose latency grows with the number of co-resident warps (shared-memory / shuffle pipe), so registers
+// (batched loads, nothing rematerialised) buy more than residency
+#define BMPC_WARP_MINB 12
 #endif
 template <int NT, int RPL>
 __global__ void __launch_bounds__(32, BMPC_WARP_MINB)

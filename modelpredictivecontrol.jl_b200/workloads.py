@@ -11,6 +11,19 @@ CONFIGS = {
 }
 
 
+# setconstraint! recipe of each config (hard input boxes, soft output bounds; C4 adds hard increment bounds and ymin)
+CONSTRAINTS = {
+    "C1": dict(umin=-1.0, umax=1.0, ymax=0.8),
+    "C2": dict(umin=-1.0, umax=1.0, ymax=0.8),
+    "C4": dict(umin=-1.0, umax=1.0, dumin=-0.2, dumax=0.2, ymin=-1.2, ymax=0.8),
+}
+
+
+def constraint_kwargs(name, nu, ny):
+    sizes = dict(umin=nu, umax=nu, dumin=nu, dumax=nu, ymin=ny, ymax=ny)
+    return {k: [v] * sizes[k] for k, v in CONSTRAINTS[name].items()}
+
+
 def random_plants(N, nx, nu, ny, seed, rho=(0.5, 0.95)):
     """A ~ N(0,1) scaled to spectral radius U(0.5, 0.95); Bu, C ~ N(0,1)."""
     rng = np.random.default_rng(seed)

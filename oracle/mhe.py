@@ -281,7 +281,7 @@ class MovingHorizonEstimator(StateEstimator):
         lb = np.full(neps + nZ, -np.inf)
         if neps:
             lb[0] = 0.0
-        return dict(H=H, q=q, r=r, A=A, b=b, lb=lb, F=F, FX=FX, EXt=EXt, Et=Et, nZ=nZ)
+        return dict(H=H, q=q, r=r, A=A, b=b, lb=lb, F=F, FX=FX, EXt=EXt, Et=Et, nZ=nZ, EZ=EZ, FZ=FZ, Mhat=M, Nt=Nt)
 
     def solve_window(self):
         """initpred! + linconstraint! + optim_objective! + getstate! (execute.jl:44-55, 576-638)."""
