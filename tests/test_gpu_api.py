@@ -50,6 +50,7 @@ def test_route_a_equals_route_b(case):
         xh = rng.standard_normal((N, mpcs[0].estim.nxhat)) * 0.5
         ry = rng.standard_normal((N, 2)) + np.stack([m.model.yop for m in mpcs])
         d0 = rng.standard_normal((N, nd)) * 0.2 if nd else None
+        lastu_before = bB.lastu0.copy()
         for b in (bA, bB):
             b.step(xh, ry=ry, d0=d0)
         assert (bA.status == 0).all() and (bB.status == 0).all()
@@ -58,10 +59,15 @@ def test_route_a_equals_route_b(case):
         iA, iB = bA.getinfo(), bB.getinfo()
         for key in ("F", "qtilde", "r"):
             assert np.abs(iA[key] - iB[key]).max() < 1e-10 * (1 + np.abs(iB[key]).max()), key
-        # ... and both against the oracle's own assembly for instance 0
+        # ... and both against the oracle's own assembly and solution for instance 0 (initpred!, linconstraint!, optimum)
         m = mpcs[0]
         m.estim.xhat0 = xh[0].copy()
-        m.lastu0 = iB["U0"][0][:0].copy() if False else m.lastu0
+        m.lastu0 = lastu_before[0].copy()
+        u_or = m.moveinput(ry[0], d=(d0[0] + m.model.dop) if nd else ())
+        for key, ref in (("F", m.F), ("qtilde", m.qtilde), ("r", m.r)):
+            assert np.abs(iB[key][0] - ref).max() < 1e-10 * (1 + np.abs(ref).max()), key
+        assert np.abs(bB.Ztilde[0] - m.Ztilde).max() < 5e-6 * (1 + np.abs(m.Ztilde).max())
+        assert np.abs(bB.u[0] - u_or).max() < 5e-6 * (1 + np.abs(u_or).max())
     assert bA.iters.max() > 0
 
 
@@ -278,3 +284,68 @@ def test_fused_kalman_filter_equals_host_and_oracle(team):
         P = mF.batch.get_cov()
         assert np.abs(P - mH.estim.Phat).max() < 1e-10 * (1 + np.abs(P).max())
         assert np.abs(P - np.stack([o.Phat for o in okf])).max() < 1e-10 * (1 + np.abs(P).max())
+
+
+def test_fused_gather_epoch_flags_two_handles_uneven_shards():
+    """bmpc_set_gather_flags / bmpc_gather_wait: two handles on one device play ranks 0 and 1 of a world of 2 with UNEVEN
+    shards (5 and 8 controllers): every period each "rank" finds all 13 rows of Z̃ of that period in the slot
+    bmpc_gather_wait names, in both buffers, with no barrier between the launches."""
+    import torch
+    from helpers import batch_from_oracle, c1_controllers
+    mpcs, plants, rng = c1_controllers(13, seed=21)
+    shards = [mpcs[:5], mpcs[5:]]
+    bs = [batch_from_oracle(sh) for sh in shards]
+    n, slots, rows = bs[0].n, 3, 13
+    bufs = [torch.zeros((slots, rows, n), dtype=torch.float64, device="cuda") for _ in range(2)]
+    flags = [torch.zeros(8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    offs = [0, 5]
+    for r, b in enumerate(bs):
+        b.set_gather_flags([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], r, offs[r], rows, slots)
+    nxh = mpcs[0].estim.nxhat
+    for k in range(5):
+        ry = rng.choice([-1.0, 1.0], (13, 2))
+        xh = rng.standard_normal((13, nxh)) * 0.3
+        Z = []
+        for r, b in enumerate(bs):
+            sl = slice(offs[r], offs[r] + b.N)
+            b.step(xh[sl], ry=ry[sl])
+            Z.append(b.Ztilde.copy())
+        Zall = np.concatenate(Z)
+        for r, b in enumerate(bs):
+            assert b.gather_epoch() == k + 1
+            slot = b.gather_wait(k + 1)
+            assert slot == (k + 1) % slots and b.gather_timed_out() == 0
+            torch.cuda.synchronize()
+            assert np.array_equal(bufs[r][slot].cpu().numpy(), Zall), (k, r)
+    with pytest.raises(Exception):
+        bs[0].gather_wait(99)  # a period that was never published
+    with pytest.raises(Exception):
+        bs[0].set_gather_flags([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], 0, 10, rows, slots)  # rows overflow
+
+
+def test_create_destroy_does_not_leak_device_memory():
+    """bmpc_destroy / bmhe_destroy release every device allocation of the handle (52 MB leaked per C1 handle)."""
+    import torch
+    import mpc_b200
+    from mpc_b200 import workloads
+    model, rng = workloads.random_plants(512, 4, 2, 2, seed=3)
+
+    def cycle():
+        mpc = mpc_b200.LinMPC(model, Hp=20, Hc=5, Cwt=1e5).setconstraint(umin=[-1, -1], umax=[1, 1], ymax=[0.8, 0.8])
+        mpc.preparestate(np.zeros((512, 2)))
+        mpc.moveinput(np.ones((512, 2)))
+        mpc.batch.close()
+        mhe = mpc_b200.MovingHorizonEstimator(model, He=4, nint_ym=[0, 0])
+        mhe.preparestate(np.zeros((512, 2)))
+        mhe.updatestate(np.zeros((512, 2)))
+        mhe.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(6):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 4 * 1024 * 1024, (free0, free1)

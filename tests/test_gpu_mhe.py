@@ -194,3 +194,33 @@ def test_mhe_status_agreement_many_windows():
         g.updatestate(u, y)
     assert ninf > 40 and nfeas_active > 40, (ninf, nfeas_active)
     print("MHE status agreement: infeasible windows", ninf, "feasible active windows", nfeas_active, "of", N * 14)
+
+
+def test_mhe_nan_measurements_match_oracle():
+    """Missing measurements (NaN in ym): the reference zeroes the affected rows of Ẽ and of F before building H̃ / q̃
+    (src/estimator/mhe/execute.jl:436-441); the kernel does the same (bmpc_mhe.cuh).  Some instances lose one output for
+    one or two periods inside the window; estimates must follow the oracle through the growing and moving windows."""
+    import mpc_b200
+    N, He = 6, 4
+    gm, oms, rng = make(N, 13, nd=0)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0])
+    os_ = [OMHE(m, He=He, nint_ym=0) for m in oms]
+    worst = 0.0
+    for k in range(2 * He + 4):
+        y = np.array([5.0, 3.0]) + rng.standard_normal((N, 2))
+        u = np.array([1.0, -2.0]) + rng.standard_normal((N, 2))
+        if k in (2, 3, 7):
+            y[k % N, k % 2] = np.nan       # one output of one instance is missing this period
+        if k == 6:
+            y[1, :] = np.nan               # both outputs of instance 1
+        xg = g.preparestate(y)
+        for i, o in enumerate(os_):
+            xo = o.preparestate(y[i])
+            assert np.isfinite(xg[i]).all(), (k, i)
+            e = np.abs(xg[i] - xo).max() / (1 + np.abs(xo).max())
+            ej = abs(g.J[i] - o.Jval) / (1 + abs(o.Jval))
+            assert e < 1e-9 and ej < 1e-8, (k, i, e, ej)
+            worst = max(worst, e)
+            o.updatestate(u[i], y[i])
+        g.updatestate(u, y)
+    print("MHE NaN measurements worst", worst)
