@@ -163,6 +163,20 @@ int bmpc_set_constraints(bmpc_handle *h, const double *U0min, const double *U0ma
                          const double *Y0max, const double *xhat0min, const double *xhat0max,
                          const bmpc_softness *soft);
 
+/* Custom linear inequality constraints (LinMPC kwargs Wy, Wu, Wd, Wr: validate_custom_lincon
+ * construct.jl:666-695, relaxW :1138-1160, linconstraint_custom! execute.jl:337-366):
+ *     Wmin <= Wy [ŷ(k); Ŷ] + Wu [U; u(k+Hp-1)] + Wd [d(k); D̂] + Wr [r̂y(k); R̂y] <= Wmax       (nw rows x (Hp + 1) steps)
+ * Wy nw x ny, Wu nw x nu, Wd nw x nd, Wr nw x ny (column-major, NM copies, NULL = zero matrix); Chat = estim.Ĉ (ny x nxhat) and
+ * Ddhat = estim.D̂d (ny x nd) give ŷ(k) = Ĉ x̂0 + D̂d d0 + yop of the first block; dop (nd) turns the deviation-form d0 / D̂0
+ * of bmpc_step into the absolute values the constraint is written in.  The rows' matrix Ew is built on the device; Fw
+ * is rebuilt every period inside the step kernel.  nw = 0 removes them.  Call before bmpc_set_constraints. */
+int bmpc_set_custom(bmpc_handle *h, int32_t nw, const double *Wy, const double *Wu, const double *Wd, const double *Wr,
+                    const double *Chat, const double *Ddhat, const double *dop);
+/* Wmin / Wmax: N x nw (Hp + 1), ABSOLUTE units (NULL = -Inf / +Inf); C_wmin / C_wmax: nw (Hp + 1) softness, shared
+ * (NULL = 1, the reference default).  Compiled into the row tables by the NEXT bmpc_set_constraints call. */
+int bmpc_set_custom_bounds(bmpc_handle *h, const double *Wmin, const double *Wmax, const double *C_wmin,
+                           const double *C_wmax);
+
 /* One control period for all N instances (= moveinput!). */
 int bmpc_step(bmpc_handle *h, const bmpc_step_io *io);
 

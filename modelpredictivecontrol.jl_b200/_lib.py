@@ -60,7 +60,8 @@ SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bm
            "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_estimator_cov", "bmpc_get_cov", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_set_stream", "bmhe_launch_count",
-           "bmpc_set_gather_flags", "bmpc_gather_epoch", "bmpc_gather_wait", "bmpc_gather_timed_out"]
+           "bmpc_set_gather_flags", "bmpc_gather_epoch", "bmpc_gather_wait", "bmpc_gather_timed_out",
+           "bmpc_set_custom", "bmpc_set_custom_bounds"]
 
 
 def lib():
@@ -105,6 +106,8 @@ def lib():
     L.bmhe_update.argtypes = [C.c_void_p, c_double_p]
     L.bmhe_update_solve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                     c_int32_p, c_int32_p, c_double_p, c_double_p]
+    L.bmpc_set_custom.argtypes = [C.c_void_p, C.c_int32] + [c_double_p] * 7
+    L.bmpc_set_custom_bounds.argtypes = [C.c_void_p] + [c_double_p] * 4
     L.bmhe_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.bmpc_set_gather_flags.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32]

@@ -49,6 +49,7 @@ class BatchLinMPC:
         self.J = np.zeros(N)
         self.status = np.zeros(N, dtype=np.int32)
         self.iters = np.zeros(N, dtype=np.int32)
+        self.nw = 0
         self.uop = np.zeros((self.NM, nu))
         self.yop = np.zeros((self.NM, ny))
 
@@ -136,6 +137,28 @@ class BatchLinMPC:
                 keep.append(a)
                 setattr(S, k, dptr(a))
         check(_lib.lib().bmpc_set_constraints(self._h, *[dptr(a) for a in arrs], C.byref(S)))
+
+    def set_custom(self, nw, Wy=None, Wu=None, Wd=None, Wr=None, Chat=None, Ddhat=None, dop=None):
+        """Custom linear constraints (bmpc_set_custom): matrices (NM, nw, cols) or (nw, cols); Chat / Ddhat of the estimator;
+        dop per model.  Call before ``set_constraints``."""
+        nx, nu, ny, nd, NM = self.nxhat, self.nu, self.ny, self.nd, self.NM
+        self.nw = int(nw)
+        if nw == 0:
+            check(_lib.lib().bmpc_set_custom(self._h, 0, *([None] * 7)))
+            return
+        m = lambda a, r, c, nm: None if a is None else self._mat(np.broadcast_to(np.asarray(a, float).reshape(-1, r, c), (NM, r, c)), r, c, nm)
+        args = [m(Wy, nw, ny, "Wy"), m(Wu, nw, nu, "Wu"), m(Wd, nw, nd, "Wd") if nd else None, m(Wr, nw, ny, "Wr"),
+                self._mat(Chat, ny, nx, "Chat"), self._mat(Ddhat, ny, nd, "Ddhat") if nd else None,
+                _vec(dop, NM, nd, "dop") if (nd and dop is not None) else None]
+        check(_lib.lib().bmpc_set_custom(self._h, int(nw), *[dptr(a) for a in args]))
+
+    def set_custom_bounds(self, Wmin=None, Wmax=None, C_wmin=None, C_wmax=None):
+        """Bounds of the custom rows, absolute units, (N, nw (Hp + 1)); compiled by the next ``set_constraints``."""
+        nFw = self.nw * (self.Hp + 1)
+        v = lambda a: None if a is None else _vec(a, self.N, nFw, "W bound")
+        c = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float).reshape(nFw))
+        args = [v(Wmin), v(Wmax), c(C_wmin), c(C_wmax)]
+        check(_lib.lib().bmpc_set_custom_bounds(self._h, *[dptr(a) for a in args]))
 
     def set_estimator(self, Ahat, Buhat, Cmhat, Khat, Bdhat=None, Ddmhat=None, fop_minus_xop=None):
         """Fused SteadyKalmanFilter (bmpc_set_estimator): the handle owns x̂0; ``step(None, y0m=...)`` then runs

@@ -57,6 +57,11 @@ struct bmpc_handle {
         t_blkstart, t_pdsrc;
     DevBuf<short> t_pi, t_pj;
     DevBuf<double> t_sig, t_c, sbase, dbound, Pd;
+    // custom linear constraints (bmpc_set_custom / bmpc_set_custom_bounds)
+    int nw = 0, nFw = 0;
+    DevBuf<double> Wc, Ewv;
+    long sWc = 0;
+    std::vector<double> hWmin, hWmax, hCwmin, hCwmax;  // N x nFw bounds (absolute), nFw softness (shared)
     // host copies of the row tables (the warp kernel's position tables are derived from them)
     std::vector<int> hs_i1, hs_i2, hs_ch, hdr_src, hdr_base, hdb_rmax, hdb_rmin;
     std::vector<double> hsig, hcc;
@@ -155,6 +160,7 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.red = take(40);
     L.bar = take(2);
     L.ev = take(h->d.ny);
+    L.Fw = take(h->nFw);
     L.total = o;
     (void)nz;
 }
@@ -286,6 +292,7 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     L.Dh = take(h->d.nd * h->d.Hp);
     L.bar = take(2);
     L.ev = take(h->d.ny);
+    L.Fw = take(h->nFw);
     L.total = o;
     if (L.H + NT * E.ldh != L.L) return BMPC_ERR_UNSUPPORTED;  // H and its factor are one TMA copy
     h->smem_bytes = L.total * 8;
@@ -380,8 +387,18 @@ int finalize(bmpc_handle* h) {
     cudaStream_t s = h->stream;
     if (!h->pd_is_ev && h->rt.nDb > 0) {
         const long tot = (long)h->NM * h->rt.nDb * h->nz;
-        bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->has_terminal_mats ? h->exv.p : nullptr, h->Pd.p,
-                                                                      h->t_pdsrc.p, h->nY, h->d.nxhat, h->nz, h->rt.nDb,
+        if (h->nw > 0) {  // relaxW: the custom rows' matrix, rebuilt from the current Ev
+            const long totw = (long)h->NM * h->nFw * h->nz;
+            CK(h->Ewv.alloc((size_t)totw));
+            bmpc::k_build_ew<<<(unsigned)((totw + 255) / 256), 256, 0, s>>>(h->Ev.p, (long)h->nEv2, h->Wc.p, h->sWc, h->t_blk.p,
+                                                                          h->Ewv.p, h->nw, h->d.ny, h->d.nu, h->d.nd, h->d.Hp,
+                                                                          h->nY, h->nz, totw);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+        bmpc::k_gather_pd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->Ev.p, h->has_terminal_mats ? h->exv.p : nullptr,
+                                                                      h->nw > 0 ? h->Ewv.p : nullptr, h->Pd.p, h->t_pdsrc.p,
+                                                                      h->nY, h->d.nxhat, h->nFw, h->nz, h->rt.nDb,
                                                                       (long)h->nEv2, h->nPd2, tot);
         h->launches++;
         CK(cudaGetLastError());
@@ -632,13 +649,15 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     auto softv = [&](const double* a, int k, double dflt) { return (neps && a) ? a[k] : (neps ? dflt : 0.0); };
     const bmpc_softness S = soft ? *soft : bmpc_softness{};
     // ---- finiteness pattern (shared by all instances) ----
-    const int plen = 2 * nU + 2 * nz + 2 * nY + 2 * nx;
+    const int nFw = h->nFw;
+    const int plen = 2 * nU + 2 * nz + 2 * nY + 2 * nx + 2 * nFw;
     std::vector<unsigned char> pat(plen, 0);
-    const double* arrs[8] = {U0min, U0max, DUmin, DUmax, Y0min, Y0max, x0min, x0max};
-    const int lens[8] = {nU, nU, nz, nz, nY, nY, nx, nx};
+    const double* arrs[10] = {U0min, U0max, DUmin, DUmax, Y0min, Y0max, x0min, x0max,
+                              h->hWmin.empty() ? nullptr : h->hWmin.data(), h->hWmax.empty() ? nullptr : h->hWmax.data()};
+    const int lens[10] = {nU, nU, nz, nz, nY, nY, nx, nx, nFw, nFw};
     for (int i = 0; i < N; ++i) {
         int o = 0;
-        for (int a = 0; a < 8; ++a) {
+        for (int a = 0; a < 10; ++a) {
             for (int k = 0; k < lens[a]; ++k, ++o) {
                 const double v = get(arrs[a], lens[a], i, k, (a & 1) ? INF : -INF);
                 if (std::isnan(v)) return fail(BMPC_ERR_ARG, "NaN bound");
@@ -652,7 +671,9 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     }
     if (h->stepped && pat != h->pattern)
         return fail(BMPC_ERR_STATE, "Cannot modify +-Inf constraints after the first step (construct.jl:548-551)");
-    const bool any_x = std::any_of(pat.begin() + 2 * nU + 2 * nz + 2 * nY, pat.end(), [](unsigned char c) { return c; });
+    const bool any_x = std::any_of(pat.begin() + 2 * nU + 2 * nz + 2 * nY, pat.begin() + 2 * nU + 2 * nz + 2 * nY + 2 * nx,
+                                   [](unsigned char c) { return c; });
+    const bool any_w = std::any_of(pat.begin() + 2 * nU + 2 * nz + 2 * nY + 2 * nx, pat.end(), [](unsigned char c) { return c; });
     if (any_x && h->have_predmat && !h->has_terminal_mats)
         return fail(BMPC_ERR_ARG, "terminal bounds need the terminal matrices (bmpc_set_predmat ex,kx,vx,bx)");
     // ---- sparse (1-/2-variable) rows, merged by (i1, i2, side, softness, shift channel) ----
@@ -728,6 +749,10 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
         add_dense(t, pat[oY + t], pat[oY + nY + t], softv(S.C_ymin, t, 1.0), softv(S.C_ymax, t, 1.0), 4, 5, t);
     for (int i = 0; i < nx; ++i)
         add_dense(nY + i, pat[oX + i], pat[oX + nx + i], softv(S.c_xmin, i, 1.0), softv(S.c_xmax, i, 1.0), 6, 7, i);
+    const int oW = oX + 2 * nx;  // custom rows: source nY + nx + r  (bound Wmin/Wmax in absolute units, against Fw[r])
+    for (int r = 0; r < nFw; ++r)
+        add_dense(nY + nx + r, pat[oW + r], pat[oW + nFw + r], neps ? (h->hCwmin.empty() ? 1.0 : h->hCwmin[r]) : 0.0,
+                  neps ? (h->hCwmax.empty() ? 1.0 : h->hCwmax[r]) : 0.0, 8, 9, r);
     const int nDr = (int)dr_base.size(), nDb = (int)pd_src.size();
     // The reference's eps >= 0 row is NOT compiled: every softness weight is non-negative (checked below, as in
     // construct.jl:456-506), so a point with eps < 0 is dominated by the same point with eps = 0 -- the optimum is
@@ -817,7 +842,7 @@ int bmpc_set_constraints(bmpc_handle* h, const double* U0min, const double* U0ma
     rt.pair_i = h->t_pi.p;
     rt.pair_j = h->t_pj.p;
     h->has_terminal_rows = any_x;
-    h->pd_is_ev = (nDb == nY) && !any_x;  // dense base rows are exactly the rows of Ev, in order
+    h->pd_is_ev = (nDb == nY) && !any_x && !any_w;  // dense base rows are exactly the rows of Ev, in order
     h->nPd2 = even(nDb * nz);
     if (!h->pd_is_ev && nDb > 0) {
         CK(h->Pd.alloc((size_t)h->NM * h->nPd2));
@@ -932,6 +957,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.nHp2 = h->nHp2; P.nPd2 = h->nPd2;
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
     P.use_ws = (h->warm_start && h->lam_ws.p) ? 1 : 0;
+    P.nw = h->nw; P.sW = d.shared_model ? 0 : h->sWc; P.Wc = h->Wc.p;
     for (int pr = 0; pr < 8; ++pr) {
         P.zg[pr] = h->zg[pr];
         P.zg_flag[pr] = h->zg_flag[pr];
@@ -1170,6 +1196,60 @@ int bmpc_gather_timed_out(bmpc_handle* h) {
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, h->zg_timeout.p, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
+}
+
+int bmpc_set_custom(bmpc_handle* h, int32_t nw, const double* Wy, const double* Wu, const double* Wd, const double* Wr,
+                    const double* Chat, const double* Ddhat, const double* dop) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    const bmpc_dims& d = h->d;
+    if (h->stepped) return fail(BMPC_ERR_STATE, "custom linear constraints cannot change after the first step");
+    if (nw < 0) return fail(BMPC_ERR_ARG, "nw must be >= 0");
+    if (nw == 0) {
+        h->nw = h->nFw = 0;
+        h->hWmin.clear(); h->hWmax.clear(); h->hCwmin.clear(); h->hCwmax.clear();
+        h->dirty = true;
+        return BMPC_OK;
+    }
+    if (!Chat) return fail(BMPC_ERR_ARG, "Chat (estim.Ĉ) is required: ŷ(k) enters the first block of the custom rows");
+    if (d.nd > 0 && !Ddhat) return fail(BMPC_ERR_ARG, "Ddhat is required when nd > 0");
+    CK(cudaSetDevice(d.device));
+    const size_t NM = (size_t)h->NM, ny = d.ny, nu = d.nu, nd = d.nd, nx = d.nxhat, w = (size_t)nw;
+    const size_t per = w * (2 * ny + nu + nd) + ny * nx + ny * nd + nd;
+    std::vector<double> pack(NM * per, 0.0);
+    for (size_t i = 0; i < NM; ++i) {
+        double* o = pack.data() + i * per;
+        auto put = [&](const double* src, size_t cnt) {
+            if (src) std::copy(src + i * cnt, src + (i + 1) * cnt, o);
+            o += cnt;
+        };
+        put(Wy, w * ny); put(Wu, w * nu); put(Wd, w * nd); put(Wr, w * ny); put(Chat, ny * nx); put(Ddhat, ny * nd); put(dop, nd);
+    }
+    CK(h->Wc.upload(pack, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->sWc = (long)per;
+    h->nw = nw;
+    h->nFw = nw * (d.Hp + 1);
+    h->hWmin.clear(); h->hWmax.clear(); h->hCwmin.clear(); h->hCwmax.clear();
+    h->dirty = true;
+    return BMPC_OK;
+}
+
+int bmpc_set_custom_bounds(bmpc_handle* h, const double* Wmin, const double* Wmax, const double* C_wmin, const double* C_wmax) {
+    if (!h) return fail(BMPC_ERR_ARG, "null handle");
+    if (h->nw <= 0) return fail(BMPC_ERR_STATE, "bmpc_set_custom_bounds needs bmpc_set_custom");
+    const size_t cnt = (size_t)h->d.N * h->nFw;
+    auto chk = [&](const double* a, size_t n) { for (size_t i = 0; a && i < n; ++i) if (std::isnan(a[i])) return false; return true; };
+    if (!chk(Wmin, cnt) || !chk(Wmax, cnt)) return fail(BMPC_ERR_ARG, "NaN bound");
+    for (int r = 0; r < h->nFw; ++r)
+        if ((C_wmin && C_wmin[r] < 0) || (C_wmax && C_wmax[r] < 0)) return fail(BMPC_ERR_ARG, "softness weights should be non-negative");
+    if ((C_wmin || C_wmax) && !h->d.neps) return fail(BMPC_ERR_ARG, "Slack variable weight Cwt must be finite to set softness parameters");
+    h->hWmin.assign(cnt, -INFINITY);
+    h->hWmax.assign(cnt, INFINITY);
+    if (Wmin) h->hWmin.assign(Wmin, Wmin + cnt);
+    if (Wmax) h->hWmax.assign(Wmax, Wmax + cnt);
+    if (C_wmin) h->hCwmin.assign(C_wmin, C_wmin + h->nFw); else h->hCwmin.clear();
+    if (C_wmax) h->hCwmax.assign(C_wmax, C_wmax + h->nFw); else h->hCwmax.clear();
+    return BMPC_OK;  // compiled into the row tables by the next bmpc_set_constraints
 }
 
 int bmpc_launch_info(bmpc_handle* h, int32_t out[8]) {

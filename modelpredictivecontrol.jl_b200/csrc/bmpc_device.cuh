@@ -36,14 +36,14 @@ struct RowTables {
     const int* db_rmax;      // [nDb] dense base row -> its max-side row index or -1
     const int* db_rmin;      // [nDb] ... min-side row index or -1
     const int* dr_base;      // [nDr] dense row -> base row k
-    const int* dr_src;       // [nDr] dense row -> source: t < nY (F[t]) or nY + i (fx[i])
+    const int* dr_src;       // [nDr] dense row -> source: t < nY (F[t]), nY + i (fx[i]) or nY + nx + r (custom row r: Fw[r])
     const short* pair_i;     // [nz(nz+1)/2] row index of packed pair p
     const short* pair_j;     //              col index
 };
 
 struct SmemLayout {  // offsets in doubles inside a team's slice
     int Pd, Hv, Phi, x, xb, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
-        xhat, lastu, dd, Dh, red, bar, ev, total;
+        xhat, lastu, dd, Dh, red, bar, ev, Fw, total;
 };
 
 struct StepParams {
@@ -82,6 +82,13 @@ struct StepParams {
     long s_eA, s_eBu, s_eBd, s_eCm, s_eDdm, s_eK, s_efx;
     const double *eA, *eBu, *eBd, *eCm, *eDdm, *eK, *efx, *y0m;
     double *xstate, *xcorr;
+    // custom linear constraints  Wmin <= Wy Ŷe + Wu Ue + Wd D̂e + Wr R̂e <= Wmax  (construct.jl:666-695, 1138-1160;
+    // linconstraint_custom!, execute.jl:337-366): nw rows per step of the extended horizon (Hp + 1 blocks).
+    // Wc per model: [Wy (nw x ny) | Wu (nw x nu) | Wd (nw x nd) | Wr (nw x ny) | Ĉ (ny x nx) | D̂d (ny x nd) | dop (nd)],
+    // each piece column-major.
+    int nw;
+    long sW;
+    const double* Wc;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -127,6 +134,50 @@ __device__ __forceinline__ void publish_epoch(const StepParams& P) {
     for (int pr = 0; pr < P.zg_world; ++pr) {
         unsigned long long* f = P.zg_flag[pr] + P.zg_rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.zg_epoch) : "memory");
+    }
+}
+
+// Fw of the custom linear constraints (linconstraint_custom! + linconstraint_custom_outputs!, execute.jl:337-366), in
+// ABSOLUTE units: block t = 0..Hp of  Wu u(k-1) + Wd d̂(k+t) + Wr r̂y(k+t) + Wy ŷ(k+t)  with ŷ(k) = Ĉ x̂0 + D̂d d0 + yop
+// (evaloutput of the estimator) and ŷ(k+t) = F[t-1] + yop for t >= 1.  xh, lu, d0, Dh, F are this instance's vectors in
+// shared memory; out has nw (Hp + 1) entries.  Called by tid = 0..nth-1 of the team; the caller synchronises.
+__device__ __forceinline__ void custom_fw(const StepParams& P, long inst, int tid, int nth, const double* xh,
+                                          const double* lu, const double* d0, const double* Dh, const double* F,
+                                          double* out) {
+    const int nw = P.nw, ny = P.ny, nu = P.nu, nd = P.nd, nx = P.nx, Hp = P.Hp;
+    const double* W = P.Wc + inst * P.sW;
+    const double* Wy = W;
+    const double* Wu = Wy + nw * ny;
+    const double* Wd = Wu + nw * nu;
+    const double* Wr = Wd + nw * nd;
+    const double* Ch = Wr + nw * ny;
+    const double* Dd = Ch + ny * nx;
+    const double* dop = Dd + ny * nd;
+    const double* guop = P.uop + inst * P.suop;
+    const double* gyop = P.yop + inst * P.syop;
+    for (int idx = tid; idx < nw * (Hp + 1); idx += nth) {
+        const int t = idx / nw, j = idx - t * nw;
+        double a = 0.0;
+        for (int c = 0; c < nu; ++c) a = fma(Wu[j + nw * c], lu[c] + guop[c], a);
+        for (int e = 0; e < nd; ++e) a = fma(Wd[j + nw * e], (t == 0 ? d0[e] : Dh[(t - 1) * nd + e]) + dop[e], a);
+        for (int o = 0; o < ny; ++o) {
+            double r;
+            if (t == 0)
+                r = P.ry ? P.ry[inst * ny + o] : P.Rhat_y[inst * P.nY + o];
+            else
+                r = P.Rhat_y ? P.Rhat_y[inst * P.nY + (t - 1) * ny + o] : P.ry[inst * ny + o];
+            a = fma(Wr[j + nw * o], r, a);
+            double y;
+            if (t == 0) {
+                y = gyop[o];
+                for (int k = 0; k < nx; ++k) y = fma(Ch[o + ny * k], xh[k], y);
+                for (int e = 0; e < nd; ++e) y = fma(Dd[o + ny * e], d0[e], y);
+            } else {
+                y = F[(t - 1) * ny + o] + gyop[o];
+            }
+            a = fma(Wy[j + nw * o], y, a);
+        }
+        out[idx] = a;
     }
 }
 
@@ -1196,6 +1247,10 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
             }
         }
         T.sync();
+        if (P.nw > 0) {  // linconstraint_custom! (execute.jl:337-366)
+            custom_fw(P, inst, T.tid, TEAM, sm_xhat, sm_lastu, sm_d0, sm_Dh, c.F, base + P.sm.Fw);
+            T.sync();
+        }
         // q_v = 2 Ev' tY (+ 2 sum_{t in block} L_t Cu_t);   Ev is Pd when pd_is_ev
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -1246,7 +1301,7 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
                 hv = gsb[r] - (ch >= 0 ? rt.row_sig[r] * sm_lastu[ch] : 0.0);
             } else if (r < nS + nDr) {
                 const int src = rt.dr_src[r - nS];
-                const double fsrc = src < nY ? c.F[src] : c.fx[src - nY];
+                const double fsrc = src < nY ? c.F[src] : (src < nY + nx ? c.fx[src - nY] : (base + P.sm.Fw)[src - nY - nx]);
                 hv = rt.row_sig[r] * (gdb[r - nS] - fsrc);
             } else {
                 hv = 0.0;

@@ -75,10 +75,10 @@ __global__ void k_chol_serial(const double* __restrict__ Hv, double* __restrict_
     ok[inst] = good;
 }
 
-// Pd[k, j] = (src_k < nY ? Ev[src_k, j] : exv[src_k - nY, j])
-__global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restrict__ exv, double* __restrict__ Pd,
-                            const int* __restrict__ pd_src, int nY, int nx, int nz, int nDb, long sEv, int nPd2,
-                            long tot) {
+// Pd[k, j] = src_k < nY ? Ev[src_k, j] : (src_k < nY + nx ? exv[src_k - nY, j] : Ewv[src_k - nY - nx, j])
+__global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restrict__ exv, const double* __restrict__ Ewv,
+                            double* __restrict__ Pd, const int* __restrict__ pd_src, int nY, int nx, int nFw, int nz, int nDb,
+                            long sEv, int nPd2, long tot) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= tot) return;
     const long per = (long)nDb * nz;
@@ -86,8 +86,38 @@ __global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restr
     const int rem = (int)(e - inst * per);
     const int j = rem / nDb, k = rem - j * nDb;
     const int src = pd_src[k];
-    const double v = src < nY ? Ev[inst * sEv + src + (long)nY * j] : exv[inst * (long)nx * nz + (src - nY) + (long)nx * j];
+    double v;
+    if (src < nY)
+        v = Ev[inst * sEv + src + (long)nY * j];
+    else if (src < nY + nx)
+        v = exv[inst * (long)nx * nz + (src - nY) + (long)nx * j];
+    else
+        v = Ewv[inst * (long)nFw * nz + (src - nY - nx) + (long)nFw * j];
     Pd[inst * nPd2 + rem] = v;
+}
+
+// relaxW (construct.jl:1138-1160) in input-level coordinates: Ewv = W̄y [0; Ev] + W̄u [Pu; pu] D, column-major [nFw x nz]:
+// row (t, j): sum_o Wy[j,o] Ev[(t-1) ny + o, :] (t >= 1)  +  Wu[j,c] on the column of input c's level at step min(t, Hp-1)
+__global__ void k_build_ew(const double* __restrict__ Ev, long sEv, const double* __restrict__ Wc, long sW,
+                           const int* __restrict__ blk_of_t, double* __restrict__ Ewv, int nw, int ny, int nu, int nd, int Hp,
+                           int nY, int nz, long tot) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tot) return;
+    const int nFw = nw * (Hp + 1);
+    const long per = (long)nFw * nz;
+    const long inst = e / per;
+    const int rem = (int)(e - inst * per);
+    const int i = rem / nFw, r = rem - i * nFw;
+    const int t = r / nw, j = r - t * nw;
+    const double* Wy = Wc + inst * sW;
+    const double* Wu = Wy + nw * ny;
+    double a = 0.0;
+    if (t >= 1)
+        for (int o = 0; o < ny; ++o) a = fma(Wy[j + nw * o], Ev[inst * sEv + (t - 1) * ny + o + (long)nY * i], a);
+    const int tc = t < Hp ? t : Hp - 1;
+    const int l = i / nu, c = i - l * nu;
+    if (l == blk_of_t[tc]) a += Wu[j + nw * c];
+    Ewv[inst * per + rem] = a;
 }
 
 // getinfo predictions (predict!, transcription.jl:1136-1145; getU0!, :1115) evaluated in level

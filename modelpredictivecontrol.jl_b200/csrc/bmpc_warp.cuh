@@ -33,7 +33,7 @@
 namespace bmpc {
 
 struct WarpLayout {  // per-warp shared-memory offsets (doubles)
-    int G, H, L, phi, vx, vy, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, ev, total;
+    int G, H, L, phi, vx, vy, w1, w2, wd, F, tY, fx, xh, lu, dd, Dh, bar, ev, Fw, total;
 };
 
 // per-position row descriptor (built on the host, bmpc_api.cu configure_warp)
@@ -342,6 +342,10 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             }
         }
         __syncwarp();
+        if (P.nw > 0) {  // linconstraint_custom! (execute.jl:337-366)
+            custom_fw(P, inst, lane, 32, sxh, slu, sd0, sDh, sF, smem + L.Fw);
+            __syncwarp();
+        }
         // ---- linconstraint!  (transcription.jl:811-848): right-hand sides of this lane's rows ----
         double hR[RPL], sR[RPL], lamR[RPL];
         double hmax = 0.0;
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                     hv = pbnd[t] - (ch >= 0 ? psig[t] * slu[ch] : 0.0);
                 } else {
                     const int src = pz3[t];
-                    const double fsrc = src < nY ? sF[src] : sfx[src - nY];
+                    const double fsrc = src < nY ? sF[src] : (src < nY + nx ? sfx[src - nY] : (smem + L.Fw)[src - nY - nx]);
                     hv = psig[t] * (pbnd[t] - fsrc);
                     // q = 2 Ev' tY = Gt' w with w = 2 sigma tY on ONE row per prediction (the max-side row if present)
                     if (pflag[t] & PI_ISQ) wq = 2.0 * psig[t] * stY[src];

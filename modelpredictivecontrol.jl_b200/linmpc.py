@@ -15,7 +15,8 @@ DEFAULT_HP0, DEFAULT_HC, DEFAULT_MWT, DEFAULT_NWT, DEFAULT_LWT, DEFAULT_CWT = 10
 
 class LinMPC:
     def __init__(self, model_or_estim, Hp=None, Hc=DEFAULT_HC, Mwt=None, Nwt=None, Lwt=None, Cwt=DEFAULT_CWT,
-                 device=0, team=0, max_iter=0, tol=0.0, fused_estimator=False, **estim_kwargs):
+                 Wy=None, Wu=None, Wd=None, Wr=None, device=0, team=0, max_iter=0, tol=0.0, fused_estimator=False,
+                 **estim_kwargs):
         estim = model_or_estim if hasattr(model_or_estim, "Ahat") else SteadyKalmanFilter(model_or_estim, **estim_kwargs)
         model = estim.model
         self.estim, self.model = estim, model
@@ -41,15 +42,26 @@ class LinMPC:
                     estim.fophat - estim.xophat, np.tile(self.Mwt, Hp), np.tile(self.Nwt, self.Hc),
                     np.tile(self.Lwt, Hp))
         b.set_oppoints(model.uop, model.yop)
+        # custom linear constraints Wy, Wu, Wd, Wr (validate_custom_lincon, construct.jl:666-695): nw rows, shared by the batch
+        given = [np.atleast_2d(np.asarray(W, float)) for W in (Wy, Wu, Wd, Wr) if W is not None]
+        self.nw = given[0].shape[0] if given else 0
+        if any(g.shape[0] != self.nw for g in given):
+            raise ValueError("Wy, Wu, Wd, Wr must have the same number of rows")
+        if self.nw:
+            z = lambda W, nc: np.zeros((self.nw, nc)) if W is None else np.atleast_2d(np.asarray(W, float)).reshape(self.nw, nc)
+            b.set_custom(self.nw, z(Wy, ny), z(Wu, nu), z(Wd, nd) if nd else None, z(Wr, ny), estim.Chat,
+                         estim.Ddhat if nd else None, model.dop if nd else None)
         self.Uop, self.Yop = np.tile(model.uop, (1, Hp)), np.tile(model.yop, (1, Hp))
         inf = np.inf
         self.con = dict(U0min=np.full((N, nu * Hp), -inf), U0max=np.full((N, nu * Hp), inf),
                         DUmin=np.full((N, nu * self.Hc), -inf), DUmax=np.full((N, nu * self.Hc), inf),
                         Y0min=np.full((N, ny * Hp), -inf), Y0max=np.full((N, ny * Hp), inf),
-                        xhat0min=np.full((N, estim.nxhat), -inf), xhat0max=np.full((N, estim.nxhat), inf))
+                        xhat0min=np.full((N, estim.nxhat), -inf), xhat0max=np.full((N, estim.nxhat), inf),
+                        Wmin=np.full((N, self.nw * (Hp + 1)), -inf), Wmax=np.full((N, self.nw * (Hp + 1)), inf))
         self.soft = dict(C_umin=np.zeros(nu * Hp), C_umax=np.zeros(nu * Hp), C_dumin=np.zeros(nu * self.Hc),
                          C_dumax=np.zeros(nu * self.Hc), C_ymin=np.ones(ny * Hp), C_ymax=np.ones(ny * Hp),
                          c_xmin=np.ones(estim.nxhat), c_xmax=np.ones(estim.nxhat))
+        self.soft_w = dict(C_wmin=np.ones(self.nw * (Hp + 1)), C_wmax=np.ones(self.nw * (Hp + 1)))
         self._solved = False
         # fused_estimator: the SteadyKalmanFilter runs INSIDE the step kernel (correct before moveinput!, predict after
         # it) and x̂0 lives in the handle: preparestate only notes ym, updatestate does nothing, one launch per period.
@@ -77,13 +89,17 @@ class LinMPC:
 
     def _push(self):
         c = self.con
+        if self.nw:
+            sw = self.soft_w if self.batch.neps else dict(C_wmin=None, C_wmax=None)
+            self.batch.set_custom_bounds(c["Wmin"], c["Wmax"], sw["C_wmin"], sw["C_wmax"])
         self.batch.set_constraints(c["U0min"], c["U0max"], c["DUmin"], c["DUmax"], c["Y0min"], c["Y0max"],
                                    c["xhat0min"], c["xhat0max"], self.soft if self.batch.neps else None)
 
     def setconstraint(self, umin=None, umax=None, dumin=None, dumax=None, ymin=None, ymax=None, xhatmin=None,
                       xhatmax=None, Umin=None, Umax=None, DUmin=None, DUmax=None, Ymin=None, Ymax=None,
                       c_umin=None, c_umax=None, c_dumin=None, c_dumax=None, c_ymin=None, c_ymax=None,
-                      c_xhatmin=None, c_xhatmax=None):
+                      c_xhatmin=None, c_xhatmax=None, wmin=None, wmax=None, Wmin=None, Wmax=None, c_wmin=None,
+                      c_wmax=None):
         """``setconstraint!``: bounds are per instance ((N, len) or (len,)), softness is shared."""
         N, Hp, Hc = self.model.N, self.Hp, self.Hc
         nu, ny, nx = self.model.nu, self.model.ny, self.estim.nxhat
@@ -101,11 +117,28 @@ class LinMPC:
         elif Ymin is not None: c["Y0min"] = _b(Ymin, N, (ny * Hp,)) - self.Yop
         if Ymax is None and ymax is not None: c["Y0max"] = rep(ymax, ny, Hp) - self.Yop
         elif Ymax is not None: c["Y0max"] = _b(Ymax, N, (ny * Hp,)) - self.Yop
+        nw = self.nw
+        if (wmin is not None or wmax is not None or Wmin is not None or Wmax is not None) and not nw:
+            raise ValueError("custom bounds need the Wy / Wu / Wd / Wr matrices of the constructor")
+        if Wmin is None and wmin is not None: c["Wmin"] = rep(wmin, nw, Hp + 1)            # construct.jl:410-418
+        elif Wmin is not None: c["Wmin"] = _b(Wmin, N, (nw * (Hp + 1),)).copy()
+        if Wmax is None and wmax is not None: c["Wmax"] = rep(wmax, nw, Hp + 1)
+        elif Wmax is not None: c["Wmax"] = _b(Wmax, N, (nw * (Hp + 1),)).copy()
         if xhatmin is not None: c["xhat0min"] = _b(xhatmin, N, (nx,)) - self.estim.xophat
         if xhatmax is not None: c["xhat0max"] = _b(xhatmax, N, (nx,)) - self.estim.xophat
         ecr = dict(C_umin=(c_umin, nu, Hp), C_umax=(c_umax, nu, Hp), C_dumin=(c_dumin, nu, Hc),
                    C_dumax=(c_dumax, nu, Hc), C_ymin=(c_ymin, ny, Hp), C_ymax=(c_ymax, ny, Hp),
                    c_xmin=(c_xhatmin, nx, 1), c_xmax=(c_xhatmax, nx, 1))
+        for key, val in (("C_wmin", c_wmin), ("C_wmax", c_wmax)):
+            if val is not None:
+                if not self.batch.neps:
+                    raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
+                if self._solved:
+                    raise RuntimeError("Cannot set softness parameters after calling moveinput!")
+                val = np.asarray(val, dtype=np.float64).reshape(nw)
+                if (val < 0).any():
+                    raise ValueError(f"{key} weights should be non-negative")
+                self.soft_w[key] = np.tile(val, Hp + 1)
         if any(v[0] is not None for v in ecr.values()):
             if not self.batch.neps:
                 raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")

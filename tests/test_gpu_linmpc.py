@@ -267,3 +267,82 @@ def test_all_features_vs_oracle(team):
                 assert np.abs(gi["Yhat0"][i] + m.Yop - oi["Yhat"]).max() < tz * (1 + np.abs(oi["Yhat"]).max()), (k, i)
     assert n_active > 10
     print("all features worst", worst, "active", n_active, b.launch_info())
+
+
+def _gpu_model2_with_disturbance(N):
+    """The plant of test/3_test_predictive_control.jl:466-467 (see tests/test_oracle_linmpc.py) as a batch of N copies."""
+    import mpc_b200
+    from oracle.linmpc import zoh_first_order
+    A1, B1, C1 = zoh_first_order(2, 10, 3.0)
+    A2, B2, C2 = zoh_first_order(0.1, 7, 3.0)
+    A = np.diag([A1[0, 0], A2[0, 0]])
+    Bu, Bd = np.array([[B1[0, 0]], [0.0]]), np.array([[0.0], [B2[0, 0]]])
+    C = np.array([[C1[0, 0], C2[0, 0]]])
+    return mpc_b200.LinModel(A, Bu, C, Bd=Bd, Dd=np.zeros((1, 1)), Ts=3.0, N=N, uop=[25], dop=[30], yop=[50]), (A, Bu, C, Bd)
+
+
+@pytest.mark.parametrize("kw,wmin,wmax,steps", [
+    (dict(Wy=[[1]]), 36, 75, [(0, "Yhat", 36), (100, "Yhat", 75)]),
+    (dict(Wu=[[1]]), 4, 20, [(0, "U", 4), (100, "U", 20)]),
+    (dict(Wd=[[1]], Wy=[[1]]), 56, 95, [(0, "Yhat", 56 - 30), (100, "Yhat", 95 - 30)]),
+    (dict(Wr=[[1]], Wy=[[1]]), 52, 175, [(21, "Yhat", 52 - 21), (100, "Yhat", 175 - 100)]),
+])
+def test_custom_linear_constraints_known_answers_gpu(kw, wmin, wmax, steps):
+    """The eight known answers of test/3_test_predictive_control.jl:468-496 through the CUDA path (hard custom rows,
+    Cwt = Inf, Hp = Hc = 50: n = 50, the CTA-team kernel), and the same steps against the oracle at the parity tolerance."""
+    import mpc_b200
+    from oracle.linmpc import LinModel as OLinModel, LinMPC as OLinMPC
+    gm, (A, Bu, C, Bd) = _gpu_model2_with_disturbance(3)
+    g = mpc_b200.LinMPC(gm, Nwt=[0], Cwt=np.inf, Hp=50, Hc=50, **kw)
+    g.setconstraint(wmin=[wmin], wmax=[wmax])
+    o = OLinMPC(OLinModel(A, Bu, C, Bd=Bd, Dd=np.zeros((1, 1)), Ts=3.0, uop=[25], dop=[30], yop=[50]), Nwt=[0],
+                Cwt=np.inf, Hp=50, Hc=50, **kw)
+    o.setconstraint(wmin=[wmin], wmax=[wmax])
+    g.preparestate([[50]] * 3, [[30]] * 3)
+    o.preparestate([50], [30])
+    for ry, key, expect in steps:
+        ug = g.moveinput([[ry]] * 3, [[30]] * 3)
+        uo = o.moveinput([ry], [30])
+        assert (g.batch.status == 0).all()
+        info = g.getinfo()
+        assert np.allclose(info[key], expect, atol=1e-1), (kw, ry, info[key][0][:5])
+        assert np.abs(g.Ztilde[0] - o.Ztilde).max() < 5e-6 * (1 + np.abs(o.Ztilde).max())
+        assert np.abs(ug[0] - uo).max() < 5e-6 * (1 + np.abs(uo).max())
+        assert np.array_equal(g.Ztilde[0], g.Ztilde[2])
+
+
+def test_custom_linear_constraints_warp_kernel_soft_rows_vs_oracle():
+    """Soft custom rows mixing outputs, inputs and setpoints on the C1 shape (n = 11: warp kernel), closed loop vs the oracle."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    from oracle.linmpc import LinModel as OLinModel, LinMPC as OLinMPC
+    N, steps = 6, 12
+    model, rng = workloads.random_plants(N, 4, 2, 2, seed=17)
+    Wy, Wu, Wr = [[1.0, -0.5]], [[0.3, 0.2]], [[-0.2, 0.0]]
+    kw = dict(Hp=20, Hc=5, Cwt=1e4, Wy=Wy, Wu=Wu, Wr=Wr)
+    g = mpc_b200.LinMPC(model, **kw).setconstraint(umin=[-1, -1], umax=[1, 1], wmin=[-0.4], wmax=[0.5], c_wmax=[0.7])
+    os_, plants = [], []
+    for i in range(N):
+        o = OLinMPC(OLinModel(model.A[i], model.Bu[i], model.C[i]), **kw)
+        o.setconstraint(umin=[-1, -1], umax=[1, 1], wmin=[-0.4], wmax=[0.5], c_wmax=[0.7])
+        os_.append(o)
+        plants.append(OLinModel(model.A[i], model.Bu[i], model.C[i]))
+    ry = workloads.setpoints(rng, N, 2, steps, period=6)
+    worst, nact = 0.0, 0
+    for k in range(steps):
+        y = np.stack([p.evaloutput() for p in plants])
+        g.preparestate(y)
+        ug = g.moveinput(ry[k])
+        assert (g.batch.status == 0).all()
+        nact += int((g.batch.iters > 0).sum())
+        for i, o in enumerate(os_):
+            o.preparestate(y[i])
+            uo = o.moveinput(ry[k, i])
+            e = np.abs(g.Ztilde[i] - o.Ztilde).max() / (1 + np.abs(o.Ztilde).max())
+            assert e < 5e-6, (k, i, e)
+            worst = max(worst, e)
+            o.updatestate(uo, y[i])
+            plants[i].updatestate(uo)
+        g.updatestate(ug, y)
+    assert nact > 10 and g.batch.launch_info()["team"] == 32
+    print("custom rows, warp kernel: worst", worst, "active solves", nact)
