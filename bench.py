@@ -427,6 +427,35 @@ def time_linmpc_e2e(mpc, rec, W, K, dev, world=1, dist=None):
                 check={"median_abs_du": float(np.median(du)), "frac_within_1e-6": float((du < 1e-6).mean())})
 
 
+def time_setmodel(mpc, rec, W, K):
+    """batched `setmodel!` EVERY period (adaptive / successive-linearisation MPC, reference
+    src/controller/execute.jl:621-790) followed by `moveinput!`: the augmented models go up, prediction matrices + Hessian
+    + its Cholesky factor + the warp kernel's row matrix are rebuilt on the device, constraints are re-pushed, then the
+    step runs -- Hessian assembly literally on the per-period path.  Host buffers, wall clock."""
+    import torch
+    b = mpc.batch
+    ms = []
+    for k in range(W + K):
+        b.lastu0[:] = rec["lastu0"][k]
+        b.Ztilde[:] = rec["Zin"][k]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mpc._push_model()
+        mpc._push()
+        t1 = time.perf_counter()
+        b.step(rec["xhat0"][k], ry=rec["ry"][k])
+        t2 = time.perf_counter()
+        if k >= W:
+            ms.append((1e3 * (t1 - t0), 1e3 * (t2 - t1)))
+    ms = np.array(ms)
+    du = np.abs(b.u - rec["u"][W + K - 1]).max(axis=1)
+    return {"ms_setmodel": float(np.median(ms[:, 0])), "ms_step_after_setmodel": float(np.median(ms[:, 1])),
+            "value": b.N / (1e-3 * float(np.median(ms.sum(axis=1)))), "unit": "instance-(setmodel + step)s/s",
+            "what": "bmpc_set_model (H2D of Â, B̂u, Ĉ; k_build_model: init_predmat + init_quadprog on the device; Cholesky of H̃) + "
+                    "bmpc_set_oppoints + bmpc_set_constraints + re-layout of the warp kernel's matrices + bmpc_step, host buffers",
+            "u_vs_recorded_last_period": {"median_abs_du": float(np.median(du)), "frac_within_1e-6": float((du < 1e-6).mean())}}
+
+
 def measure_fp64_peak(dev):
     """cuBLAS DGEMM throughput measured in this run (MEASURED_PEAKS.json has no fp64 entry): torch.matmul fp64 4096^3."""
     import torch
@@ -687,6 +716,7 @@ def main():
         dist.barrier()
         b.set_gather(None, 0)
     e = time_linmpc_e2e(mpc, rec, W, K, dev, world, dist)
+    sm = time_setmodel(mpc, rec, 2, min(K, 10)) if (world == 1 and not args.no_configs) else None
     ms_per_step = v["dev_ms"] / K
     value = world * N * K / (v["dev_ms"] * 1e-3)
     iters_rec = rec["iters"][W:W + K]
@@ -718,6 +748,7 @@ def main():
                    "non_optimal_statuses": int((rec["status"][W:W + K] != 0).sum()), "tol": 1e-11, "launch": b.launch_info()},
         "roofline": roofline_linmpc("C1", b, nu, ny, Hp, Hc, mean_iters, world * N, ms_per_step, fp64_peak * world, hbm_peak, traffic, traffic_src),
         "clocks": clk.summary(),
+        "setmodel_every_period": sm,
         "wall_s_timed_region": v["wall_s"],
     }
     b.close()

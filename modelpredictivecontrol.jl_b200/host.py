@@ -123,7 +123,7 @@ def augment_model(model, nint_u=0, nint_ym=None, i_ym=None):
     xop = np.concatenate([model.xop, np.zeros((N, nxs))], axis=1)
     fop = np.concatenate([model.fop, np.zeros((N, nxs))], axis=1)
     return dict(Ahat=Ahat, Buhat=Buhat, Chat=Chat, Bdhat=Bdhat, Ddhat=model.Dd.copy(), xophat=xop, fophat=fop,
-                nxhat=nxh, nxs=nxs, nsu=nsu, i_ym=i_ym, nint_ym=list(nint_ym))
+                nxhat=nxh, nxs=nxs, nsu=nsu, i_ym=i_ym, nint_ym=list(nint_ym), nint_u=nint_u)
 
 
 def dare_filter_sda(A, C, Q, R, iters=60, tol=1e-13):
@@ -184,6 +184,23 @@ class SteadyKalmanFilter:
 
     def setstate(self, xhat):
         self.xhat0 = _b(xhat, self.model.N, (self.nxhat,)) - self.xophat
+
+    def setmodel(self, model):
+        """setmodel!(estim, model) (reference src/estimator/execute.jl:483-544), batched: new plant matrices and operating
+        points, same stochastic model; x̂0 is re-expressed around the new x̂op.  SteadyKalmanFilter itself refuses, as the
+        reference does (kalman.jl:229-234); KalmanFilter and ManualEstimator accept."""
+        if type(self) is SteadyKalmanFilter:
+            raise RuntimeError("SteadyKalmanFilter does not support setmodel! (use KalmanFilter instead)")
+        old = self.model
+        if (model.N, model.nx, model.nu, model.ny, model.nd) != (old.N, old.nx, old.nu, old.ny, old.nd):
+            raise ValueError("model dimensions must be the same")
+        xhat = self.xhat0 + self.xophat
+        keep = {k: getattr(self, k) for k in ("xhat0",)}
+        self.model = model
+        self.__dict__.update(augment_model(model, self.nint_u, self.nint_ym, self.i_ym))
+        self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]
+        self.xhat0 = xhat - self.xophat
+        return self
 
     def preparestate(self, ym, d=None):
         y0m = _b(ym, self.model.N, (len(self.i_ym),)) - self.model.yop[:, self.i_ym]

@@ -38,19 +38,8 @@ class LinMPC:
         self.batch = BatchLinMPC(N, nu, ny, estim.nxhat, Hp, self.nb, nd=nd, Cwt=Cwt, device=device, team=team,
                                  max_iter=max_iter, tol=tol)
         b = self.batch
-        b.set_model(estim.Ahat, estim.Buhat, estim.Chat, estim.Bdhat if nd else None, estim.Ddhat if nd else None,
-                    estim.fophat - estim.xophat, np.tile(self.Mwt, Hp), np.tile(self.Nwt, self.Hc),
-                    np.tile(self.Lwt, Hp))
-        b.set_oppoints(model.uop, model.yop)
-        # custom linear constraints Wy, Wu, Wd, Wr (validate_custom_lincon, construct.jl:666-695): nw rows, shared by the batch
-        given = [np.atleast_2d(np.asarray(W, float)) for W in (Wy, Wu, Wd, Wr) if W is not None]
-        self.nw = given[0].shape[0] if given else 0
-        if any(g.shape[0] != self.nw for g in given):
-            raise ValueError("Wy, Wu, Wd, Wr must have the same number of rows")
-        if self.nw:
-            z = lambda W, nc: np.zeros((self.nw, nc)) if W is None else np.atleast_2d(np.asarray(W, float)).reshape(self.nw, nc)
-            b.set_custom(self.nw, z(Wy, ny), z(Wu, nu), z(Wd, nd) if nd else None, z(Wr, ny), estim.Chat,
-                         estim.Ddhat if nd else None, model.dop if nd else None)
+        self._W = (Wy, Wu, Wd, Wr)
+        self._push_model(first=True)
         self.Uop, self.Yop = np.tile(model.uop, (1, Hp)), np.tile(model.yop, (1, Hp))
         inf = np.inf
         self.con = dict(U0min=np.full((N, nu * Hp), -inf), U0max=np.full((N, nu * Hp), inf),
@@ -78,6 +67,59 @@ class LinMPC:
             b.set_state(estim.xhat0)
             self._y0m = None
         self._push()
+
+    def _push_model(self, first=False):
+        """Route A: the augmented model, the diagonal weights, the operating points and the custom-constraint matrices go to
+        the handle; prediction matrices, Hessian and the custom rows' matrix are (re)built on the device."""
+        estim, model, b, Hp = self.estim, self.estim.model, self.batch, self.Hp
+        nu, ny, nd = model.nu, model.ny, model.nd
+        b.set_model(estim.Ahat, estim.Buhat, estim.Chat, estim.Bdhat if nd else None, estim.Ddhat if nd else None,
+                    estim.fophat - estim.xophat, np.tile(self.Mwt, Hp), np.tile(self.Nwt, self.Hc),
+                    np.tile(self.Lwt, Hp))
+        b.set_oppoints(model.uop, model.yop)
+        # custom linear constraints Wy, Wu, Wd, Wr (validate_custom_lincon, construct.jl:666-695): nw rows, shared by the batch
+        Wy, Wu, Wd, Wr = self._W
+        given = [np.atleast_2d(np.asarray(W, float)) for W in (Wy, Wu, Wd, Wr) if W is not None]
+        self.nw = given[0].shape[0] if given else 0
+        if any(g.shape[0] != self.nw for g in given):
+            raise ValueError("Wy, Wu, Wd, Wr must have the same number of rows")
+        if self.nw and first:
+            z = lambda W, nc: np.zeros((self.nw, nc)) if W is None else np.atleast_2d(np.asarray(W, float)).reshape(self.nw, nc)
+            b.set_custom(self.nw, z(Wy, ny), z(Wu, nu), z(Wd, nd) if nd else None, z(Wr, ny), estim.Chat,
+                         estim.Ddhat if nd else None, model.dop if nd else None)
+
+    def setmodel(self, model=None, Mwt=None, Nwt=None, Lwt=None):
+        """Batched ``setmodel!`` (reference src/controller/execute.jl:621-790): new plant models and / or diagonal weights
+        at run time.  Z̃ is kept; u0(k-1) and the deviation-form bounds are re-expressed around the new operating points
+        (:757-776); prediction matrices and Hessian are rebuilt ON THE DEVICE (bmpc_set_model)."""
+        if self.nw:
+            raise NotImplementedError("setmodel with custom linear constraints (the reference drops them too: Appendix C-2)")
+        if self.fused_estimator:
+            raise NotImplementedError("setmodel with the fused estimator: re-create the controller")
+        m_old = self.estim.model
+        N, Hp = m_old.N, self.Hp
+        uop_old, yop_old, xop_old = m_old.uop.copy(), m_old.yop.copy(), self.estim.xophat.copy()
+        if model is not None:
+            self.estim.setmodel(model)
+            self.model = model
+        m = self.estim.model
+        chk = lambda w, n, name: np.asarray(w, dtype=np.float64).reshape(n)
+        if Mwt is not None: self.Mwt = chk(Mwt, m.ny, "Mwt")
+        if Nwt is not None: self.Nwt = chk(Nwt, m.nu, "Nwt")
+        if Lwt is not None: self.Lwt = chk(Lwt, m.nu, "Lwt")
+        if (self.Mwt < 0).any() or (self.Nwt < 0).any() or (self.Lwt < 0).any():
+            raise ValueError("weights should be nonnegative")
+        c = self.con
+        Uop_new, Yop_new = np.tile(m.uop, (1, Hp)), np.tile(m.yop, (1, Hp))
+        for k, shift in (("U0min", self.Uop - Uop_new), ("U0max", self.Uop - Uop_new), ("Y0min", self.Yop - Yop_new),
+                         ("Y0max", self.Yop - Yop_new), ("xhat0min", xop_old - self.estim.xophat),
+                         ("xhat0max", xop_old - self.estim.xophat)):
+            c[k] = c[k] + shift
+        self.batch.lastu0[:] = self.batch.lastu0 + uop_old - m.uop
+        self.Uop, self.Yop = Uop_new, Yop_new
+        self._push_model()
+        self._push()
+        return self
 
     @property
     def Ztilde(self):

@@ -158,6 +158,7 @@ class StateEstimator:
         if nint_ym is None:
             nint_ym = default_nint(model, self.i_ym, nint_u)
         As, Cs_u, Cs_y, self.nint_u, self.nint_ym = init_estimstoch(model, self.i_ym, nint_u, nint_ym)
+        self._As, self._Cs_u, self._Cs_y = As, Cs_u, Cs_y
         (self.Ahat, self.Buhat, self.Chat, self.Bdhat, self.Ddhat,
          self.xophat, self.fophat) = augment_model(model, As, Cs_u, Cs_y)
         self.nxhat = self.Ahat.shape[0]
@@ -206,6 +207,31 @@ class StateEstimator:
     def update_estimate(self, u0, y0m, d0):
         pass
 
+    def setmodel(self, model, Qhat=None, Rhat=None):
+        """setmodel!(estim, model; Q̂, R̂) (src/estimator/execute.jl:483-544): the new LinModel's matrices and operating
+        points replace the old ones (setmodel_linmodel!, :500-516), the augmented matrices are rebuilt with the same
+        stochastic model, and x̂0 is re-expressed around the new x̂op (setmodel_estimator!, :524-544)."""
+        old = self.model
+        if (model.nu, model.ny, model.nd, model.nx) != (old.nu, old.ny, old.nd, old.nx):
+            raise ValueError("model dimensions must be the same")
+        if model is not old:
+            for k in ("A", "Bu", "C", "Bd", "Dd", "uop", "yop", "dop", "xop", "fop"):
+                setattr(old, k, np.array(getattr(model, k), dtype=float, copy=True))
+        self._setmodel_estimator(Qhat, Rhat)
+        return self
+
+    def _setmodel_estimator(self, Qhat, Rhat):
+        Ah, Bu, Ch, Bd, Dd, xop, fop = augment_model(self.model, self._As, self._Cs_u, self._Cs_y, verify_obsv=False)
+        self.Ahat, self.Buhat, self.Chat, self.Bdhat, self.Ddhat = Ah, Bu, Ch, Bd, Dd
+        self.Cmhat, self.Ddmhat = Ch[self.i_ym], Dd[self.i_ym]
+        xhat = self.xhat0 + self.xophat           # x̂ with the old operating point
+        self.xophat, self.fophat = xop, fop
+        self.xhat0 = xhat - self.xophat
+        if Qhat is not None:
+            self.Qhat = np.atleast_2d(np.asarray(Qhat, float))
+        if Rhat is not None:
+            self.Rhat = np.atleast_2d(np.asarray(Rhat, float))
+
 
 class SteadyKalmanFilter(StateEstimator):
     """src/estimator/kalman.jl:163-227 (gain) and :284-309 (correct / predict).
@@ -233,6 +259,10 @@ class SteadyKalmanFilter(StateEstimator):
         K = np.linalg.solve(S.T, (P @ Cm.T).T).T
         self.Khat = K if direct else A @ K
         self.Phat = P
+
+    def _setmodel_estimator(self, Qhat, Rhat):
+        # src/estimator/kalman.jl:229-234
+        raise RuntimeError("SteadyKalmanFilter does not support setmodel! (use KalmanFilter instead)")
 
     def correct_estimate(self, y0m, d0):
         if np.isnan(y0m).any():  # kalman.jl:248-251
@@ -691,6 +721,75 @@ class LinMPC:
     def setstate(self, xhat):
         self.estim.setstate(xhat)
         return self
+
+
+def _setmodel_linmpc(self, model=None, Mwt=None, Nwt=None, Lwt=None, M_Hp=None, Ntilde_Hc=None, L_Hp=None, **kw):
+    """setmodel!(mpc, model; Mwt, Nwt, Lwt, M_Hp, Ñ_Hc, L_Hp) and setmodel_controller! (src/controller/execute.jl:621-790):
+    new plant model / weights at run time; Z̃ is kept, u0(k-1) and the deviation-form bounds are re-expressed around the
+    new operating points, the prediction matrices, the constraint matrices and H̃ are rebuilt."""
+    m, estim = self.model, self.estim
+    nu, ny, Hp, Hc, neps = m.nu, m.ny, self.Hp, self.Hc, self.neps
+    uop_old, yop_old, xop_old = m.uop.copy(), m.yop.copy(), estim.xophat.copy()
+    estim.setmodel(m if model is None else model, **kw)
+    m = estim.model
+    diag = lambda w, n, reps, name: np.diag(np.tile(_chk_w(w, n, name), reps))
+    if M_Hp is None and Mwt is not None:
+        self.M_Hp = diag(Mwt, ny, Hp, "Mwt")
+    elif M_Hp is not None:
+        self.M_Hp = _herm(M_Hp, ny * Hp, "M_Hp")
+    if Ntilde_Hc is None and Nwt is not None:
+        self.Ntilde_Hc[:nu * Hc, :nu * Hc] = diag(Nwt, nu, Hc, "Nwt")
+    elif Ntilde_Hc is not None:
+        self.Ntilde_Hc = _herm(Ntilde_Hc, nu * Hc + neps, "Ñ_Hc")
+    self.N_Hc = self.Ntilde_Hc[:nu * Hc, :nu * Hc]
+    if L_Hp is None and Lwt is not None:
+        self.L_Hp = diag(Lwt, nu, Hp, "Lwt")
+    elif L_Hp is not None:
+        self.L_Hp = _herm(L_Hp, nu * Hp, "L_Hp")
+    # ---- setmodel_controller! ----
+    nZ = nu * Hc
+    (self.E, self.G, self.J, self.K, self.V, self.B,
+     self.ex, self.gx, self.jx, self.kx, self.vx, self.bx) = init_predmat(estim, Hp, Hc, self.nb)
+    if neps:
+        self.Etilde = np.hstack([self.E, np.zeros((ny * Hp, 1))])
+        self.etilde_x = np.hstack([self.ex, np.zeros((estim.nxhat, 1))])
+    else:
+        self.Etilde, self.etilde_x = self.E, self.ex
+    self.Ew = (self.Wbar_y @ np.vstack([np.zeros((ny, nZ)), self.E]) + self.Wbar_u @ np.vstack([self.Pu, self.Pu[-nu:]]))
+    c = self.con
+    c.U0min, c.U0max = c.U0min + self.Uop, c.U0max + self.Uop            # to absolute with the OLD operating points
+    c.Y0min, c.Y0max = c.Y0min + self.Yop, c.Y0max + self.Yop
+    c.xhat0min, c.xhat0max = c.xhat0min + xop_old, c.xhat0max + xop_old
+    self.lastu0 = self.lastu0 + uop_old - m.uop
+    self.Uop, self.Yop, self.Dop = np.tile(m.uop, Hp), np.tile(m.yop, Hp), np.tile(m.dop, Hp)
+    c.U0min, c.U0max = c.U0min - self.Uop, c.U0max - self.Uop            # back to deviations with the NEW ones
+    c.Y0min, c.Y0max = c.Y0min - self.Yop, c.Y0max - self.Yop
+    c.xhat0min, c.xhat0max = c.xhat0min - estim.xophat, c.xhat0max - estim.xophat
+    self._rebuild_constraints()
+    self.Htilde = 2 * (self.Etilde.T @ self.M_Hp @ self.Etilde + self.Ptilde_Du.T @ self.Ntilde_Hc @ self.Ptilde_Du
+                       + self.Ptilde_u.T @ self.L_Hp @ self.Ptilde_u)
+    return self
+
+
+def _chk_w(w, n, name):
+    w = np.asarray(w, float).reshape(-1)
+    if w.shape != (n,):
+        raise ValueError(f"{name} should be a vector of length {n}")
+    if (w < 0).any():
+        raise ValueError(f"{name} values should be nonnegative")
+    return w
+
+
+def _herm(M, n, name):
+    M = np.asarray(M, float)
+    if M.ndim == 1:
+        M = np.diag(M)
+    if M.shape != (n, n):
+        raise ValueError(f"{name} size should be ({n}, {n})")
+    return np.tril(M) + np.tril(M, -1).T
+
+
+LinMPC.setmodel = _setmodel_linmpc
 
 
 class ExplicitMPC(LinMPC):

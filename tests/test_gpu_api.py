@@ -349,3 +349,56 @@ def test_create_destroy_does_not_leak_device_memory():
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 4 * 1024 * 1024, (free0, free1)
+
+
+def test_batched_setmodel_successive_linearisation_vs_oracle():
+    """Batched ``setmodel!`` (reference src/controller/execute.jl:621-790) between control periods: every few
+    periods each instance gets a new plant model (gain / pole drift as a successive linearisation would produce) and
+    new operating points, once also new weights; the controller keeps Z̃, re-expresses u0(k-1) and the bounds, and the
+    device rebuilds prediction matrices and Hessian.  Closed loop against N oracle controllers doing the same."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    from oracle.linmpc import LinModel as OLinModel, LinMPC as OLinMPC
+    from oracle.mhe import KalmanFilter as OKF
+    N, steps = 6, 24
+    model, rng = workloads.random_plants(N, 3, 2, 2, seed=23)
+    op = dict(uop=[0.5, -0.5], yop=[2.0, 1.0])
+    gm = mpc_b200.LinModel(model.A, model.Bu, model.C, N=N, **op)
+    g = mpc_b200.LinMPC(mpc_b200.KalmanFilter(gm), Hp=12, Hc=3, Cwt=1e5)
+    g.setconstraint(umin=[-1.5, -1.5], umax=[1.5, 1.5], ymax=[3.0, 2.2])
+    os_, plants = [], []
+    for i in range(N):
+        o = OLinMPC(OKF(OLinModel(model.A[i], model.Bu[i], model.C[i], **op)), Hp=12, Hc=3, Cwt=1e5)
+        o.setconstraint(umin=[-1.5, -1.5], umax=[1.5, 1.5], ymax=[3.0, 2.2])
+        os_.append(o)
+        plants.append(OLinModel(model.A[i], model.Bu[i], model.C[i], **op))
+    ry = workloads.setpoints(rng, N, 2, steps, period=8) + np.array([2.0, 1.0])
+    A, Bu, C = model.A.copy(), model.Bu.copy(), model.C.copy()
+    worst, nact = 0.0, 0
+    for k in range(steps):
+        if k in (5, 11, 17):
+            # new linearisation: drifted matrices, shifted operating points (and new weights once)
+            A = A * rng.uniform(0.9, 1.05, (N, 1, 1))
+            Bu = Bu * rng.uniform(0.8, 1.25, (N, 1, 1))
+            op = dict(uop=[0.5 + 0.1 * k, -0.5], yop=[2.0 - 0.05 * k, 1.0 + 0.02 * k])
+            wkw = dict(Mwt=[2.0, 1.0], Nwt=[0.2, 0.05], Lwt=[0.01, 0.0]) if k == 11 else {}
+            g.setmodel(mpc_b200.LinModel(A, Bu, C, N=N, **op), **wkw)
+            for i, o in enumerate(os_):
+                o.setmodel(OLinModel(A[i], Bu[i], C[i], **op), **wkw)
+        y = np.stack([p.evaloutput() for p in plants])
+        g.preparestate(y)
+        ug = g.moveinput(ry[k])
+        assert (g.batch.status == 0).all(), (k, g.batch.status)
+        nact += int((g.batch.iters > 0).sum())
+        for i, o in enumerate(os_):
+            o.preparestate(y[i])
+            uo = o.moveinput(ry[k, i])
+            e = np.abs(g.Ztilde[i] - o.Ztilde).max() / (1 + np.abs(o.Ztilde).max())
+            eu = np.abs(ug[i] - uo).max() / (1 + np.abs(uo).max())
+            assert e < 5e-6 and eu < 5e-6, (k, i, e, eu, g.batch.iters[i])
+            worst = max(worst, e)
+            o.updatestate(uo, y[i])
+            plants[i].updatestate(uo)
+        g.updatestate(ug, y)
+    assert nact > 10
+    print("batched setmodel: worst", worst, "active solves", nact)

@@ -286,3 +286,38 @@ def test_custom_linear_constraints_matrices():
     Re = np.full(8, 55.0)
     W = mpc.Wbar_y @ Ye + mpc.Wbar_u @ Ue + mpc.Wbar_d @ De + mpc.Wbar_r @ Re
     assert np.allclose(W, mpc.Ew @ Z[:3] + mpc.con.Fw, atol=1e-9)
+
+
+def test_setmodel_known_answers():
+    """test/3_test_predictive_control.jl:529-568 ("LinMPC set model"): operating-point change re-expresses the bounds and
+    u0(k-1), a gain change moves the steady-state input (u ~ 2, 15, 13), weights can be replaced."""
+    from oracle.mhe import KalmanFilter
+    A, B, C = zoh_first_order(5, 2, 3.0)
+    mk = lambda gain, yop, uop: LinModel(*zoh_first_order(gain, 2, 3.0), Ts=3.0, yop=[yop], uop=[uop])
+    mpc = LinMPC(KalmanFilter(mk(5, 10, 1)), Nwt=[0], Cwt=1e4, Hp=1000, Hc=1)
+    mpc.setconstraint(umin=[-24], umax=[26])
+    mpc.setconstraint(ymin=[-54], ymax=[56])
+    assert np.allclose(mpc.Yop, 10) and np.allclose(mpc.Uop, 1)
+    assert np.allclose(mpc.con.U0min, -25) and np.allclose(mpc.con.U0max, 25)
+    assert np.allclose(mpc.con.Y0min, -64) and np.allclose(mpc.con.Y0max, 46)
+    mpc.preparestate([10])
+    u = mpc.moveinput([15])
+    assert u == pytest.approx([2], abs=1e-2) and mpc.lastu0 == pytest.approx([1], abs=1e-2)
+    mpc.setmodel(mk(5, 20, 11))
+    assert np.allclose(mpc.Yop, 20) and np.allclose(mpc.Uop, 11)
+    assert np.allclose(mpc.con.U0min, -24.0 - 11) and np.allclose(mpc.con.U0max, 26.0 - 11)
+    assert np.allclose(mpc.con.Y0min, -54.0 - 20) and np.allclose(mpc.con.Y0max, 56.0 - 20)
+    assert mpc.lastu0 == pytest.approx([2 - 11], abs=1e-2)
+    u = mpc.moveinput([40])
+    assert u == pytest.approx([15], abs=1e-2)
+    mpc.setmodel(mk(10, 20, 11))
+    u = mpc.moveinput([40])
+    assert u == pytest.approx([13], abs=1e-2)
+    mpc.setmodel(Mwt=[100], Nwt=[200], Lwt=[300])
+    assert np.allclose(mpc.M_Hp, np.diag(np.full(1000, 100.0)))
+    assert np.allclose(mpc.Ntilde_Hc, np.diag([200.0, 1e4]))
+    assert np.allclose(mpc.L_Hp, np.diag(np.full(1000, 300.0)))
+    mpc.setmodel(M_Hp=np.diag(np.arange(1.0, 1001)), Ntilde_Hc=np.diag([0.1, 1e6]), L_Hp=np.diag(np.arange(1.1, 1001)))
+    assert np.allclose(mpc.M_Hp, np.diag(np.arange(1.0, 1001))) and np.allclose(mpc.Ntilde_Hc, np.diag([0.1, 1e6]))
+    with pytest.raises(RuntimeError):
+        LinMPC(mk(5, 10, 1)).setmodel(mk(5, 20, 11))  # SteadyKalmanFilter: kalman.jl:229-234
