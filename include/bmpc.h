@@ -163,6 +163,16 @@ int bmpc_set_constraints(bmpc_handle *h, const double *U0min, const double *U0ma
                          const double *Y0max, const double *xhat0min, const double *xhat0max,
                          const bmpc_softness *soft);
 
+/* MultipleShooting transcription (LinMPC(...; transcription = MultipleShooting())).  For a LinModel the
+ * MultipleShooting QP -- decision vector Z = [ΔU; X̂0], equality constraints ES Z + FS = 0 (init_predmat
+ * transcription.jl:217-240, init_defectmat :373-414, linconstrainteq! :913-928) -- has the same optimum as the condensed
+ * SingleShooting QP: the defect equations are exactly init_predmat's state recursion.  The CUDA path therefore always
+ * solves the condensed problem; bmpc_get_states returns the X̂0 block (N x nxhat Hp: x̂0(k+1) ... x̂0(k+Hp), deviation
+ * form) implied by the ΔU of the last step, so that a host can assemble Z̃ = [ΔU; X̂0; ε] in the reference's layout.
+ * Needs the augmented model of route A (bmpc_set_model).  After an infeasible period (status 2) ΔU is the shifted
+ * previous solution and X̂0 is the trajectory THAT sequence produces (the reference keeps the shifted previous states). */
+int bmpc_get_states(bmpc_handle *h, double *X0);
+
 /* Custom linear inequality constraints (LinMPC kwargs Wy, Wu, Wd, Wr: validate_custom_lincon
  * construct.jl:666-695, relaxW :1138-1160, linconstraint_custom! execute.jl:337-366):
  *     Wmin <= Wy [ŷ(k); Ŷ] + Wu [U; u(k+Hp-1)] + Wd [d(k); D̂] + Wr [r̂y(k); R̂y] <= Wmax       (nw rows x (Hp + 1) steps)

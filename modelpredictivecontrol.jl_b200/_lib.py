@@ -61,7 +61,7 @@ SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bm
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_set_stream", "bmhe_launch_count",
            "bmpc_set_gather_flags", "bmpc_gather_epoch", "bmpc_gather_wait", "bmpc_gather_timed_out",
-           "bmpc_set_custom", "bmpc_set_custom_bounds"]
+           "bmpc_set_custom", "bmpc_set_custom_bounds", "bmpc_get_states"]
 
 
 def lib():
@@ -106,6 +106,7 @@ def lib():
     L.bmhe_update.argtypes = [C.c_void_p, c_double_p]
     L.bmhe_update_solve.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                     c_int32_p, c_int32_p, c_double_p, c_double_p]
+    L.bmpc_get_states.argtypes = [C.c_void_p, c_double_p]
     L.bmpc_set_custom.argtypes = [C.c_void_p, C.c_int32] + [c_double_p] * 7
     L.bmpc_set_custom_bounds.argtypes = [C.c_void_p] + [c_double_p] * 4
     L.bmhe_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]

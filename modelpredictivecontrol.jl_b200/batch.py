@@ -265,6 +265,12 @@ class BatchLinMPC:
     def gather_timed_out(self):
         return int(_lib.lib().bmpc_gather_timed_out(self._h))
 
+    def get_states(self):
+        """X̂0 block of the MultipleShooting decision vector for the last step (bmpc_get_states): (N, nxhat Hp)."""
+        X0 = np.zeros((self.N, self.nxhat * self.Hp))
+        check(_lib.lib().bmpc_get_states(self._h, dptr(X0)))
+        return X0
+
     def set_stream(self, stream_ptr):
         check(_lib.lib().bmpc_set_stream(self._h, C.c_void_p(stream_ptr)))
 

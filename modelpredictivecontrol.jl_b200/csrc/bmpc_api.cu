@@ -57,6 +57,9 @@ struct bmpc_handle {
         t_blkstart, t_pdsrc;
     DevBuf<short> t_pi, t_pj;
     DevBuf<double> t_sig, t_c, sbase, dbound, Pd;
+    // augmented model kept from route A (bmpc_set_model) for the MultipleShooting state block (bmpc_get_states)
+    DevBuf<double> mA, mBu, mBd, mf;
+    bool have_model_mats = false;
     // custom linear constraints (bmpc_set_custom / bmpc_set_custom_bounds)
     int nw = 0, nFw = 0;
     DevBuf<double> Wc, Ewv;
@@ -1198,6 +1201,28 @@ int bmpc_gather_timed_out(bmpc_handle* h) {
     return v;
 }
 
+int bmpc_get_states(bmpc_handle* h, double* X0) {
+    if (!h || !X0) return fail(BMPC_ERR_ARG, "null argument");
+    if (!h->stepped) return fail(BMPC_ERR_STATE, "bmpc_get_states needs a previous bmpc_step");
+    if (!h->have_model_mats) return fail(BMPC_ERR_STATE, "bmpc_get_states needs the augmented model (bmpc_set_model, route A)");
+    const bmpc_dims& d = h->d;
+    CK(cudaSetDevice(d.device));
+    cudaStream_t s = h->stream;
+    const size_t N = d.N, nx = d.nxhat;
+    DevBuf<double> X;
+    CK(X.alloc(N * nx * d.Hp));
+    const long sh = d.shared_model ? 0 : 1;
+    const int threads = 32 * (int)((nx + 31) / 32);
+    bmpc::k_ms_states<<<(unsigned)N, threads, (2 * nx + d.nu) * sizeof(double), s>>>(
+        h->mA.p, sh * (long)(nx * nx), h->mBu.p, sh * (long)(nx * d.nu), h->mBd.p, sh * (long)(nx * d.nd), h->mf.p, sh * (long)nx,
+        h->last_Z, h->last_xhat0, h->lastu_prev.p, h->last_d0, h->last_Dhat0, h->t_blk.p, X.p, (int)nx, d.nu, d.nd, d.Hp, h->n);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(X0, X.p, N * nx * d.Hp * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return BMPC_OK;
+}
+
 int bmpc_set_custom(bmpc_handle* h, int32_t nw, const double* Wy, const double* Wu, const double* Wd, const double* Wr,
                     const double* Chat, const double* Ddhat, const double* dop) {
     if (!h) return fail(BMPC_ERR_ARG, "null handle");
@@ -1289,7 +1314,8 @@ int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, cons
     CK(cudaSetDevice(d.device));
     cudaStream_t s = h->stream;
     const size_t NM = h->NM, nY = h->nY, nz = h->nz, nx = d.nxhat, nu = d.nu, ny = d.ny, nd = d.nd, Hp = d.Hp, nU = h->nU;
-    DevBuf<double> A, Bu, C, Bd, Dd, f, Nd;
+    DevBuf<double>&A = h->mA, &Bu = h->mBu, &Bd = h->mBd, &f = h->mf;
+    DevBuf<double> C, Dd, Nd;
     std::vector<double> zeros;
     CK(A.upload(Ahat, NM * nx * nx, s));
     CK(Bu.upload(Buhat, NM * nx * nu, s));
@@ -1359,7 +1385,8 @@ int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, cons
     h->have_weights = true;
     h->dirty = true;
     CK(cudaStreamSynchronize(s));
-    A.release(); Bu.release(); C.release(); Bd.release(); Dd.release(); f.release(); Nd.release();
+    C.release(); Dd.release(); Nd.release();
+    h->have_model_mats = true;
     return BMPC_OK;
 }
 

@@ -96,6 +96,54 @@ __global__ void k_gather_pd(const double* __restrict__ Ev, const double* __restr
     Pd[inst * nPd2 + rem] = v;
 }
 
+// X̂0 block of the MultipleShooting decision vector Z = [ΔU; X̂0] (src/controller/transcription.jl:28-60): the states the
+// defect equations ES Z + FS = 0 (init_defectmat :373-414, linconstrainteq! :913-928) tie to the inputs --
+//   x̂0(k+j+1) = Â x̂0(k+j) + B̂u u0(k+j) + B̂d d̂0(k+j) + (f̂op - x̂op),  u0(k+j) = u0(k-1) + sum of the moves up to block(j)
+// -- evaluated from the optimal ΔU of the last step.  One CTA per instance, one thread per state, Hp sequential steps.
+__global__ void k_ms_states(const double* __restrict__ A, long sA, const double* __restrict__ Bu, long sBu,
+                            const double* __restrict__ Bd, long sBd, const double* __restrict__ f, long sf,
+                            const double* __restrict__ Z, const double* __restrict__ xhat0, const double* __restrict__ lastu_prev,
+                            const double* __restrict__ d0, const double* __restrict__ Dhat0, const int* __restrict__ blk_of_t,
+                            double* __restrict__ X0, int nx, int nu, int nd, int Hp, int n) {
+    extern __shared__ double sm[];
+    double* xa = sm;
+    double* xb = sm + nx;
+    double* u = sm + 2 * nx;
+    const long inst = blockIdx.x;
+    const int i = threadIdx.x;
+    const double* Ai = A + inst * sA;
+    const double* Bi = Bu + inst * sBu;
+    const double* Di = Bd + inst * sBd;
+    const double* z = Z + inst * n;
+    if (i < nx) xa[i] = xhat0[inst * nx + i];
+    if (i < nu) u[i] = lastu_prev[inst * nu + i];
+    int blk_done = -1;
+    __syncthreads();
+    for (int j = 0; j < Hp; ++j) {
+        const int bl = blk_of_t[j];
+        if (bl != blk_done) {  // a new move block starts at step j: u0 += Δu_block
+            if (i < nu) u[i] += z[bl * nu + i];
+            blk_done = bl;
+            __syncthreads();
+        }
+        if (i < nx) {
+            double a = f[inst * sf + i];
+            for (int k = 0; k < nx; ++k) a = fma(Ai[i + (long)nx * k], xa[k], a);
+            for (int c = 0; c < nu; ++c) a = fma(Bi[i + (long)nx * c], u[c], a);
+            for (int e = 0; e < nd; ++e) {
+                const double dv = j == 0 ? d0[inst * nd + e] : (Dhat0 ? Dhat0[inst * nd * Hp + (j - 1) * nd + e] : d0[inst * nd + e]);
+                a = fma(Di[i + (long)nx * e], dv, a);
+            }
+            xb[i] = a;
+            X0[inst * (long)nx * Hp + (long)j * nx + i] = a;
+        }
+        __syncthreads();
+        double* t = xa;
+        xa = xb;
+        xb = t;
+    }
+}
+
 // relaxW (construct.jl:1138-1160) in input-level coordinates: Ewv = W̄y [0; Ev] + W̄u [Pu; pu] D, column-major [nFw x nz]:
 // row (t, j): sum_o Wy[j,o] Ev[(t-1) ny + o, :] (t >= 1)  +  Wu[j,c] on the column of input c's level at step min(t, Hp-1)
 __global__ void k_build_ew(const double* __restrict__ Ev, long sEv, const double* __restrict__ Wc, long sW,

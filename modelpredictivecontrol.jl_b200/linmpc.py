@@ -15,8 +15,8 @@ DEFAULT_HP0, DEFAULT_HC, DEFAULT_MWT, DEFAULT_NWT, DEFAULT_LWT, DEFAULT_CWT = 10
 
 class LinMPC:
     def __init__(self, model_or_estim, Hp=None, Hc=DEFAULT_HC, Mwt=None, Nwt=None, Lwt=None, Cwt=DEFAULT_CWT,
-                 Wy=None, Wu=None, Wd=None, Wr=None, device=0, team=0, max_iter=0, tol=0.0, fused_estimator=False,
-                 **estim_kwargs):
+                 Wy=None, Wu=None, Wd=None, Wr=None, transcription="singleshooting", device=0, team=0, max_iter=0, tol=0.0,
+                 fused_estimator=False, **estim_kwargs):
         estim = model_or_estim if hasattr(model_or_estim, "Ahat") else SteadyKalmanFilter(model_or_estim, **estim_kwargs)
         model = estim.model
         self.estim, self.model = estim, model
@@ -35,6 +35,11 @@ class LinMPC:
         if (self.Mwt < 0).any() or (self.Nwt < 0).any() or (self.Lwt < 0).any():
             raise ValueError("weights should be nonnegative")
         self.Cwt = float(Cwt)
+        # transcription: "singleshooting" (default) or "multipleshooting".  Both are solved as the condensed QP (same optimum
+        # for a LinModel); with MultipleShooting ``Ztilde`` is assembled in the reference's layout [ΔU; X̂0; ε]
+        self.transcription = str(transcription).lower().replace("_", "")
+        if self.transcription not in ("singleshooting", "multipleshooting"):
+            raise ValueError("transcription must be 'singleshooting' or 'multipleshooting'")
         self.batch = BatchLinMPC(N, nu, ny, estim.nxhat, Hp, self.nb, nd=nd, Cwt=Cwt, device=device, team=team,
                                  max_iter=max_iter, tol=tol)
         b = self.batch
@@ -123,6 +128,10 @@ class LinMPC:
 
     @property
     def Ztilde(self):
+        if self.transcription == "multipleshooting" and self._solved:
+            b = self.batch
+            Z = b.Ztilde
+            return np.concatenate([Z[:, :b.nDU], b.get_states(), Z[:, b.nDU:]], axis=1)
         return self.batch.Ztilde
 
     @property
@@ -238,6 +247,8 @@ class LinMPC:
         out = dict(DU=i["DU"], eps=i["eps"], J=i["J"], U=i["U0"] + self.Uop, Yhat=i["Yhat0"] + self.Yop,
                    xhatend=i["xhat0end"] + self.estim.xophat, status=i["status"], iters=i["iters"])
         out["u"] = out["U"][:, :self.model.nu]
+        if self.transcription == "multipleshooting":
+            out["X0"] = self.batch.get_states()
         return out
 
 

@@ -308,3 +308,33 @@ def solve_qp(H, q, A=None, b=None, lb=None, ub=None):
         status = INFEASIBLE if viol > 1e-6 else ITERATION_LIMIT
     return dict(z=z, lam=lam, status=status, kkt=res, iters=iters,
                 J0=float(0.5 * z @ H @ z + q @ z))
+
+
+def solve_qp_eq(H, q, A, b, Aeq, beq, lb=None, ub=None):
+    """Exact optimum of  min 1/2 z'Hz + q'z  s.t.  A z <= b,  Aeq z = beq,  lb <= z <= ub  (H only positive
+    semidefinite on the whole space, as the MultipleShooting Hessian is).  The equalities are eliminated with a GENERIC
+    orthonormal null-space basis of Aeq (SVD; nothing of the problem's structure is used): z = z_p + N w, then the
+    reduced inequality QP goes through ``solve_qp``.  Returns the same dict, with z in the original space."""
+    H = np.asarray(H, float)
+    H = 0.5 * (H + H.T)
+    q = np.asarray(q, float)
+    n = q.size
+    Aeq = np.asarray(Aeq, float).reshape(-1, n)
+    beq = np.asarray(beq, float).reshape(-1)
+    G, h = _stack_constraints(n, A, b, lb, ub)
+    if Aeq.shape[0] == 0:
+        return solve_qp(H, q, G, h)
+    U, s, Vt = np.linalg.svd(Aeq, full_matrices=True)
+    rank = int((s > 1e-12 * max(Aeq.shape) * (s[0] if s.size else 1.0)).sum())
+    zp = Vt[:rank].T @ ((U[:, :rank].T @ beq) / s[:rank])
+    if np.abs(Aeq @ zp - beq).max() > 1e-8 * (1 + np.abs(beq).max()):
+        return dict(z=np.full(n, np.nan), lam=None, status=INFEASIBLE, kkt=np.inf, iters=0)
+    N = Vt[rank:].T
+    Hr = N.T @ H @ N
+    qr = N.T @ (H @ zp + q)
+    sol = solve_qp(Hr, qr, G @ N, h - G @ zp)
+    z = zp + N @ sol["z"] if np.all(np.isfinite(sol["z"])) else np.full(n, np.nan)
+    out = dict(sol)
+    out["z"] = z
+    out["J0"] = float(0.5 * z @ H @ z + q @ z) if np.all(np.isfinite(z)) else np.nan
+    return out

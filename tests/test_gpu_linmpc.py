@@ -346,3 +346,51 @@ def test_custom_linear_constraints_warp_kernel_soft_rows_vs_oracle():
         g.updatestate(ug, y)
     assert nact > 10 and g.batch.launch_info()["team"] == 32
     print("custom rows, warp kernel: worst", worst, "active solves", nact)
+
+
+def test_multiple_shooting_vs_oracle_ms():
+    """LinMPC(transcription = MultipleShooting()) through the CUDA path: the condensed solve + bmpc_get_states against the
+    oracle's ACTUAL MultipleShooting QP (equality constrained, oracle/linmpc_ms.py): Z̃ = [ΔU; X̂0; ε], u, J over a closed loop
+    with hard input / increment bounds and soft output bounds; then the reference's known answers (test/3:120-127)."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    from oracle.linmpc import LinModel as OLinModel, zoh_first_order
+    from oracle.linmpc_ms import LinMPCMultipleShooting
+    N, steps = 5, 10
+    model, rng = workloads.random_plants(N, 3, 2, 2, seed=29)
+    kw = dict(Hp=9, Hc=3, Cwt=1e4, Lwt=[0.05, 0.0])
+    cons = dict(umin=[-1, -1], umax=[1, 1], dumin=[-0.6, -0.6], dumax=[0.6, 0.6], ymax=[0.7, 0.7])
+    g = mpc_b200.LinMPC(model, transcription="MultipleShooting", **kw).setconstraint(**cons)
+    os_ = [LinMPCMultipleShooting(OLinModel(model.A[i], model.Bu[i], model.C[i]), **kw).setconstraint(**cons) for i in range(N)]
+    plants = [OLinModel(model.A[i], model.Bu[i], model.C[i]) for i in range(N)]
+    ry = workloads.setpoints(rng, N, 2, steps, period=5)
+    worst, nact = 0.0, 0
+    for k in range(steps):
+        y = np.stack([p.evaloutput() for p in plants])
+        g.preparestate(y)
+        ug = g.moveinput(ry[k])
+        Zg = g.Ztilde
+        info = g.getinfo()
+        assert Zg.shape == (N, os_[0].n) and (g.batch.status == 0).all()
+        nact += int((g.batch.iters > 0).sum())
+        for i, o in enumerate(os_):
+            o.preparestate(y[i])
+            uo = o.moveinput(ry[k, i])
+            e = np.abs(Zg[i] - o.Ztilde).max() / (1 + np.abs(o.Ztilde).max())
+            assert e < 5e-6 and np.abs(ug[i] - uo).max() < 5e-6, (k, i, e)
+            io = o.getinfo()
+            assert abs(info["J"][i] - io["J"]) < 1e-7 * (1 + abs(io["J"]))
+            assert np.abs(info["X0"][i] - io["X0"]).max() < 5e-6 * (1 + np.abs(io["X0"]).max())
+            worst = max(worst, e)
+            o.updatestate(uo, y[i])
+            plants[i].updatestate(uo)
+        g.updatestate(ug, y)
+    assert nact > 5
+    print("MultipleShooting vs oracle MS: worst", worst, "active solves", nact)
+    # test/3_test_predictive_control.jl:120-127
+    A, B, C = zoh_first_order(5, 2, 3.0)
+    g5 = mpc_b200.LinMPC(mpc_b200.LinModel(A, B, C, Ts=3.0, yop=[10]), Nwt=[0], Hp=1000, Hc=1, transcription="multipleshooting")
+    g5.preparestate([[10]])
+    u = g5.moveinput([[15]])
+    assert abs(u[0, 0] - 1) < 1e-2 and abs(g5.getinfo()["Yhat"][0, -1] - 15) < 1e-2
+    assert g5.Ztilde.shape == (1, 1 + 2 * 1000 + 1)
