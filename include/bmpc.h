@@ -107,6 +107,11 @@ typedef struct {
     const double *y0m;    /* N x nym  measured outputs, deviation (ym - yop[i_ym]).  Used instead of xhat0 (which must
                            * then be NULL) after bmpc_set_estimator: the step kernel runs the observer's correction
                            * before the controller and its prediction after it (one launch per control period).   */
+    const double *Yhat_s; /* N x nYhat or NULL  stochastic output predictions Ŷs = Ks x̂s + Ps ŷs of an InternalModel estimator
+                           * (init_stochpred construct.jl:1254-1267, predictstoch! execute.jl:321-327): F starts from them.     */
+    double *kkt;          /* out, N x 3 or NULL  relative KKT residuals of the returned iterate: primal ||Gx+s-h|| / (1+||h||),
+                           * dual ||Hx+q+G'lam|| / (1+||q||+terms), complementarity s'lam / ((1+||q||)(1+||h||)).  Zeros for the
+                           * unconstrained exit.  Tells a tol-level solve (1e-11) from an "acceptable" one (<= 1e-8).           */
 } bmpc_step_io;
 
 /* Diagnostics of the last step (= getinfo, execute.jl:145-198); any pointer may be NULL.

@@ -6,12 +6,12 @@ this package is only the host-side mirror of the reference interface for that pa
 from . import _lib
 from ._lib import (BmpcError, STATUS_INFEASIBLE, STATUS_ITERATION_LIMIT, STATUS_OPTIMAL)
 from .batch import BatchLinMPC
-from .host import KalmanFilter, LinModel, ManualEstimator, SteadyKalmanFilter, move_blocking
+from .host import InternalModel, KalmanFilter, LinModel, ManualEstimator, SteadyKalmanFilter, move_blocking
 from .linmpc import LinMPC, sim
 from .mhe import MovingHorizonEstimator
 from . import workloads
 from .shard import gather_moves, shard_range
 
-__all__ = ["BatchLinMPC", "LinMPC", "MovingHorizonEstimator", "LinModel", "SteadyKalmanFilter", "KalmanFilter", "ManualEstimator", "sim", "workloads", "shard_range", "gather_moves",
+__all__ = ["BatchLinMPC", "LinMPC", "MovingHorizonEstimator", "LinModel", "SteadyKalmanFilter", "KalmanFilter", "InternalModel", "ManualEstimator", "sim", "workloads", "shard_range", "gather_moves",
            "BmpcError", "move_blocking", "STATUS_OPTIMAL", "STATUS_ITERATION_LIMIT",
            "STATUS_INFEASIBLE"]

@@ -34,7 +34,7 @@ class StepIO(C.Structure):
                  ("Rhat_u", C.c_void_p), ("d0", C.c_void_p), ("Dhat0", C.c_void_p), ("Ztilde", C.c_void_p),
                  ("u", C.c_void_p), ("J", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p),
                  ("device_ptrs", C.c_int32), ("sync", C.c_int32), ("resident", C.c_int32), ("host_mapped", C.c_int32),
-                 ("y0m", C.c_void_p)])
+                 ("y0m", C.c_void_p), ("Yhat_s", C.c_void_p), ("kkt", C.c_void_p)])
 
 
 class MheDims(C.Structure):

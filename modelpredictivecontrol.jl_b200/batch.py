@@ -49,6 +49,7 @@ class BatchLinMPC:
         self.J = np.zeros(N)
         self.status = np.zeros(N, dtype=np.int32)
         self.iters = np.zeros(N, dtype=np.int32)
+        self.kkt = np.zeros((N, 3))  # relative KKT residuals of the returned iterate (primal, dual, complementarity)
         self.nw = 0
         self.uop = np.zeros((self.NM, nu))
         self.yop = np.zeros((self.NM, ny))
@@ -195,7 +196,7 @@ class BatchLinMPC:
         return a, b
 
     # ---- per-period call (= moveinput!) ----------------------------------------------------
-    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None, resident=False, y0m=None):
+    def step(self, xhat0, ry=None, Rhat_y=None, Rhat_u=None, d0=None, Dhat0=None, resident=False, y0m=None, Yhat_s=None):
         """One control period (moveinput!).  ``resident=True``: lastu0 and Z̃ stay in the handle between calls
         (they are fields of the reference controller, not arguments of moveinput!): only x̂0/ry go up and only
         u/status come back; self.lastu0, self.Ztilde, self.J, self.iters are then NOT refreshed."""
@@ -207,14 +208,15 @@ class BatchLinMPC:
         Ru = None if Rhat_u is None else _vec(Rhat_u, N, self.nU, "Rhat_u")
         d0v = None if d0 is None or self.nd == 0 else _vec(d0, N, self.nd, "d0")
         Dh = None if Dhat0 is None or self.nd == 0 else _vec(Dhat0, N, self.nd * self.Hp, "Dhat0")
+        Ys = None if Yhat_s is None else _vec(Yhat_s, N, self.nY, "Yhat_s")
         p = lambda a: None if a is None else a.ctypes.data
         if resident:
             io = _lib.StepIO(xhat0=p(x), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v), Dhat0=p(Dh), u=p(self.u),
-                             status=p(self.status), device_ptrs=0, sync=1, resident=1, y0m=p(ym))
+                             status=p(self.status), device_ptrs=0, sync=1, resident=1, y0m=p(ym), Yhat_s=p(Ys), kkt=p(self.kkt))
         else:
             io = _lib.StepIO(xhat0=p(x), lastu0=p(self.lastu0), ry=p(ryv), Rhat_y=p(Ry), Rhat_u=p(Ru), d0=p(d0v),
                              Dhat0=p(Dh), Ztilde=p(self.Ztilde), u=p(self.u), J=p(self.J), status=p(self.status),
-                             iters=p(self.iters), device_ptrs=0, sync=1, y0m=p(ym))
+                             iters=p(self.iters), device_ptrs=0, sync=1, y0m=p(ym), Yhat_s=p(Ys), kkt=p(self.kkt))
         check(_lib.lib().bmpc_step(self._h, C.byref(io)))
         return self.u
 

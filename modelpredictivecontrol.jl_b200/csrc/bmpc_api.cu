@@ -72,7 +72,7 @@ struct bmpc_handle {
     int nPd2 = 0;
     bool pd_is_ev = false, pd_in_smem = false, has_terminal_rows = false, hv_in_smem = true;
     // io staging
-    DevBuf<double> xhat0, lastu0, ry, Rhat_y, Rhat_u, d0, Dhat0, Z, u, Jv, F, qt, r, lastu_prev;
+    DevBuf<double> xhat0, lastu0, ry, Rhat_y, Rhat_u, d0, Dhat0, Z, u, Jv, F, qt, r, lastu_prev, Ys, kkt;
     DevBuf<int> status, iters;
     DevBuf<unsigned int> counters;
     // launch geometry
@@ -916,6 +916,15 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     CK(in(h->Rhat_u, io->Rhat_u, N * nU, &P.Rhat_u));
     CK(in(h->d0, io->d0, N * nd, &P.d0));
     CK(in(h->Dhat0, io->Dhat0, N * nd * Hp, &P.Dhat0));
+    CK(in(h->Ys, io->Yhat_s, N * nY, &P.Ys));
+    if (io->kkt) {
+        if (dev || mapped) {
+            P.kkt_out = io->kkt;
+        } else {
+            CK(h->kkt.alloc(N * 3));
+            P.kkt_out = h->kkt.p;
+        }
+    }
     if (dev) {
         P.lastu0 = io->lastu0;
         P.Z = io->Ztilde;
@@ -1024,6 +1033,7 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
             if (io->J) CK(cudaMemcpyAsync(io->J, h->Jv.p, N * 8, cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(io->status, h->status.p, N * 4, cudaMemcpyDeviceToHost, s));
             if (io->iters) CK(cudaMemcpyAsync(io->iters, h->iters.p, N * 4, cudaMemcpyDeviceToHost, s));
+            if (io->kkt) CK(cudaMemcpyAsync(io->kkt, h->kkt.p, N * 3 * 8, cudaMemcpyDeviceToHost, s));
         }
     }
     if (io->sync || !dev) CK(cudaStreamSynchronize(s));

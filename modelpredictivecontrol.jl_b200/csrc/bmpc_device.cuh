@@ -89,6 +89,8 @@ struct StepParams {
     int nw;
     long sW;
     const double* Wc;
+    const double* Ys;     // [N x nY] stochastic output predictions Ŷs added to F (InternalModel, predictstoch! execute.jl:321-327) or nullptr
+    double* kkt_out;      // [N x 3] relative KKT residuals of the returned iterate: primal, dual, complementarity (or nullptr)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -906,7 +908,8 @@ __device__ __forceinline__ double max_step(const Team<TEAM>& T, const Ctx& c, in
 // lam0: multipliers of the previous period (warm start; c.x / c.yb / c.s then describe the previous solution), or nullptr
 template <int TEAM>
 __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, const StepParams& P, double Hee, double qs,
-                                          double hscale, int& status, int& iters, const double* lam0 = nullptr) {
+                                          double hscale, int& status, int& iters, const double* lam0 = nullptr,
+                                          double* kkt3 = nullptr) {
     const RowTables& rt = P.rt;
     const int n = P.n, m = rt.m, nDb = rt.nDb;
     const double mu0 = fmax(1e-2 * qs * hscale / (double)m, 1e-8);
@@ -954,6 +957,11 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         // merit = worst of the three scaled KKT residuals (1.0 = exactly at tolerance)
         const double merit = fmax(fmax(e_d / (P.tol * qd), e_p / (P.tol * hscale)),
                                   mu * (double)m / (P.tol_mu * qs * hscale));
+        if (kkt3 && merit <= best_merit) {  // residuals of the best iterate so far (the one a non-converged exit returns)
+            kkt3[0] = e_p / hscale;
+            kkt3[1] = e_d / qd;
+            kkt3[2] = mu * (double)m / (qs * hscale);
+        }
         if (merit <= 1.0) {
             status = ST_OPTIMAL;
             break;
@@ -1192,7 +1200,7 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
         const double* gM = P.Mw + (long)inst * P.sM;
         double racc = 0.0;
         for (int t = T.tid; t < nY; t += TEAM) {
-            double f = gB[t];
+            double f = gB[t] + (P.Ys ? P.Ys[(long)inst * nY + t] : 0.0);
             for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sm_xhat[k], f);
             for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], sm_lastu[k], f);
             if (nd > 0) {
@@ -1354,15 +1362,26 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
                 for (int r = T.tid; r < m; r += TEAM) c.s[r] = c.h[r] - row_gx(c, r, c.x, c.yb);
                 T.sync();
             }
-            ipm_solve(T, c, P, Hee, qs, hscale, status, iters, lam0);
+            double kkt3[3] = {0.0, 0.0, 0.0};
+            ipm_solve(T, c, P, Hee, qs, hscale, status, iters, lam0, kkt3);
+            if (P.kkt_out && T.tid == 0) {
+                P.kkt_out[(long)inst * 3] = kkt3[0];
+                P.kkt_out[(long)inst * 3 + 1] = kkt3[1];
+                P.kkt_out[(long)inst * 3 + 2] = kkt3[2];
+            }
             if (P.use_ws) {
                 const bool keep = status == ST_OPTIMAL && iters > 0;
                 if (keep)
                     for (int r = T.tid; r < m; r += TEAM) P.lam_ws[(long)inst * P.ws_stride + r] = c.lam[r];
                 if (T.tid == 0) P.ws_flag[inst] = keep ? 1 : 0;
             }
-        } else if (P.use_ws && T.tid == 0) {
-            P.ws_flag[inst] = 0;
+        } else {
+            if (P.use_ws && T.tid == 0) P.ws_flag[inst] = 0;
+            if (P.kkt_out && T.tid == 0) {  // unconstrained minimiser feasible: an exact solve
+                P.kkt_out[(long)inst * 3] = 0.0;
+                P.kkt_out[(long)inst * 3 + 1] = 0.0;
+                P.kkt_out[(long)inst * 3 + 2] = 0.0;
+            }
         }
         // ---- stage 4: getinput! ----
         double* gZ = P.Z + (long)inst * n;

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             for (int k = 0; k < KC; ++k) kpre[h][k] = (okt && k < nx) ? gK[tc + (long)nY * k] : 0.0;
 #pragma unroll
             for (int k = 0; k < VC; ++k) vpre[h][k] = (okt && k < nu) ? gV[tc + (long)nY * k] : 0.0;
-            bpre[h] = okt ? gB[tc] : 0.0;
+            bpre[h] = okt ? gB[tc] + (P.Ys ? P.Ys[(long)inst * nY + tc] : 0.0) : 0.0;
             mpre[h] = okt ? gM[tc] : 0.0;
             rypre[h] = okt ? (P.Rhat_y ? P.Rhat_y[(long)inst * nY + tc] : P.ry[(long)inst * ny + (tc % ny)]) : 0.0;
             yoppre[h] = okt ? gyop[tc % ny] : 0.0;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
         }
 #pragma unroll 1
         for (int t = lane + 64; t < nY; t += 32) {
-            double f = gB[t];
+            double f = gB[t] + (P.Ys ? P.Ys[(long)inst * nY + t] : 0.0);
 #pragma unroll 2
             for (int k = 0; k < nx; ++k) f = fma(gK[t + (long)nY * k], sxh[k], f);
 #pragma unroll 1
@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
         const bool feasible = (m == 0) || (lv_ok && smin >= -1e-12 * hscale);
         PCLK(14);
         int status = ST_OPTIMAL, iters = 0;
+        double kk0 = 0.0, kk1 = 0.0, kk2 = 0.0;  // relative KKT residuals of the returned iterate (io.kkt)
         if (__any_sync(WFULL, !feasible)) {
             // ---- stage 3: Mehrotra predictor-corrector ----
             const double mu0 = fmax(1e-2 * qs * hscale * minv, 1e-8);
@@ -623,6 +624,9 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 }
                 // (the scales of the primal residual and of the gap are loop invariants: multiplications, one reciprocal)
                 const double merit = fmax(fmax(e_d * __drcp_rn(P.tol * qd), e_p * inv_tol_p), musum * inv_tol_mu);
+                kk0 = e_p * inv_tol_p * P.tol;
+                kk1 = e_d * __drcp_rn(qd);
+                kk2 = musum * inv_tol_mu * P.tol_mu;
                 if (__any_sync(WFULL, merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) ||
                                               (it == P.max_iter && merit <= 1e3))) {
                     status = ST_OPTIMAL;
@@ -920,6 +924,11 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             if (lane == 0) P.ws_flag[inst] = keep ? 1 : 0;
         }
         if (lane == 0) {
+            if (P.kkt_out) {
+                P.kkt_out[(long)inst * 3] = kk0;
+                P.kkt_out[(long)inst * 3 + 1] = kk1;
+                P.kkt_out[(long)inst * 3 + 2] = kk2;
+            }
             P.r_out[inst] = rconst;
             if (P.J_out) P.J_out[inst] = jacc;
             P.status[inst] = status;

@@ -277,3 +277,79 @@ class ManualEstimator(SteadyKalmanFilter):
 
     def updatestate(self, u, ym, d=None):
         return self.xhat0 + self.xophat
+
+
+class InternalModel(SteadyKalmanFilter):
+    """Batched ``InternalModel`` estimator (reference src/estimator/internal_model.jl): no state augmentation
+    (Â = A, ...), a stochastic model of the measured outputs (default one integrator per measured output,
+    ``stoch_ym = (As, Bs, Cs, Ds)`` shared by the batch otherwise) updated by  x̂s <- Âs x̂s + B̂s ŷs  with
+    ŷs^m = ym - ŷd^m (correct_estimate! :262-277, update_estimate! :293-311).  The controller adds the stochastic
+    predictions Ŷs = Ks x̂s + Ps ŷs (init_stochpred, construct.jl:1254-1267) to F through ``io.Yhat_s``."""
+
+    def __init__(self, model, i_ym=None, stoch_ym=None):
+        if np.any(np.abs(np.linalg.eigvals(model.A)) >= 1):
+            raise ValueError("InternalModel does not support integrating or unstable model")
+        self.model = model
+        N, ny = model.N, model.ny
+        self.i_ym = list(range(ny)) if i_ym is None else list(i_ym)
+        nym = len(self.i_ym)
+        if stoch_ym is None:
+            Asm = Bsm = Csm = Dsm = np.eye(nym)
+        else:
+            Asm, Bsm, Csm, Dsm = [np.atleast_2d(np.asarray(M, float)) for M in stoch_ym]
+        if not np.any(Dsm):
+            raise ValueError("Stochastic model requires a nonzero direct transmission matrix D")
+        nxs = Asm.shape[0]
+        Bs, Cs, Ds = np.zeros((nxs, ny)), np.zeros((ny, nxs)), np.eye(ny)
+        Bs[:, self.i_ym] = Bsm
+        Cs[self.i_ym] = Csm
+        Ds[np.ix_(self.i_ym, self.i_ym)] = Dsm
+        self.As, self.Cs = Asm, Cs
+        self.Bs_hat = Bs @ np.linalg.inv(Ds)
+        self.As_hat = Asm - self.Bs_hat @ Cs
+        self.nxs, self.nxhat, self.nsu = nxs, model.nx, 0
+        self.nint_u, self.nint_ym = 0, [0] * nym
+        self._set_matrices()
+        self.xhat0 = np.zeros((N, model.nx))
+        self.xs = np.zeros((N, nxs))
+        self.ys = np.zeros((N, ny))
+
+    def _set_matrices(self):
+        m = self.model
+        self.Ahat, self.Buhat, self.Chat, self.Bdhat, self.Ddhat = m.A, m.Bu, m.C, m.Bd, m.Dd
+        self.xophat, self.fophat = m.xop.copy(), m.fop.copy()
+        self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]
+
+    def setmodel(self, model):
+        xhat = self.xhat0 + self.xophat
+        self.model = model
+        self._set_matrices()
+        self.xhat0 = xhat - self.xophat
+        return self
+
+    def stochpred(self, Hp):
+        """init_stochpred: (Ks, Ps) with Ŷs = Ks x̂s + Ps ŷs (shared by the batch)."""
+        ny = self.model.ny
+        Ks, Ps = np.zeros((ny * Hp, self.nxs)), np.zeros((ny * Hp, ny))
+        Ap = np.eye(self.nxs)
+        for i in range(1, Hp + 1):
+            Ms = self.Cs @ Ap @ self.Bs_hat
+            Ap = Ap @ self.As
+            Ks[ny * (i - 1):ny * i] = self.Cs @ Ap - Ms @ self.Cs
+            Ps[ny * (i - 1):ny * i] = Ms
+        return Ks, Ps
+
+    def preparestate(self, ym, d=None):
+        m, N = self.model, self.model.N
+        y0m = _b(ym, N, (len(self.i_ym),)) - m.yop[:, self.i_ym]
+        d0 = self._d0(d)
+        yd = np.einsum("nij,nj->ni", self.Chat, self.xhat0) + np.einsum("nij,nj->ni", self.Ddhat, d0)
+        ys = np.zeros((N, m.ny))
+        ys[:, self.i_ym] = np.where(np.isfinite(y0m), y0m - yd[:, self.i_ym], 0.0)
+        self.ys = ys
+        return self.xhat0 + self.xophat
+
+    def updatestate(self, u, ym, d=None):
+        out = SteadyKalmanFilter.updatestate(self, u, ym, d)
+        self.xs = self.xs @ self.As_hat.T + self.ys @ self.Bs_hat.T
+        return out

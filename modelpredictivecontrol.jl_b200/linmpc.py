@@ -45,6 +45,8 @@ class LinMPC:
         b = self.batch
         self._W = (Wy, Wu, Wd, Wr)
         self._push_model(first=True)
+        # InternalModel: stochastic output predictions Ŷs = Ks x̂s + Ps ŷs enter F every period (predictstoch!)
+        self._stoch = estim.stochpred(Hp) if hasattr(estim, "stochpred") else None
         self.Uop, self.Yop = np.tile(model.uop, (1, Hp)), np.tile(model.yop, (1, Hp))
         inf = np.inf
         self.con = dict(U0min=np.full((N, nu * Hp), -inf), U0max=np.full((N, nu * Hp), inf),
@@ -240,7 +242,11 @@ class LinMPC:
             if self._y0m is None:
                 raise RuntimeError("call preparestate(ym) before moveinput with fused_estimator")
             return self.batch.step(None, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0, y0m=self._y0m).copy()
-        return self.batch.step(self.estim.xhat0, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0).copy()
+        Ys = None
+        if self._stoch is not None:
+            Ks, Ps = self._stoch
+            Ys = self.estim.xs @ Ks.T + self.estim.ys @ Ps.T
+        return self.batch.step(self.estim.xhat0, ry=ry, Rhat_y=Rhat_y, Rhat_u=Rhat_u, d0=d0, Dhat0=Dh0, Yhat_s=Ys).copy()
 
     def getinfo(self):
         i = self.batch.getinfo()

@@ -277,6 +277,96 @@ class SteadyKalmanFilter(StateEstimator):
                       + self.fophat - self.xophat)
 
 
+class InternalModel(StateEstimator):
+    """``InternalModel`` estimator (src/estimator/internal_model.jl:1-381) for a LinModel: the plant model gives the
+    deterministic state x̂d (no augmentation: Â = A ..., matrices_internalmodel :158-162), a stochastic model
+    ``stoch_ym = (As, Bs, Cs, Ds)`` of the measured outputs (default: one integrator per measured output,
+    ss(I, I, I, I), :96) gives x̂s through  x̂s(k+1) = Âs x̂s + B̂s ŷs,  Âs = As - Bs Ds^-1 Cs,  B̂s = Bs Ds^-1
+    (init_internalmodel :222-226);  ŷs^m = ym - ŷd^m,  ŷs^u = 0 (correct_estimate! :262-277)."""
+
+    def __init__(self, model, i_ym=None, stoch_ym=None):
+        if np.any(np.abs(np.linalg.eigvals(model.A)) >= 1):
+            raise ValueError("InternalModel does not support integrating or unstable model")
+        self.model = model
+        self.i_ym = list(range(model.ny)) if i_ym is None else list(i_ym)
+        nym, ny = len(self.i_ym), model.ny
+        if stoch_ym is None:
+            Asm = Bsm = Csm = Dsm = np.eye(nym)
+        else:
+            Asm, Bsm, Csm, Dsm = [np.atleast_2d(np.asarray(M, float)) for M in stoch_ym]
+        if Csm.shape[0] != nym or Dsm.shape[0] != nym:
+            raise ValueError("Stochastic model output quantity is different from measured output quantity")
+        if not np.any(Dsm):
+            raise ValueError("Stochastic model requires a nonzero direct transmission matrix D")
+        # stoch_ym2y (src/estimator/construct.jl): rows of the unmeasured outputs are zero
+        nxs = Asm.shape[0]
+        self.As, self.Bs = Asm, np.zeros((nxs, ny))
+        self.Cs, self.Ds = np.zeros((ny, nxs)), np.eye(ny)
+        self.Bs[:, self.i_ym] = Bsm
+        self.Cs[self.i_ym] = Csm
+        self.Ds[np.ix_(self.i_ym, self.i_ym)] = Dsm
+        self.nxs, self.nxhat = nxs, model.nx
+        self.nint_u, self.nint_ym = np.zeros(model.nu, int), np.zeros(nym, int)
+        self._set_matrices()
+        self.Bs_hat = self.Bs @ np.linalg.inv(self.Ds)                      # init_internalmodel
+        self.As_hat = self.As - self.Bs_hat @ self.Cs
+        self.xhat0 = np.zeros(model.nx)
+        self.xs = np.zeros(nxs)
+        self.ys = np.zeros(ny)
+
+    def _set_matrices(self):
+        m = self.model
+        self.Ahat, self.Buhat, self.Chat, self.Bdhat, self.Ddhat = m.A, m.Bu, m.C, m.Bd, m.Dd
+        self.xophat, self.fophat = m.xop.copy(), m.fop.copy()
+        self.Cmhat, self.Ddmhat = self.Chat[self.i_ym], self.Ddhat[self.i_ym]
+
+    def _setmodel_estimator(self, Qhat, Rhat):
+        xhat = self.xhat0 + self.xophat
+        self._set_matrices()
+        self.xhat0 = xhat - self.xophat
+
+    def evaloutput(self, d=()):
+        """internal_model.jl:357-368: ŷ = Ĉ x̂d + D̂d d0 + yop + ŷs."""
+        return StateEstimator.evaloutput(self, d) + self.ys
+
+    def correct_estimate(self, y0m, d0):
+        yd = self.Chat @ self.xhat0 + self.Ddhat @ d0
+        ys = np.zeros(self.model.ny)
+        for k, i in enumerate(self.i_ym):
+            ys[i] = y0m[k] - yd[i] if np.isfinite(y0m[k]) else 0.0
+        self.ys = ys
+
+    def update_estimate(self, u0, y0m, d0):
+        self.xhat0 = self.Ahat @ self.xhat0 + self.Buhat @ u0 + self.Bdhat @ d0 + self.fophat - self.xophat
+        self.xs = self.As_hat @ self.xs + self.Bs_hat @ self.ys
+
+    def initstate(self, u, ym, d=()):
+        """init_estimate! (internal_model.jl:325-343): both parts at steady state."""
+        m = self.model
+        u0, d0 = np.asarray(u, float) - m.uop, np.asarray(d, float).reshape(m.nd) - m.dop
+        y0m = np.asarray(ym, float) - m.yop[self.i_ym]
+        self.xhat0 = np.linalg.solve(np.eye(m.nx) - m.A, m.Bu @ u0 + m.Bd @ d0 + self.fophat - self.xophat)
+        self.correct_estimate(y0m, d0)
+        self.xs = np.linalg.solve(np.eye(self.nxs) - self.As_hat, self.Bs_hat @ self.ys)
+        return self.xhat0 + self.xophat
+
+
+def init_stochpred(estim, Hp):
+    """src/controller/construct.jl:1254-1272: Ŷs = Ks x̂s + Ps ŷs for an InternalModel, empty otherwise."""
+    ny = estim.model.ny
+    if not isinstance(estim, InternalModel):
+        return np.zeros((0, estim.nxs)), np.zeros((0, ny))
+    As, Bs, Cs = estim.As, estim.Bs_hat, estim.Cs
+    Ks, Ps = np.zeros((ny * Hp, estim.nxs)), np.zeros((ny * Hp, ny))
+    Ap = np.eye(estim.nxs)
+    for i in range(1, Hp + 1):
+        Ms = Cs @ Ap @ Bs                      # Cs As^(i-1) B̂s
+        Ap = Ap @ As
+        Ks[ny * (i - 1):ny * i] = Cs @ Ap - Ms @ Cs
+        Ps[ny * (i - 1):ny * i] = Ms
+    return Ks, Ps
+
+
 class ManualEstimator(StateEstimator):
     """src/estimator/manual.jl:60-64,150-154: the host supplies xhat through setstate!; prepare /
     update are no-ops.  This is exactly the contract of the batched C-ABI step."""
@@ -608,7 +698,10 @@ class LinMPC:
             self.Dhat0 = np.asarray(Dhat, float) - self.Dop
         self.Rhat_y, self.Rhat_u = np.asarray(Rhat_y, float), np.asarray(Rhat_u, float)
         self.ry = np.asarray(ry, float).reshape(-1)
-        F = self.B + self.K @ self.estim.xhat0 + self.V @ self.lastu0
+        # F starts from the stochastic predictions Ŷs of an InternalModel (predictstoch!, execute.jl:321-327), else from 0
+        Ks, Ps = init_stochpred(self.estim, self.Hp)
+        F = Ks @ self.estim.xs + Ps @ self.estim.ys if Ks.shape[0] else 0.0
+        F = F + self.B + self.K @ self.estim.xhat0 + self.V @ self.lastu0
         if m.nd > 0:
             F = F + self.G @ self.d0 + self.J @ self.Dhat0
         self.F = F

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported():
 def test_struct_layouts_match_header():
     # bmpc_dims: 12 int32 + 1 double; bmpc_step_io: 12 pointers + 2 int32; bmpc_info: 6 pointers
     assert C.sizeof(_lib.Dims) == 12 * 4 + 8
-    assert C.sizeof(_lib.StepIO) == 12 * 8 + 16 + 8  # 12 pointers + device_ptrs, sync, resident, host_mapped + y0m
+    assert C.sizeof(_lib.StepIO) == 12 * 8 + 16 + 3 * 8  # 12 pointers + device_ptrs, sync, resident, host_mapped + y0m, Yhat_s, kkt
     assert C.sizeof(_lib.Info) == 6 * 8
     assert C.sizeof(_lib.Softness) == 8 * 8
     assert C.sizeof(_lib.MheDims) == 12 * 4 + 8

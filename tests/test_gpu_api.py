@@ -402,3 +402,51 @@ def test_batched_setmodel_successive_linearisation_vs_oracle():
         g.updatestate(ug, y)
     assert nact > 10
     print("batched setmodel: worst", worst, "active solves", nact)
+
+
+def test_internalmodel_stochastic_predictions_and_kkt_output():
+    """InternalModel estimator: the stochastic predictions Ŷs = Ks x̂s + Ps ŷs enter F through io.Yhat_s
+    (predictstoch!, src/controller/execute.jl:321-327).  The reference's known answer (test/3:159-176: constant output
+    disturbance, u -> 2, ym -> 15) through the CUDA path, and a constrained batch against the oracle; io.kkt reports the
+    relative KKT residuals of every returned iterate."""
+    import mpc_b200
+    from mpc_b200 import workloads
+    from oracle.linmpc import InternalModel as OIM, LinModel as OLinModel, LinMPC as OLinMPC, zoh_first_order
+    A, B, C = zoh_first_order(5, 2, 3.0)
+    gm = mpc_b200.LinModel(A, B, C, Ts=3.0, yop=[10])
+    g = mpc_b200.LinMPC(mpc_b200.InternalModel(gm))
+    plant = OLinModel(A, B, C, Ts=3.0, yop=[10])
+    for i in range(25):
+        ym = plant.evaloutput() - 5
+        g.preparestate([ym])
+        u = g.moveinput([[15]])
+        g.updatestate(u, [ym])
+        plant.updatestate(u[0])
+    assert abs(u[0, 0] - 2) < 1e-2 and abs(ym[0] - 15) < 1e-2
+    # constrained batch vs the oracle
+    N, steps = 6, 14
+    model, rng = workloads.random_plants(N, 3, 2, 2, seed=31)
+    kw = dict(Hp=12, Hc=3, Cwt=1e5)
+    cons = dict(umin=[-1, -1], umax=[1, 1], ymax=[0.6, 0.6])
+    g = mpc_b200.LinMPC(mpc_b200.InternalModel(model), **kw).setconstraint(**cons)
+    os_ = [OLinMPC(OIM(OLinModel(model.A[i], model.Bu[i], model.C[i])), **kw).setconstraint(**cons) for i in range(N)]
+    plants = [OLinModel(model.A[i], model.Bu[i], model.C[i]) for i in range(N)]
+    ry = workloads.setpoints(rng, N, 2, steps, period=7)
+    dist = rng.uniform(-0.3, 0.3, (N, 2))   # constant output disturbances
+    nact = 0
+    for k in range(steps):
+        y = np.stack([p.evaloutput() for p in plants]) + dist
+        g.preparestate(y)
+        ug = g.moveinput(ry[k])
+        b = g.batch
+        assert (b.status == 0).all()
+        assert (b.kkt >= 0).all() and (b.kkt[b.iters == 0] == 0).all() and b.kkt.max() < 1e-7, b.kkt.max()
+        nact += int((b.iters > 0).sum())
+        for i, o in enumerate(os_):
+            o.preparestate(y[i])
+            uo = o.moveinput(ry[k, i])
+            assert np.abs(g.Ztilde[i] - o.Ztilde).max() < 5e-6 * (1 + np.abs(o.Ztilde).max()), (k, i)
+            o.updatestate(uo, y[i])
+            plants[i].updatestate(uo)
+        g.updatestate(ug, y)
+    assert nact > 10

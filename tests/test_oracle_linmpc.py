@@ -321,3 +321,40 @@ def test_setmodel_known_answers():
     assert np.allclose(mpc.M_Hp, np.diag(np.arange(1.0, 1001))) and np.allclose(mpc.Ntilde_Hc, np.diag([0.1, 1e6]))
     with pytest.raises(RuntimeError):
         LinMPC(mk(5, 10, 1)).setmodel(mk(5, 20, 11))  # SteadyKalmanFilter: kalman.jl:229-234
+
+
+def test_internalmodel_step_disturbance_rejection():
+    """test/3_test_predictive_control.jl:159-176 ("LinMPC step disturbance rejection", InternalModel): with a constant
+    output disturbance of -5 the loop settles at ym = r = 15 with u = 2 (plant gain 5, yop = 10: 10 + 5*2 - 5 = 15)."""
+    from oracle.linmpc import InternalModel
+    mk = lambda: LinModel(*zoh_first_order(5, 2, 3.0), Ts=3.0, yop=[10])
+    plant = mk()
+    mpc = LinMPC(InternalModel(mk()))
+    u = ym = None
+    for i in range(25):
+        ym = plant.evaloutput() - 5
+        mpc.preparestate(ym)
+        u = mpc.moveinput([15])
+        mpc.updatestate(u, ym)
+        plant.updatestate(u)
+    assert u == pytest.approx([2], abs=1e-2) and ym == pytest.approx([15], abs=1e-2)
+
+
+def test_internalmodel_estimator_methods():
+    """test/2_test_state_estim.jl:475-513 (IM estimator methods): unit offsets land in x̂s, ŷ reproduces the measurement."""
+    from oracle.linmpc import InternalModel
+    rng = np.random.default_rng(2)
+    A = np.diag([0.5, 0.7])
+    m = LinModel(A, np.eye(2), np.eye(2), uop=[10, 50], yop=[50, 30])
+    im = InternalModel(m)
+    u, y = [10, 50], np.array([51.0, 31.0])
+    im.preparestate(y)
+    assert im.updatestate(u, y) == pytest.approx(np.zeros(2))
+    im.preparestate(y)
+    assert im.updatestate(u, y) == pytest.approx(np.zeros(2))
+    assert im.xs == pytest.approx(np.ones(2))
+    im.preparestate(y)
+    assert im.evaloutput() == pytest.approx([51, 31])
+    assert im.initstate([10, 50], [50, 30]) == pytest.approx(np.zeros(2)) and im.xs == pytest.approx(np.zeros(2))
+    with pytest.raises(ValueError):
+        InternalModel(LinModel(np.eye(1), np.ones((1, 1)), np.ones((1, 1))))  # integrating model
