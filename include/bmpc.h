@@ -156,6 +156,10 @@ int bmpc_set_predmat(bmpc_handle *h, const double *E, const double *K, const dou
 /* Weights needed per step for q̃ and r (ControllerWeights, construct.jl:45-93).
  * M: nYhat (diag) or nYhat x nYhat when M_dense = 1; L_diag: nU or NULL (= 0). */
 int bmpc_set_weights(bmpc_handle *h, const double *M, int32_t M_dense, const double *L_diag);
+/* The same with a DENSE input-setpoint weight: L is nU x nU (column-major, lower triangle authoritative, Hermitian as
+ * the reference stores it) when L_dense = 1, else the diagonal (nU).  A dense Ñ_Hc only enters H̃ (route B).  Route B
+ * only: on route A the weights are arguments of bmpc_set_model (BMPC_ERR_STATE). */
+int bmpc_set_weights_dense(bmpc_handle *h, const double *M, int32_t M_dense, const double *L, int32_t L_dense);
 
 /* Operating points uop (nu), yop (ny) per instance (Uop/Yop = repeat, linmpc.jl:90).
  * NULL = zeros. */
@@ -279,7 +283,7 @@ int bmhe_destroy(bmhe_handle *h);
  * (init_predmat_mhe, src/estimator/mhe/transcription.jl:151-260), column-major, NM copies. */
 int bmhe_set_predmat(bmhe_handle *h, const double *E, const double *G, const double *J, const double *B,
                      const double *EX, const double *GX, const double *JX, const double *BX);
-/* estim.Â, Ĉm and the covariances P̂_0, Q̂, R̂ (R̂ diagonal) of cov (estimator/construct.jl:60-119); resets. */
+/* estim.Â, Ĉm and the covariances P̂_0, Q̂, R̂ of cov (estimator/construct.jl:60-119; R̂ diagonal or dense SPD); resets. */
 int bmhe_set_cov(bmhe_handle *h, const double *Ahat, const double *Cmhat, const double *P0, const double *Qhat,
                  const double *Rhat, double Cwt);
 /* setconstraint!(mhe; x̂min, x̂max, ŵmin, ŵmax, v̂min, v̂max) in deviation form, N x len (NULL = none);

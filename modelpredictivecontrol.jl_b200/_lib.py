@@ -61,7 +61,7 @@ SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bm
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_set_stream", "bmhe_launch_count",
            "bmpc_set_gather_flags", "bmpc_gather_epoch", "bmpc_gather_wait", "bmpc_gather_timed_out",
-           "bmpc_set_custom", "bmpc_set_custom_bounds", "bmpc_get_states"]
+           "bmpc_set_custom", "bmpc_set_custom_bounds", "bmpc_get_states", "bmpc_set_weights_dense"]
 
 
 def lib():
@@ -82,6 +82,7 @@ def lib():
     L.bmpc_set_model.argtypes = [C.c_void_p] + [c_double_p] * 9 + [C.c_double]
     L.bmpc_set_predmat.argtypes = [C.c_void_p] + [c_double_p] * 13
     L.bmpc_set_weights.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p]
+    L.bmpc_set_weights_dense.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p, C.c_int32]
     L.bmpc_set_oppoints.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.bmpc_set_constraints.argtypes = [C.c_void_p] + [c_double_p] * 8 + [C.POINTER(Softness)]
     L.bmpc_step.argtypes = [C.c_void_p, C.POINTER(StepIO)]

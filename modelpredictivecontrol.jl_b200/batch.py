@@ -108,8 +108,14 @@ class BatchLinMPC:
             Mc = self._mat(M, self.nY, self.nY, "M_Hp")
         else:
             Mc = _vec(M, self.NM, self.nY, "M_diag")
-        L = None if L_diag is None else _vec(L_diag, self.NM, self.nU, "L_diag")
-        check(_lib.lib().bmpc_set_weights(self._h, dptr(Mc), int(dense), dptr(L)))
+        Ld = False
+        if L_diag is None:
+            L = None
+        else:
+            La = np.asarray(L_diag, dtype=np.float64)
+            Ld = La.ndim >= 2 and La.shape[-1] == self.nU and La.shape[-2] == self.nU and self.nU > 1
+            L = self._mat(La, self.nU, self.nU, "L_Hp") if Ld else _vec(La, self.NM, self.nU, "L_diag")
+        check(_lib.lib().bmpc_set_weights_dense(self._h, dptr(Mc), int(dense), dptr(L), int(Ld)))
 
     def set_oppoints(self, uop=None, yop=None):
         if uop is not None:

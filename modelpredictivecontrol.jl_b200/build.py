@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
                     sys.stderr.write(r.stderr)
     objs = [_obj(u) for u in UNITS]
     if todo or _stale(OUT, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs, capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc link failed for libbmpc.so")

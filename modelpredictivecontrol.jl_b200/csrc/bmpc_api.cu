@@ -46,7 +46,7 @@ struct bmpc_handle {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     int num_sms = 148;
     bool have_predmat = false, have_weights = false, have_constraints = false, stepped = false;
-    bool has_terminal_mats = false, M_dense = false, has_L = false;
+    bool has_terminal_mats = false, M_dense = false, has_L = false, L_dense = false, route_a = false;
     // model-dependent constants
     DevBuf<double> E, ex, Ht;                         // reference coordinates (kept for getinfo)
     DevBuf<double> Ev, exv, Hv, Lv, Hee, K, V, B, G, J, kx, vx, bx, gx, jx, Mw, Lw, uop, yop;
@@ -164,6 +164,8 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.bar = take(2);
     L.ev = take(h->d.ny);
     L.Fw = take(h->nFw);
+    L.cu = take(h->L_dense ? h->nU : 0);
+    L.tU = take(h->L_dense ? h->nU : 0);
     L.total = o;
     (void)nz;
 }
@@ -360,7 +362,7 @@ int configure_launch(bmpc_handle* h) {
     h->warp = nullptr;
     const int forced = h->d.team ? h->d.team : (getenv("BMPC_TEAM") ? atoi(getenv("BMPC_TEAM")) : 0);
     const int m_rows = h->rt.nS + h->rt.nDr;
-    if (forced == 0 && h->n <= 16 && m_rows <= 128 && !h->M_dense && h->have_predmat &&
+    if (forced == 0 && h->n <= 16 && m_rows <= 128 && !h->M_dense && !h->L_dense && h->have_predmat &&
         !(getenv("BMPC_NO_WARP") && atoi(getenv("BMPC_NO_WARP")))) {
         const bmpc::WarpEntry* best = nullptr;
         for (const bmpc::WarpEntry& E : warp_registry()) {
@@ -538,6 +540,7 @@ int bmpc_set_predmat(bmpc_handle* h, const double* E, const double* K, const dou
     CK(cudaSetDevice(d.device));
     cudaStream_t s = h->stream;
     const size_t NM = h->NM, nY = h->nY, nz = h->nz, n = h->n, nx = d.nxhat, nu = d.nu, nd = d.nd, Hp = d.Hp;
+    h->route_a = false;
     CK(up(h->E, E, NM * nY * nz, s));
     CK(up(h->K, K, NM * nY * nx, s));
     CK(up(h->V, V, NM * nY * nu, s));
@@ -598,18 +601,27 @@ int bmpc_set_predmat(bmpc_handle* h, const double* E, const double* K, const dou
 }
 
 int bmpc_set_weights(bmpc_handle* h, const double* M, int32_t M_dense, const double* L_diag) {
+    return bmpc_set_weights_dense(h, M, M_dense, L_diag, 0);
+}
+
+int bmpc_set_weights_dense(bmpc_handle* h, const double* M, int32_t M_dense, const double* L, int32_t L_dense) {
     if (!h || !M) return fail(BMPC_ERR_ARG, "null argument");
+    if (h->route_a)
+        return fail(BMPC_ERR_STATE, "the weights of a route-A handle are arguments of bmpc_set_model (its Hessian was built from them)");
     CK(cudaSetDevice(h->d.device));
-    const size_t NM = h->NM, nY = h->nY;
+    const size_t NM = h->NM, nY = h->nY, nU = h->nU;
     CK(up(h->Mw, M, NM * (M_dense ? nY * nY : nY), h->stream));
     h->M_dense = M_dense != 0;
     h->has_L = false;
-    if (L_diag) {
+    h->L_dense = false;
+    if (L) {
+        const size_t cnt = NM * (L_dense ? nU * nU : nU);
         bool any = false;
-        for (size_t i = 0; i < NM * (size_t)h->nU && !any; ++i) any = L_diag[i] != 0.0;
+        for (size_t i = 0; i < cnt && !any; ++i) any = L[i] != 0.0;
         if (any) {  // iszero_L_Hp short-circuit, construct.jl:86 / execute.jl:268
-            CK(up(h->Lw, L_diag, NM * h->nU, h->stream));
+            CK(up(h->Lw, L, cnt, h->stream));
             h->has_L = true;
+            h->L_dense = L_dense != 0;
         }
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -953,11 +965,11 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.sm = h->sm;
     P.pd_in_smem = h->pd_in_smem; P.pd_is_ev = h->pd_is_ev; P.has_terminal = h->has_terminal_rows;
     P.hv_in_smem = h->hv_in_smem ? 1 : 0;
-    P.M_dense = h->M_dense; P.has_L = h->has_L;
+    P.M_dense = h->M_dense; P.has_L = h->has_L; P.L_dense = h->L_dense ? 1 : 0;
     const long sh = d.shared_model ? 0 : 1;
     P.sEv = sh * h->nEv2; P.sH = sh * h->nHp2; P.sK = sh * nY * nx; P.sV = sh * nY * nu; P.sB = sh * nY;
     P.sG = sh * nY * nd; P.sJ = sh * nY * nd * Hp; P.skx = sh * nx * nx; P.svx = sh * nx * nu; P.sbx = sh * nx;
-    P.sgx = sh * nx * nd; P.sjx = sh * nx * nd * Hp; P.sM = sh * (h->M_dense ? nY * nY : nY); P.sL = sh * nU;
+    P.sgx = sh * nx * nd; P.sjx = sh * nx * nd * Hp; P.sM = sh * (h->M_dense ? nY * nY : nY); P.sL = sh * (h->L_dense ? nU * nU : nU);
     P.suop = sh * nu; P.syop = sh * ny;
     P.Ev = h->Ev.p; P.Hv = h->Hv.p; P.Lv = h->Lv.p; P.Hee = h->Hee.p; P.K = h->K.p; P.V = h->V.p; P.B = h->B.p;
     P.G = h->G.p; P.J = h->J.p; P.kx = h->kx.p; P.vx = h->vx.p; P.bx = h->bx.p; P.gx = h->gx.p; P.jx = h->jx.p;
@@ -1393,6 +1405,8 @@ int bmpc_set_model(bmpc_handle* h, const double* Ahat, const double* Buhat, cons
     h->has_terminal_mats = true;
     h->have_predmat = true;
     h->have_weights = true;
+    h->route_a = true;
+    h->L_dense = false;
     h->dirty = true;
     CK(cudaStreamSynchronize(s));
     C.release(); Dd.release(); Nd.release();

@@ -43,7 +43,7 @@ struct RowTables {
 
 struct SmemLayout {  // offsets in doubles inside a team's slice
     int Pd, Hv, Phi, x, xb, q, rd, rhs, dx, invd, F, tY, fx, yb, ybd, wd, s, lam, h, rp, t, ds, dl,
-        xhat, lastu, dd, Dh, red, bar, ev, Fw, total;
+        xhat, lastu, dd, Dh, red, bar, ev, Fw, cu, tU, total;
 };
 
 struct StepParams {
@@ -52,7 +52,7 @@ struct StepParams {
     double tol, tol_mu;
     RowTables rt;
     SmemLayout sm;
-    int pd_in_smem, pd_is_ev, has_terminal, M_dense, has_L;
+    int pd_in_smem, pd_is_ev, has_terminal, M_dense, has_L, L_dense;
     int hv_in_smem;          // 0: the packed Hessian stays in HBM/L2 (large n), read where it is used
     long sPd, sEv, sH, sK, sV, sB, sG, sJ, skx, svx, sbx, sgx, sjx, sM, sL, suop, syop;
     const double *Pd, *Ev, *Hv, *Lv, *Hee, *K, *V, *B, *G, *J, *kx, *vx, *bx, *gx, *jx, *Mw, *Lw,
@@ -1265,6 +1265,27 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
         const double* gEv = P.Ev + (long)inst * P.sEv;
         const double* gL = P.has_L ? P.Lw + (long)inst * P.sL : nullptr;
         const double* guop = P.uop + (long)inst * P.suop;
+        double* s_cu = base + P.sm.cu;
+        double* s_tU = base + P.sm.tU;
+        if (gL && P.L_dense) {
+            // dense L_Hp (ControllerWeights, construct.jl:45-93): tU = L_Hp Cu with Cu = Tu u0(k-1) + Uop - R̂u  (execute.jl:269-271)
+            for (int idx = T.tid; idx < P.nU; idx += TEAM) {
+                const int ch = idx % nu;
+                const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];
+                s_cu[idx] = sm_lastu[ch] + guop[ch] - ru;
+            }
+            T.sync();
+            for (int idx = T.tid; idx < P.nU; idx += TEAM) {
+                double a = 0.0;
+                for (int k = 0; k < P.nU; ++k) {  // column-major, lower triangle authoritative (Hermitian)
+                    const double lv = (idx >= k) ? gL[idx + (long)P.nU * k] : gL[k + (long)P.nU * idx];
+                    a = fma(lv, s_cu[k], a);
+                }
+                s_tU[idx] = a;
+                racc = fma(s_cu[idx], a, racc);
+            }
+            T.sync();
+        }
         for (int j = T.tid; j < nz; j += TEAM) {
             const double* col = (P.pd_is_ev && P.pd_in_smem) ? (sm_Pd + (long)nY * j) : (gEv + (long)nY * j);
             double a0 = 0.0, a1 = 0.0;
@@ -1277,7 +1298,10 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
             }
             if (cnt < nY) a0 = fma(col[k], c.tY[k], a0);
             double a = a0 + a1;
-            if (gL) {
+            if (gL && P.L_dense) {
+                const int l = j / nu, ch = j % nu;
+                for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) a += s_tU[tt * nu + ch];
+            } else if (gL) {
                 const int l = j / nu, ch = j % nu;
                 for (int tt = P.blk_start[l]; tt < P.blk_start[l + 1]; ++tt) {
                     const int idx = tt * nu + ch;
@@ -1288,7 +1312,7 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
             }
             c.q[j] = 2.0 * a;
         }
-        if (gL) {
+        if (gL && !P.L_dense) {
             for (int idx = T.tid; idx < P.nU; idx += TEAM) {
                 const int ch = idx % nu;
                 const double ru = P.Rhat_u ? P.Rhat_u[(long)inst * P.nU + idx] : guop[ch];

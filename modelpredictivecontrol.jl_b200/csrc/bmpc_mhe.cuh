@@ -26,6 +26,7 @@ struct MheParams {
     int ldE, ldEX;            // leading dimensions of E (nym*He) and EX (nx*He)
     long sE, sEX, sG, sGX, sJ, sJX, sB, sBX, sCm, sCov;   // per-instance strides (0 = shared model)
     const double *E, *EX, *G, *GX, *J, *JX, *B, *BX, *Cm, *Rm, *rinv, *Qinv;
+    const double* Rinvd;      // dense R̂^-1 (nym x nym per model) when R̂ is not diagonal, else nullptr
     double Cwt;
     double *Y0m, *U0, *D0, *X0old, *x0arr, *Parr, *invP, *Z, *xhat0, *lastu0;  // handle-owned state
     const double *xmin, *xmax, *wmin, *wmax, *vmin, *vmax;                    // per-instance bounds
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
             }
             const bool bad = !(f == f);  // NaN measurement: the row leaves the objective (:436-441)
             sF[t] = bad ? 0.0 : f;
-            wrow[t] = bad ? 0.0 : grinv[t % nym];
+            wrow[t] = bad ? 0.0 : (Q.Rinvd ? 1.0 : grinv[t % nym]);  // dense R̂: wrow is the 0/1 row mask
         }
         const double* gGX = Q.GX + (long)inst * Q.sGX;
         const double* gBX = Q.BX + (long)inst * Q.sBX;
@@ -176,17 +177,31 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
         T.sync();
         // ---- H = 2(E' Rinv E + blockdiag(invP, Qinv...)), q = 2(E' Rinv F - invP fx̄), r ----
         const int npair = nz * (nz + 1) / 2;
+        const double* gRi = Q.Rinvd ? Q.Rinvd + (long)inst * Q.sCov * nym * nym : nullptr;
         for (int p = T.tid; p < npair; p += TEAM) {
             const int i = rt.pair_i[p], j = rt.pair_j[p];
             const double* ci = gE + (long)ldE * i;
             const double* cj = gE + (long)ldE * j;
             double a0 = 0.0, a1 = 0.0;
-            int t = 0;
-            for (; t + 1 < nYk; t += 2) {
-                a0 = fma(ci[t] * wrow[t], cj[t], a0);
-                a1 = fma(ci[t + 1] * wrow[t + 1], cj[t + 1], a1);
+            if (gRi) {
+                // non-diagonal R̂: invR̂_He = blockdiag(R̂^-1) couples the outputs of one time step
+                // (src/estimator/construct.jl:60-119); rows of missing measurements are masked out on both sides
+                for (int tb = 0; tb < nYk; tb += nym)
+                    for (int o = 0; o < nym; ++o) {
+                        const double ei = ci[tb + o] * wrow[tb + o];
+                        if (ei == 0.0) continue;
+                        double w = 0.0;
+                        for (int o2 = 0; o2 < nym; ++o2) w = fma(gRi[o + nym * o2] * wrow[tb + o2], cj[tb + o2], w);
+                        a0 = fma(ei, w, a0);
+                    }
+            } else {
+                int t = 0;
+                for (; t + 1 < nYk; t += 2) {
+                    a0 = fma(ci[t] * wrow[t], cj[t], a0);
+                    a1 = fma(ci[t + 1] * wrow[t + 1], cj[t + 1], a1);
+                }
+                if (t < nYk) a0 = fma(ci[t] * wrow[t], cj[t], a0);
             }
-            if (t < nYk) a0 = fma(ci[t] * wrow[t], cj[t], a0);
             double a = a0 + a1;
             if (i < nx) {
                 a += sP[i + nx * j];  // arrival block: ex̄' invP̄ ex̄ = invP̄
@@ -196,10 +211,25 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
             c.Hv[p] = 2.0 * a;
         }
         double racc = 0.0;
+        double* sRF = c.dl;  // R̂^-1-weighted F (scratch: dl holds max(m, nY) doubles and is unused before the IPM)
+        T.sync();
+        for (int t = T.tid; t < nYk; t += TEAM) {
+            double w;
+            if (gRi) {
+                const int tb = t - t % nym, o = t % nym;
+                w = 0.0;
+                for (int o2 = 0; o2 < nym; ++o2) w = fma(gRi[o + nym * o2] * wrow[tb + o2], sF[tb + o2], w);
+                w *= wrow[t];
+            } else {
+                w = wrow[t] * sF[t];
+            }
+            sRF[t] = w;
+        }
+        T.sync();
         for (int i = T.tid; i < nz; i += TEAM) {
             const double* ci = gE + (long)ldE * i;
             double a = 0.0;
-            for (int t = 0; t < nYk; ++t) a = fma(ci[t] * wrow[t], sF[t], a);
+            for (int t = 0; t < nYk; ++t) a = fma(ci[t], sRF[t], a);
             if (i < nx) {
                 double b = 0.0;
                 for (int k = 0; k < nx; ++k) b = fma(sP[i + nx * k], x0arr[k], b);
@@ -209,7 +239,7 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
             c.q[i] = 2.0 * a;
         }
         if (neps && T.tid == 0) c.q[nz] = 0.0;
-        for (int t = T.tid; t < nYk; t += TEAM) racc = fma(wrow[t] * sF[t], sF[t], racc);
+        for (int t = T.tid; t < nYk; t += TEAM) racc = fma(sRF[t], sF[t], racc);
         const double rconst = T.sum(racc);
         const double Hee = neps ? 2.0 * Q.Cwt : 0.0;
         // ---- linconstraint!: row right-hand sides ----

@@ -25,7 +25,8 @@ struct bmhe_handle {
     bool have_predmat = false, have_cov = false, have_con = false;
     int Nk = 0, compiled_Nk = -1;
     double Cwt = 0.0;
-    DevBuf<double> E, EX, G, GX, J, JX, B, BX, A, Cm, Qc, Rm, rinv, Qinv, P0;
+    DevBuf<double> E, EX, G, GX, J, JX, B, BX, A, Cm, Qc, Rm, rinv, Qinv, P0, Rinvd;
+    bool R_dense = false;
     DevBuf<double> Y0m, U0, D0, X0old, x0arr, Parr, invP, Z, xhat0, lastu0;
     DevBuf<double> xmin, xmax, wmin, wmax, vmin, vmax;
     std::vector<double> cx_min, cx_max, cw_min, cw_max, cv_min, cv_max;
@@ -256,6 +257,7 @@ static int solve_window(bmhe_handle* h, const double* y0m, const double* d0, con
     Q.sCm = sh * nym * nx; Q.sCov = sh;
     Q.E = h->E.p; Q.EX = h->EX.p; Q.G = h->G.p; Q.GX = h->GX.p; Q.J = h->J.p; Q.JX = h->JX.p; Q.B = h->B.p; Q.BX = h->BX.p;
     Q.Cm = h->Cm.p; Q.Rm = h->Rm.p; Q.rinv = h->rinv.p; Q.Qinv = h->Qinv.p; Q.Cwt = h->Cwt;
+    Q.Rinvd = h->R_dense ? h->Rinvd.p : nullptr;
     Q.Y0m = h->Y0m.p; Q.U0 = h->U0.p; Q.D0 = h->D0.p; Q.X0old = h->X0old.p; Q.x0arr = h->x0arr.p; Q.Parr = h->Parr.p;
     Q.invP = h->invP.p; Q.Z = h->Z.p; Q.xhat0 = h->xhat0.p; Q.lastu0 = const_cast<double*>(u_window_dev);
     Q.xmin = h->xmin.p; Q.xmax = h->xmax.p; Q.wmin = h->wmin.p; Q.wmax = h->wmax.p; Q.vmin = h->vmin.p; Q.vmax = h->vmax.p;
@@ -387,33 +389,42 @@ int bmhe_set_cov(bmhe_handle* h, const double* Ahat, const double* Cmhat, const 
     CK(cudaSetDevice(h->d.device));
     const size_t NM = h->NM, nx = h->nx, nym = h->nym;
     cudaStream_t s = h->stream;
-    // inverse covariances on the host (one-off): Rhat must be diagonal (reference default, kalman.jl:166-171)
-    std::vector<double> rinv(NM * nym), Qinv(NM * nx * nx);
+    // inverse covariances on the host (one-off).  A diagonal Rhat (the reference default, kalman.jl:166-171) keeps the
+    // per-row weights; a non-diagonal one switches the kernel to the dense R̂^-1 path
+    std::vector<double> rinv(NM * nym), Qinv(NM * nx * nx), Rinvd(NM * nym * nym);
+    // inverse of a small SPD matrix by Gauss-Jordan (column-major n x n); false if a pivot is not positive
+    auto spd_inverse = [](const double* Msrc, size_t n, double* out) {
+        std::vector<double> M(Msrc, Msrc + n * n), I(n * n, 0.0);
+        for (size_t k = 0; k < n; ++k) I[k + n * k] = 1.0;
+        for (size_t k = 0; k < n; ++k) {
+            const double piv = M[k + n * k];
+            if (!(piv > 0)) return false;
+            for (size_t c = 0; c < n; ++c) { M[k + n * c] /= piv; I[k + n * c] /= piv; }
+            for (size_t r = 0; r < n; ++r) {
+                if (r == k) continue;
+                const double fct = M[r + n * k];
+                for (size_t c = 0; c < n; ++c) { M[r + n * c] -= fct * M[k + n * c]; I[r + n * c] -= fct * I[k + n * c]; }
+            }
+        }
+        std::copy(I.begin(), I.end(), out);
+        return true;
+    };
+    bool r_dense = false;
     for (size_t i = 0; i < NM; ++i) {
         const double* R = Rhat + i * nym * nym;
         for (size_t a = 0; a < nym; ++a)
             for (size_t b = 0; b < nym; ++b) {
-                if (a != b && R[a + nym * b] != 0.0) return fail(BMPC_ERR_UNSUPPORTED, "only a diagonal Rhat is supported");
+                if (a != b && R[a + nym * b] != 0.0) r_dense = true;
                 if (a == b) {
                     if (!(R[a + nym * a] > 0)) return fail(BMPC_ERR_ARG, "Rhat is not positive definite");
                     rinv[i * nym + a] = 1.0 / R[a + nym * a];
                 }
             }
-        // Qinv by Gauss-Jordan on the (small) SPD matrix
-        std::vector<double> M(Qhat + i * nx * nx, Qhat + (i + 1) * nx * nx), I(nx * nx, 0.0);
-        for (size_t k = 0; k < nx; ++k) I[k + nx * k] = 1.0;
-        for (size_t k = 0; k < nx; ++k) {
-            const double piv = M[k + nx * k];
-            if (!(piv > 0)) return fail(BMPC_ERR_ARG, "Qhat is not positive definite");
-            for (size_t c = 0; c < nx; ++c) { M[k + nx * c] /= piv; I[k + nx * c] /= piv; }
-            for (size_t r = 0; r < nx; ++r) {
-                if (r == k) continue;
-                const double fct = M[r + nx * k];
-                for (size_t c = 0; c < nx; ++c) { M[r + nx * c] -= fct * M[k + nx * c]; I[r + nx * c] -= fct * I[k + nx * c]; }
-            }
-        }
-        std::copy(I.begin(), I.end(), Qinv.begin() + i * nx * nx);
+        if (!spd_inverse(R, nym, Rinvd.data() + i * nym * nym)) return fail(BMPC_ERR_ARG, "Rhat is not positive definite");
+        if (!spd_inverse(Qhat + i * nx * nx, nx, Qinv.data() + i * nx * nx)) return fail(BMPC_ERR_ARG, "Qhat is not positive definite");
     }
+    h->R_dense = r_dense;
+    CK(h->Rinvd.upload(Rinvd, s));
     CK(h->A.upload(Ahat, NM * nx * nx, s)); CK(h->Cm.upload(Cmhat, NM * nym * nx, s));
     CK(h->P0.upload(P0, NM * nx * nx, s)); CK(h->Qc.upload(Qhat, NM * nx * nx, s)); CK(h->Rm.upload(Rhat, NM * nym * nym, s));
     CK(h->rinv.upload(rinv, s)); CK(h->Qinv.upload(Qinv, s));

@@ -59,7 +59,7 @@ def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He, direct=True):
 class MovingHorizonEstimator:
     def __init__(self, model, He, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None, nint_u=0, nint_ym=None,
                  sigmaPint_ym_0=None, sigmaQint_ym=None, Cwt=np.inf, shared_model=False, device=0, max_iter=0,
-                 tol=0.0, direct=True):
+                 tol=0.0, direct=True, P0hat=None, Qhat=None, Rhat=None):
         self.model, self.He, self.direct = model, int(He), bool(direct)
         self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
         N, nx, nxh = model.N, model.nx, self.nxhat
@@ -70,6 +70,10 @@ class MovingHorizonEstimator:
         sQ = np.concatenate([one(sigmaQ, nx, 1 / nx), one(sigmaQint_ym, nsy, 1.0)])
         sR = one(sigmaR, self.nym, 1.0)
         self.P0hat, self.Qhat, self.Rhat = np.diag(sP ** 2), np.diag(sQ ** 2), np.diag(sR ** 2)
+        # full covariance matrices, shared by the batch (the reference's second constructor, mhe/construct.jl:632-660)
+        if P0hat is not None: self.P0hat = np.atleast_2d(np.asarray(P0hat, float))
+        if Qhat is not None: self.Qhat = np.atleast_2d(np.asarray(Qhat, float))
+        if Rhat is not None: self.Rhat = np.atleast_2d(np.asarray(Rhat, float))
         self.Cwt = float(Cwt)
         self.neps = 0 if np.isinf(self.Cwt) else 1
         self.Cmhat, self.Ddmhat = self.Chat[:, self.i_ym], self.Ddhat[:, self.i_ym]

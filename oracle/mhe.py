@@ -86,7 +86,7 @@ class MovingHorizonEstimator(StateEstimator):
 
     def __init__(self, model, He, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None, nint_u=0, nint_ym=None,
                  sigmaPint_u_0=None, sigmaQint_u=None, sigmaPint_ym_0=None, sigmaQint_ym=None, Cwt=np.inf,
-                 direct=True):
+                 direct=True, P0hat=None, Qhat=None, Rhat=None):
         self._init_common(model, i_ym, nint_u, nint_ym)
         self.He, self.direct = int(He), bool(direct)
         if self.He < 1:
@@ -99,6 +99,10 @@ class MovingHorizonEstimator(StateEstimator):
         sQ = np.concatenate([one(sigmaQ, nx, 1 / nx), one(sigmaQint_u, nsu, 1.0), one(sigmaQint_ym, nsy, 1.0)])
         sR = one(sigmaR, nym, 1.0)
         self.P0hat, self.Qhat, self.Rhat = np.diag(sP ** 2), np.diag(sQ ** 2), np.diag(sR ** 2)
+        # full covariance matrices (the reference's second constructor, src/estimator/mhe/construct.jl:632-660)
+        if P0hat is not None: self.P0hat = np.atleast_2d(np.asarray(P0hat, float))
+        if Qhat is not None: self.Qhat = np.atleast_2d(np.asarray(Qhat, float))
+        if Rhat is not None: self.Rhat = np.atleast_2d(np.asarray(Rhat, float))
         self.Cwt = float(Cwt)
         self.neps = 0 if np.isinf(self.Cwt) else 1
         f = self.fophat - self.xophat

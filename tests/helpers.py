@@ -32,7 +32,10 @@ def batch_from_oracle(mpcs, shared_model=False, team=0, tol=0.0, max_iter=0, wit
     M = st("M_Hp")
     if all(np.count_nonzero(Mi - np.diag(np.diag(Mi))) == 0 for Mi in M):
         M = np.stack([np.diag(Mi) for Mi in M])
-    b.set_weights(M, np.stack([np.diag(m.L_Hp) for m in src]))
+    L = st("L_Hp")
+    if all(np.count_nonzero(Li - np.diag(np.diag(Li))) == 0 for Li in L):
+        L = np.stack([np.diag(Li) for Li in L])
+    b.set_weights(M, L)
     b.set_oppoints(np.stack([m.model.uop for m in src]), np.stack([m.model.yop for m in src]))
     push_constraints(b, mpcs)
     return b

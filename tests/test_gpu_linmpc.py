@@ -394,3 +394,42 @@ def test_multiple_shooting_vs_oracle_ms():
     u = g5.moveinput([[15]])
     assert abs(u[0, 0] - 1) < 1e-2 and abs(g5.getinfo()["Yhat"][0, -1] - 15) < 1e-2
     assert g5.Ztilde.shape == (1, 1 + 2 * 1000 + 1)
+
+
+def test_dense_L_Hp_and_N_Hc_weights_vs_oracle():
+    """Dense (non-diagonal, symmetric positive semidefinite) L_Hp, Ñ_Hc and M_Hp weight matrices (ControllerWeights,
+    src/controller/construct.jl:45-93) with an input-setpoint trajectory R̂u, operating points and active constraints:
+    route B carries Ñ_Hc inside H̃, the kernel forms L_Hp Cu and M_Hp Cy itself.  GPU vs oracle, closed loop."""
+    from helpers import random_plant
+    rng = np.random.default_rng(77)
+    N, Hp, Hc, nu, ny = 4, 6, 3, 2, 2
+    mpcs, plants = [], []
+    psd = lambda n, s: (lambda Q: s * (Q @ Q.T) / n + 0.05 * np.eye(n))(rng.standard_normal((n, n)))
+    for i in range(N):
+        p = random_plant(rng, nx=3, nu=nu, ny=ny)
+        m = LinModel(p.A, p.Bu, p.C, uop=[0.2, -0.1], yop=[1.0, 0.5])
+        mpc = LinMPC(m, Hp=Hp, Hc=Hc, M_Hp=psd(ny * Hp, 1.0), N_Hc=psd(nu * Hc, 0.1), L_Hp=psd(nu * Hp, 0.3), Cwt=1e4)
+        mpc.setconstraint(umin=[-0.8, -0.8], umax=[0.8, 0.8], ymax=[1.6, 1.2])
+        mpcs.append(mpc)
+        plants.append(LinModel(p.A, p.Bu, p.C, uop=[0.2, -0.1], yop=[1.0, 0.5]))
+    b = batch_from_oracle(mpcs)
+    worst, nact = 0.0, 0
+    for k in range(10):
+        ry = np.array([1.0, 0.5]) + rng.choice([-1.0, 1.0], (N, ny))
+        Ru = np.tile([0.2, -0.1], Hp) + 0.3 * rng.standard_normal((N, nu * Hp))
+        ys = [p.evaloutput() for p in plants]
+        for m, y in zip(mpcs, ys):
+            m.preparestate(y)
+        b.lastu0[:] = np.stack([m.lastu0 for m in mpcs])
+        ug = b.step(np.stack([m.estim.xhat0 for m in mpcs]), ry=ry, Rhat_u=Ru).copy()
+        assert (b.status == 0).all()
+        nact += int((b.iters > 0).sum())
+        for i, m in enumerate(mpcs):
+            u = m.moveinput(ry[i], Rhat_u=Ru[i])
+            e = np.abs(b.Ztilde[i] - m.Ztilde).max() / (1 + np.abs(m.Ztilde).max())
+            assert e < 5e-6 and abs(b.J[i] - m.getinfo()["J"]) < 1e-8 * (1 + abs(m.getinfo()["J"])), (k, i, e)
+            worst = max(worst, e)
+            m.updatestate(u, ys[i])
+            plants[i].updatestate(u)
+    assert nact > 5
+    print("dense L_Hp / N_Hc / M_Hp: worst", worst, "active solves", nact)

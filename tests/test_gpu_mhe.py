@@ -224,3 +224,37 @@ def test_mhe_nan_measurements_match_oracle():
             o.updatestate(u[i], y[i])
         g.updatestate(u, y)
     print("MHE NaN measurements worst", worst)
+
+
+def test_mhe_dense_covariances_match_oracle():
+    """Non-diagonal R̂ (and Q̂, P̂_0): the reference's full-matrix constructor (src/estimator/mhe/construct.jl:632-660).
+    invR̂_He = blockdiag(R̂^-1) couples the outputs of one time step in H̃ and q̃; with bounds and a missing measurement."""
+    import mpc_b200
+    N, He = 5, 4
+    gm, oms, rng = make(N, 41, nd=0)
+    spd = lambda n, s: (lambda Q: s * (Q @ Q.T) / n + 0.3 * s * np.eye(n))(rng.standard_normal((n, n)))
+    cov = dict(Rhat=spd(2, 1.0), Qhat=spd(3, 0.2), P0hat=spd(3, 0.5))
+    kw = dict(xhatmin=[-0.8] * 3, xhatmax=[0.8] * 3, whatmin=[-0.4] * 3, whatmax=[0.4] * 3, vhatmin=[-3.0] * 2, vhatmax=[3.0] * 2)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0], **cov).setconstraint(**kw)
+    os_ = [OMHE(m, He=He, nint_ym=0, **cov).setconstraint(**kw) for m in oms]
+    worst, nact = 0.0, 0
+    for k in range(2 * He + 3):
+        y = np.array([5.0, 3.0]) + rng.standard_normal((N, 2))
+        u = np.array([1.0, -2.0]) + rng.standard_normal((N, 2))
+        if k == 5:
+            y[2, 1] = np.nan
+        xg = g.preparestate(y)
+        for i, o in enumerate(os_):
+            xo = o.preparestate(y[i])
+            assert g.status[i] == o.last_qp["status"], (k, i)
+            if g.status[i] == 0:
+                tol = 2e-6 if g.iters[i] > 0 else 1e-9
+                e = np.abs(xg[i] - xo).max() / (1 + np.abs(xo).max())
+                ej = abs(g.J[i] - o.Jval) / (1 + abs(o.Jval))
+                assert e < tol and ej < 1e-8, (k, i, e, ej, g.iters[i])
+                worst = max(worst, e)
+                nact += int(g.iters[i] > 0)
+            o.updatestate(u[i], y[i])
+        g.updatestate(u, y)
+    assert nact > 5
+    print("MHE dense covariances worst", worst, "active solves", nact)
