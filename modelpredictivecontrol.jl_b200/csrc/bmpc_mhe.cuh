@@ -18,7 +18,7 @@
 namespace bmpc {
 
 struct MheLayout {  // shared-memory offsets in doubles
-    int Hv, Phi, x, xb, q, rd, rhs, dx, invd, yb, ybd, wd, s, lam, h, rp, t, ds, dl, F, FX, wrow, P, P2, K, M, red, total;
+    int Hv, Phi, x, xb, q, rd, rhs, dx, invd, yb, ybd, wd, s, lam, h, rp, t, ds, dl, F, FX, wrow, RF, P, P2, K, M, red, total;
 };
 
 struct MheParams {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TEAM, MINB) mhe_step_kernel(const __grid_const
             c.Hv[p] = 2.0 * a;
         }
         double racc = 0.0;
-        double* sRF = c.dl;  // R̂^-1-weighted F (scratch: dl holds max(m, nY) doubles and is unused before the IPM)
+        double* sRF = smem + L.RF;  // R̂^-1-weighted F
         T.sync();
         for (int t = T.tid; t < nYk; t += TEAM) {
             double w;

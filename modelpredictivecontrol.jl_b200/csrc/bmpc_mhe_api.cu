@@ -190,7 +190,7 @@ int compile_rows(bmhe_handle* h, int Nk) {
     L.x = take(n); L.xb = take(n); L.q = take(n); L.rd = take(n); L.rhs = take(n); L.dx = take(n); L.invd = take(n);
     L.yb = take(nDb); L.ybd = take(nDb); L.wd = take(nDb);
     L.s = take(m); L.lam = take(m); L.h = take(m); L.rp = take(m); L.t = take(m); L.ds = take(m); L.dl = take(m);
-    L.F = take(nYm); L.FX = take(nXm); L.wrow = take(nYm);
+    L.F = take(nYm); L.FX = take(nXm); L.wrow = take(nYm); L.RF = take(nYm);
     L.P = take(nx * nx); L.P2 = take(2 * nq * nq + nx * nym); L.K = take(nx * nym); L.M = take(nym * nym + nq * nq);
     L.red = take(40);
     L.total = o;
