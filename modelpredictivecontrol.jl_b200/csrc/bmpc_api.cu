@@ -982,6 +982,13 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     P.lam_ws = h->lam_ws.p; P.ws_flag = h->ws_flag.p; P.ws_stride = even(std::max(h->rt.m, 1));
     P.use_ws = (h->warm_start && h->lam_ws.p) ? 1 : 0;
     P.nw = h->nw; P.sW = d.shared_model ? 0 : h->sWc; P.Wc = h->Wc.p;
+#ifdef BMPC_PHASE_CLK
+    if (!h->clk.p) {
+        CK(h->clk.alloc(32));
+        CK(cudaMemsetAsync(h->clk.p, 0, 32 * sizeof(long long), s));
+    }
+    P.gclk = h->warp ? nullptr : h->clk.p;
+#endif
     for (int pr = 0; pr < 8; ++pr) {
         P.zg[pr] = h->zg[pr];
         P.zg_flag[pr] = h->zg_flag[pr];

@@ -23,6 +23,17 @@ namespace bmpc {
 
 constexpr int ST_OPTIMAL = 0, ST_ITERATION_LIMIT = 1, ST_INFEASIBLE = 2;  // = BMPC_STATUS_* in bmpc.h
 
+// Study builds (-DBMPC_PHASE_CLK, tools/studies/phase_clk_general.py): thread 0 of a team accumulates the cycles between marks
+#ifdef BMPC_PHASE_CLK
+#define GCLK_DECL long long gclk_t = clock64()
+#define GCLK(P_, tid_, i) do { if ((tid_) == 0 && (P_).gclk) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&(P_).gclk[i], (unsigned long long)(t_ - gclk_t)); gclk_t = t_; } } while (0)
+#define GCLK_COUNT(P_, tid_, i, v) do { if ((tid_) == 0 && (P_).gclk) atomicAdd((unsigned long long*)&(P_).gclk[i], (unsigned long long)(v)); } while (0)
+#else
+#define GCLK_DECL
+#define GCLK(P_, tid_, i)
+#define GCLK_COUNT(P_, tid_, i, v)
+#endif
+
 struct RowTables {
     int nS, nDr, nDb, m;     // sparse rows, dense rows, dense base rows, total rows (incl. eps>=0)
     const int* s_i1;         // [nS] variable with coefficient +sigma
@@ -89,6 +100,9 @@ struct StepParams {
     int nw;
     long sW;
     const double* Wc;
+#ifdef BMPC_PHASE_CLK
+    long long* gclk;      // study builds: [32] accumulated cycles per phase of the general kernel's IPM
+#endif
     const double* Ys;     // [N x nY] stochastic output predictions Ŷs added to F (InternalModel, predictstoch! execute.jl:321-327) or nullptr
     double* kkt_out;      // [N x 3] relative KKT residuals of the returned iterate: primal, dual, complementarity (or nullptr)
 };
@@ -240,7 +254,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int TEAM>
 __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, double* invd, int n) {
     int bad = 0;
-    if (TEAM >= 64 && n < 56) {
+#ifndef BMPC_CHOL_BLOCKED_MIN
+#define BMPC_CHOL_BLOCKED_MIN 56
+#endif
+    if (TEAM >= 64 && n < BMPC_CHOL_BLOCKED_MIN) {
         // CTA teams, small n: right-looking, ONE barrier per column.  Column k is used unscaled for the trailing update
         // (A_ij -= A_ik A_jk / d_k) and scaled to L during the next column's phase, when nobody reads it any more.
         // Threads form a TX x TY grid over the trailing triangle: TY rows per pass, TX threads along a row.
@@ -259,6 +276,9 @@ __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, doubl
                 rs = rsqrt(dk);
                 invdk = rs * rs;
                 const int rem = n - k - 1;
+                // (a variant that enumerates the trailing triangle through the packed pair tables -- every lane busy, 1/5 of
+                // the instructions -- was measured SLOWER at n = 41: 68 k vs 58 k cycles per factorisation; the phase is bound by
+                // the 41 barrier + rsqrt + dependent update round trips, not by instruction issue)
                 for (int a = ty; a < rem; a += TY) {
                     const int i = k + 1 + a;
                     const double lik = A[pidx(i, k)] * invdk;
@@ -699,6 +719,9 @@ template <int TEAM>
 __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, double Hee, const double* d) {
     const RowTables& rt = c.P->rt;
     const int nDb = rt.nDb, nz = c.P->nz, neps = c.P->neps;
+#ifdef BMPC_PHASE_CLK
+    const long long bp_t0 = clock64();
+#endif
     // dense weights: wd[k] = d_max + d_min ; ybd[k] = sig*c*d summed (for the slack border)
     for (int k = T.tid; k < nDb; k += TEAM) {
         const int a = rt.db_rmax[k], b = rt.db_rmin[k];
@@ -859,6 +882,9 @@ __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, dou
         }
     }
     T.sync();
+#ifdef BMPC_PHASE_CLK
+    if (T.tid == 0 && c.P->gclk) atomicAdd((unsigned long long*)&c.P->gclk[9], (unsigned long long)(clock64() - bp_t0));
+#endif
     // 1-/2-variable rows: gather per variable (each packed entry has exactly one writer)
     for (int j = T.tid; j < nz; j += TEAM) {
         double dg = 0.0, be = 0.0;
@@ -925,13 +951,16 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
     int stall = 0, stagn = 0;
     double mu_first = 0.0, ep_chk = 1e300;
     bool ray_prev = false;
+    GCLK_DECL;
     for (int it = 0; it <= P.max_iter; ++it) {
+        GCLK(P, T.tid, 8);
         // residuals
         hess_apply(T, c, Hee, c.x, c.rhs);  // rhs <- H x
         T.sync();
         for (int j = T.tid; j < n; j += TEAM) c.rhs[j] += c.q[j];
         T.sync();
         gt_apply(T, c, c.lam, 1.0, c.rhs, c.rd);  // rd = Hx + q + G' lam
+        GCLK(P, T.tid, 0);
         double e_d = 0.0, e_p = 0.0, musum = 0.0, dsc = 0.0;
         for (int j = T.tid; j < n; j += TEAM) {
             e_d = fmax(e_d, fabs(c.rd[j]));
@@ -1003,17 +1032,22 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
             break;
         }
         iters = it + 1;
+        GCLK(P, T.tid, 1);
         // Phi = H + G' D G, factor
         for (int r = T.tid; r < m; r += TEAM) c.t[r] = c.lam[r] / c.s[r];
         T.sync();
         build_phi(T, c, Hee, c.t);
+        GCLK(P, T.tid, 2);
         chol_packed(T, c.Phi, c.invd, n);
+        GCLK(P, T.tid, 3);
         // predictor: rhs = -rd - G'(d*rp - lam)
         for (int r = T.tid; r < m; r += TEAM) c.dl[r] = c.t[r] * c.rp[r] - c.lam[r];
         T.sync();
         gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
         for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+        GCLK(P, T.tid, 4);
         chol_solve(T, c.Phi, c.invd, c.dx, n);
+        GCLK(P, T.tid, 5);
         dense_apply(T, c, c.dx, c.ybd);
         T.sync();
         for (int r = T.tid; r < m; r += TEAM) {
@@ -1022,6 +1056,7 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
             c.dl[r] = -c.lam[r] - c.t[r] * dsv;
         }
         T.sync();
+        GCLK(P, T.tid, 6);
         const double a_aff = max_step(T, c, m);
         double mua = 0.0;
         for (int r = T.tid; r < m; r += TEAM)
@@ -1036,9 +1071,12 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
             c.dl[r] = (c.lam[r] * c.rp[r] - rc) / c.s[r];
         }
         T.sync();
+        GCLK(P, T.tid, 7);
         gt_apply(T, c, c.dl, 1.0, c.rd, c.dx);
         for (int j = T.tid; j < n; j += TEAM) c.dx[j] = -c.dx[j];
+        GCLK(P, T.tid, 4);
         chol_solve(T, c.Phi, c.invd, c.dx, n);
+        GCLK(P, T.tid, 5);
         dense_apply(T, c, c.dx, c.ybd);
         T.sync();
         for (int r = T.tid; r < m; r += TEAM) {
@@ -1048,6 +1086,7 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
             c.dl[r] = -(rc + c.lam[r] * dsv) / c.s[r];
         }
         T.sync();
+        GCLK(P, T.tid, 6);
         // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap (never exactly 1)
         const double tau = fmin(fmax(0.99, 1.0 - mua / mu), 1.0 - 1e-6);
         const double a = fmin(1.0, tau * max_step(T, c, m));
@@ -1088,6 +1127,9 @@ __device__ __forceinline__ void ipm_solve(const Team<TEAM>& T, const Ctx& c, con
         }
         T.sync();
     }
+    GCLK(P, T.tid, 8);
+    GCLK_COUNT(P, T.tid, 16, iters);
+    GCLK_COUNT(P, T.tid, 17, 1);
     // status INFEASIBLE is reserved for the certified exits above (collapsed steps, Farkas ray, NaN): an iteration-limit
     // exit keeps its iterate (general.jl `iserror`: only INFEASIBLE / NUMERICAL_ERROR ... discard the solver's value)
     (void)rp_inf;
