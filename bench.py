@@ -234,8 +234,11 @@ def build_linmpc(name, rank, world, total_periods, device):
     import mpc_b200
     from mpc_b200 import workloads
     N0, nx, nu, ny, Hp, Hc, seed = workloads.CONFIGS[name]
-    if name == "C1":  # weak scaling: every rank its own 4096 controllers
-        model, rng = workloads.random_plants(N0, nx, nu, ny, seed + 1000 * rank)
+    if name == "C1":
+        # weak scaling: every rank runs the SAME 4096 controllers (configs[1] replicated per GPU) -- equal work per GPU by
+        # construction; BMPC_RANK_SEEDS=1 gives every rank its own plants instead (the unluckiest set then paces the run)
+        rs = rank if os.environ.get("BMPC_RANK_SEEDS", "0") != "0" else 0
+        model, rng = workloads.random_plants(N0, nx, nu, ny, seed + 1000 * rs)
         N = N0
         ry = workloads.setpoints(rng, N, ny, total_periods, period=25)
     else:             # strong scaling: the config's batch is split over the ranks
@@ -266,7 +269,9 @@ def build_linmpc(name, rank, world, total_periods, device):
 
 
 class Gather:
-    """Epoch-flag fused all-gather of Z̃ (bmpc_set_gather_flags) over torch symmetric memory, NCCL as the fallback."""
+    """Fused all-gather of Z̃, pull protocol (bmpc_set_gather_pull) over torch symmetric memory; NCCL as the fallback.
+    The step kernel stores Z̃ into its own slot buffer and publishes the period number; a one-sided pull kernel on a SIDE
+    stream copies every peer's rows over NVLink while the next period computes."""
 
     def __init__(self, b, world, rank, N, n, dev, dist):
         import torch
@@ -278,48 +283,66 @@ class Gather:
         self.mode = "ncclAllGather of Ztilde after every step"
         if os.environ.get("BMPC_FUSED_GATHER", "1") == "0":
             return
+        if os.environ.get("BMPC_FUSED_GATHER") == "off":  # diagnostic: independent shards, no collection at all
+            self.world, self.mode = 1, "off (diagnostic)"
+            return
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            slots = 3
-            self.buf = symm_mem.empty((slots, world * N, n), dtype=torch.float64, device=dev)
+            slots = 4
+            self.buf = symm_mem.empty((slots, N, n), dtype=torch.float64, device=dev)
             self.buf.zero_()
-            self.flags = symm_mem.empty((8,), dtype=torch.int64, device=dev)
+            self.localbuf = torch.zeros((slots, N, n), dtype=torch.float64, device=dev) if os.environ.get("BMPC_PULL_LOCALBUF") else None
+            self.flags = symm_mem.empty((16,), dtype=torch.int64, device=dev)
             self.flags.zero_()
             hb = symm_mem.rendezvous(self.buf, dist.group.WORLD)
             hf = symm_mem.rendezvous(self.flags, dist.group.WORLD)
+            self.dst = torch.zeros((world * N, n), dtype=torch.float64, device=dev)
+            self.side = torch.cuda.Stream(device=dev)
             torch.cuda.synchronize()
             dist.barrier()
-            b.set_gather_flags([int(hb.buffer_ptrs[p]) for p in range(world)], [int(hf.buffer_ptrs[p]) for p in range(world)],
-                               rank, rank * N, world * N, slots)
+            b.set_gather_pull([self.localbuf.data_ptr() if (self.localbuf is not None and p == rank) else int(hb.buffer_ptrs[p]) for p in range(world)], [int(hf.buffer_ptrs[p]) for p in range(world)],
+                              rank, [p * N for p in range(world + 1)], slots)
             self.fused = True
-            self.mode = ("fused, epoch flags: the step kernel's epilogue stores Ztilde into every peer's symmetric-memory buffer "
-                         "(NVLink), the last CTA publishes the period with st.release.sys; a one-warp reader acquires period k-1 "
-                         "while period k runs (3 slots); no cross-rank barrier per period")
+            self.mode = (f"fused, pull protocol: the step kernel's epilogue stores Ztilde into its own symmetric-memory slot buffer "
+                         f"({slots} slots) and its last CTA publishes the period number in its OWN flag array (st.release.sys); a one-sided pull "
+                         "kernel on a side stream polls the peers' flags and copies their rows over NVLink while the next period "
+                         "runs, then acks; no cross-rank barrier, no sender-side remote stores")
         except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory path falls back to NCCL
             sys.stderr.write(f"[bench] symmetric memory unavailable ({e!r}); using ncclAllGather\n")
 
     def after_step(self, z_dev):
-        """Called right after a step was enqueued: make the moves of all ranks available (one period late when fused)."""
+        """Called right after a step was enqueued: collect that period's moves of all ranks."""
         if self.world <= 1:
             return
         if self.fused:
-            e = self.b.gather_epoch()
-            if e >= 2:
-                self.b.gather_wait(e - 1)
+            pm = os.environ.get("BMPC_PULL_MODE", "side")  # diagnostics: "none" = publish only, "main" = pull on the step's stream
+            if pm != "none":
+                self.b.gather_pull(self.b.gather_epoch(), self.dst.data_ptr(), self.side.cuda_stream if pm == "side" else None)
         else:
             self.dist.all_gather_into_tensor(self.gather_nccl.view(-1), z_dev.reshape(-1))
 
+    def join(self, stream):
+        """The launching stream waits for the side stream's pulls (end of a timed region)."""
+        if self.fused:
+            stream.wait_stream(self.side)
+
+    def disable(self):
+        import torch
+        if self.fused:
+            torch.cuda.synchronize()
+            self.dist.barrier()
+            self.b.set_gather(None, 0)
+        self.world = 1
+
     def verify(self, z_dev):
-        """The fused buffer of the LAST period against ncclAllGather of the same Z̃."""
+        """The pulled array of the LAST period against ncclAllGather of the same Z̃."""
         import torch
         if not self.fused:
             return None
-        e = self.b.gather_epoch()
-        slot = self.b.gather_wait(e)
+        torch.cuda.synchronize()
         self.dist.all_gather_into_tensor(self.gather_nccl.view(-1), z_dev.reshape(-1))
         torch.cuda.synchronize()
-        ok = bool(torch.equal(self.gather_nccl.view(-1), self.buf[slot].reshape(-1))) and self.b.gather_timed_out() == 0
-        return ok
+        return bool(torch.equal(self.gather_nccl.view(-1), self.dst.reshape(-1))) and self.b.gather_timed_out() == 0
 
 
 def time_linmpc(mpc, rec, W, K, dev, stream, flush, gather=None, world=1, dist=None, busy_passes=0, sampler=None):
@@ -359,10 +382,18 @@ def time_linmpc(mpc, rec, W, K, dev, stream, flush, gather=None, world=1, dist=N
         ev[j][0].record(stream)
         launch(W + j)
         ev[j][1].record(stream)
+    # the pulls of the last periods may still be in flight on the side stream: their completion is part of the timed work
+    ev_tail = torch.cuda.Event(enable_timing=True)
+    if gather is not None:
+        gather.join(stream)
+    ev_tail.record(stream)
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
     launches = b.launch_count() - l_before
+    tail_ms = ev[K - 1][1].elapsed_time(ev_tail)
     check = gather.verify(tZ[W + K - 1]) if gather is not None else None
+    if gather is not None:
+        gather.disable()  # the passes below (and the e2e leg) run without readers
     # extra passes without flushes keep the GPU busy long enough for the 10 Hz clock sampler (never used for `value`)
     for _ in range(busy_passes):
         tLU.copy_(tLU0)
@@ -373,7 +404,9 @@ def time_linmpc(mpc, rec, W, K, dev, stream, flush, gather=None, world=1, dist=N
                                iters=tI.data_ptr()))
     torch.cuda.synchronize()
     ms = [a.elapsed_time(c) for a, c in ev]
-    dev_ms = sum(ms)
+    dev_ms = sum(ms) + tail_ms
+    if os.environ.get("BMPC_PULL_MODE"):
+        sys.stderr.write(f"[bench] tail_ms {tail_ms:.4f} sum {sum(ms):.4f} min {min(ms):.4f} max {max(ms):.4f}\n")
     if world > 1:
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -710,11 +743,7 @@ def main():
     gather = Gather(b, world, rank, N, n, dev, dist)
     with ClockSampler(local_rank) as clk:
         v = time_linmpc(mpc, rec, W, K, dev, stream, flush, gather, world, dist, busy_passes=60)
-    if world > 1 and gather.fused:
-        # the e2e leg below runs without the gather: a host-side caller reads u, not the peers' moves
-        torch.cuda.synchronize()
-        dist.barrier()
-        b.set_gather(None, 0)
+    # (the e2e leg below runs without the gather: a host-side caller reads u, not the peers' moves)
     e = time_linmpc_e2e(mpc, rec, W, K, dev, world, dist)
     sm = time_setmodel(mpc, rec, 2, min(K, 10)) if (world == 1 and not args.no_configs) else None
     ms_per_step = v["dev_ms"] / K
@@ -725,7 +754,7 @@ def main():
     config = {"workload": workload_text("C1"), "instances_per_gpu": N, "nu": nu, "ny": ny, "Hp": Hp, "Hc": Hc,
               "n_decision": nu * Hc + 1, "rows_reference": 2 * nu * Hp + ny * Hp + 1,
               "l2": "flushed (256 MiB memset) before every timed launch",
-              "parallelism": f"{world} independent shard(s) of {N} instances"}
+              "parallelism": f"{world} independent shard(s) of {N} instances (weak scaling: configs[1] replicated on every GPU)"}
     traffic, traffic_src = None, None
     for f in ("ncu_r02_warp_summary.json", "ncu_r01_warp_summary.json"):
         pth = os.path.join(ROOT, "profiles", f)
@@ -738,7 +767,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "gather": {"mode": gather.mode, "equals_ncclAllGather": v["gather_check"]},
-        "config": config, "gpu_launches": v["launches"],  # (with --gpus > 1: one step kernel + one reader kernel per period)
+        "config": config, "gpu_launches": v["launches"],  # (with --gpus > 1: one step kernel + one pull kernel per period)
         "e2e": {"value": world * N * K / e["seconds"], "unit": "instance-steps/s", "h2d_bytes_per_step": e["h2d"],
                 "d2h_bytes_per_step": e["d2h"], "ms_per_step": 1e3 * e["seconds"] / K,
                 "copies_per_step": "H2D xhat0, ry; D2H u, status (u0(k-1), Z̃ are handle state, io.resident = 1)" +

@@ -230,23 +230,28 @@ int bmpc_get_state(bmpc_handle *h, double *xhat0, double *xhat0_corrected);
  * memory, peer access over NVLink).  The step kernel's epilogue then stores every instance's Z̃ straight into slot
  * (rank, instance) of every peer's buffer, so no separate collective kernel runs; the caller only needs a
  * cross-rank barrier before reading the buffer.  world = 0 or peer_bufs = NULL switches it off.  world <= 8.
- * Every rank must hold the SAME number of instances N (row block `rank`); for uneven shards use bmpc_set_gather_flags. */
+ * Every rank must hold the SAME number of instances N (row block `rank`); for uneven shards, or to
+ * drop the per-period barrier and the 8-byte remote stores, use bmpc_set_gather_pull. */
 int bmpc_set_gather(bmpc_handle *h, void *const *peer_bufs, int32_t world, int32_t rank);
 
-/* The same fused gather WITHOUT a cross-rank barrier per period (epoch-flag protocol).  peer_bufs[p] is rank p's gather
- * buffer [slots x rows_total x n] doubles, peer_flags[p] its flag array [world] of uint64 (zero-initialised), both mapped
- * into this process.  This rank's N instances are rows [row_offset, row_offset + N) of the rows_total rows (shards may
- * be UNEVEN).  Period e = 1, 2, ... of this handle (bmpc_gather_epoch() after the step) is stored into slot e % slots of
- * every peer's buffer; after ALL of the launch's peer stores the last CTA out publishes e into flag `rank` of every peer
- * with st.release.sys.  A reader calls bmpc_gather_wait(h, e, &slot): a one-warp kernel on the handle's stream that
- * acquires flags[r] >= e for every rank r (gives up after ~2 s: bmpc_gather_timed_out), after which slot `slot` holds
- * period e of every rank.  slots >= 3: a reader consuming period e - 1 while it runs period e bounds the skew between
- * ranks to one period, so the slot being read (e - 1) and the slot a fast peer writes (e + 1) never coincide. */
-int bmpc_set_gather_flags(bmpc_handle *h, void *const *peer_bufs, void *const *peer_flags, int32_t world, int32_t rank,
-                          int32_t row_offset, int32_t rows_total, int32_t slots);
+/* The gather WITHOUT a cross-rank barrier and without sender-side traffic (pull protocol, uneven shards allowed).
+ * peer_bufs[p] is rank p's slot buffer [slots x N_p x n] doubles (N_p = row_offsets[p+1] - row_offsets[p] rows: rank p's own
+ * instances), peer_flags[p] its flag array [2 world] of uint64 (zero-initialised); both mapped into this process (CUDA IPC /
+ * symmetric memory).  Period e = 1, 2, ... of this handle (bmpc_gather_epoch() after the step): the step kernel's epilogue
+ * stores Z̃ into slot e % slots of THIS rank's buffer -- local, coalesced stores -- and its last CTA publishes e into entry
+ * `rank` of THIS rank's flag array with st.release.sys: a launch never touches remote memory.  A reader calls
+ * bmpc_gather_pull(h, e, dst, stream): a kernel on `stream` (NULL = the handle's; a side stream overlaps the next period and
+ * is made to wait for this rank's own launch of period e) that, per rank p, polls peer_flags[p][p] >= e over NVLink
+ * (ld.acquire.sys) and copies rank p's rows of period e into dst rows [row_offsets[p], row_offsets[p+1]) of the device array
+ * [row_offsets[world] x n] (dst = NULL: wait only), then publishes its ack (entry world + rank of every peer's flag array).
+ * Once a handle has pulled, its step kernels wait, before overwriting a slot, until every rank has acknowledged the period
+ * that lived there (normally satisfied at once; every wait gives up after ~2 s: bmpc_gather_timed_out).
+ * slots >= 2; readers that lag L periods need slots >= L + 2. */
+int bmpc_set_gather_pull(bmpc_handle *h, void *const *peer_bufs, void *const *peer_flags, int32_t world, int32_t rank,
+                         const int32_t *row_offsets, int32_t slots);
 int64_t bmpc_gather_epoch(bmpc_handle *h);
-int bmpc_gather_wait(bmpc_handle *h, int64_t epoch, int32_t *slot);
-int bmpc_gather_timed_out(bmpc_handle *h); /* 1 if a bmpc_gather_wait gave up (synchronises the stream) */
+int bmpc_gather_pull(bmpc_handle *h, int64_t epoch, double *dst, void *stream);
+int bmpc_gather_timed_out(bmpc_handle *h); /* 1 if a wait gave up (synchronises the device) */
 
 /* Launch geometry actually used: {team, teams_per_cta, grid, smem_bytes_per_cta,
  * pd_in_smem, n_rows_m, n_sparse_rows, n_dense_rows} -- for DESIGN.md / bench reporting. */

@@ -60,7 +60,7 @@ SYMBOLS = ["bmpc_last_error", "bmpc_version", "bmpc_create", "bmpc_destroy", "bm
            "bmpc_getinfo", "bmpc_set_estimator", "bmpc_set_estimator_cov", "bmpc_get_cov", "bmpc_set_state", "bmpc_get_state", "bmpc_set_gather", "bmpc_launch_info", "bmpc_launch_count",
            "bmhe_create", "bmhe_destroy", "bmhe_set_predmat", "bmhe_set_cov", "bmhe_set_constraints", "bmhe_reset",
            "bmhe_correct", "bmhe_update", "bmhe_update_solve", "bmhe_set_stream", "bmhe_launch_count",
-           "bmpc_set_gather_flags", "bmpc_gather_epoch", "bmpc_gather_wait", "bmpc_gather_timed_out",
+           "bmpc_set_gather_pull", "bmpc_gather_epoch", "bmpc_gather_pull", "bmpc_gather_timed_out",
            "bmpc_set_custom", "bmpc_set_custom_bounds", "bmpc_get_states", "bmpc_set_weights_dense"]
 
 
@@ -111,11 +111,11 @@ def lib():
     L.bmpc_set_custom.argtypes = [C.c_void_p, C.c_int32] + [c_double_p] * 7
     L.bmpc_set_custom_bounds.argtypes = [C.c_void_p] + [c_double_p] * 4
     L.bmhe_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
-    L.bmpc_set_gather_flags.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
-                                        C.c_int32, C.c_int32, C.c_int32]
+    L.bmpc_set_gather_pull.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                       c_int32_p, C.c_int32]
     L.bmpc_gather_epoch.argtypes = [C.c_void_p]
     L.bmpc_gather_epoch.restype = C.c_int64
-    L.bmpc_gather_wait.argtypes = [C.c_void_p, C.c_int64, c_int32_p]
+    L.bmpc_gather_pull.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.bmpc_gather_timed_out.argtypes = [C.c_void_p]
     L.bmhe_launch_count.argtypes = [C.c_void_p]
     L.bmhe_launch_count.restype = C.c_int64

@@ -252,23 +252,23 @@ class BatchLinMPC:
         arr = (C.c_void_p * max(world, 1))(*[C.c_void_p(int(p)) for p in (peer_ptrs or [])])
         check(_lib.lib().bmpc_set_gather(self._h, arr if world else None, world, int(rank)))
 
-    def set_gather_flags(self, peer_ptrs, flag_ptrs, rank, row_offset, rows_total, slots=3):
-        """Fused all-gather of Z̃ without a cross-rank barrier per period (epoch flags, include/bmpc.h
-        bmpc_set_gather_flags): ``peer_ptrs[p]`` / ``flag_ptrs[p]`` = device addresses of rank p's [slots, rows_total, n]
-        float64 buffer and [world] uint64 flag array, mapped into this process."""
+    def set_gather_pull(self, peer_ptrs, flag_ptrs, rank, row_offsets, slots=3):
+        """Fused all-gather of Z̃, pull protocol (include/bmpc.h bmpc_set_gather_pull): ``peer_ptrs[p]`` / ``flag_ptrs[p]`` =
+        device addresses of rank p's [slots, N_p, n] float64 slot buffer and [2 world] uint64 flag array, mapped into this
+        process; ``row_offsets`` (world + 1) places every rank's rows in the gathered array."""
         world = len(peer_ptrs)
         arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         farr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in flag_ptrs])
-        check(_lib.lib().bmpc_set_gather_flags(self._h, arr, farr, world, int(rank), int(row_offset), int(rows_total), int(slots)))
+        ro = (C.c_int32 * (world + 1))(*[int(v) for v in row_offsets])
+        check(_lib.lib().bmpc_set_gather_pull(self._h, arr, farr, world, int(rank), ro, int(slots)))
 
     def gather_epoch(self):
         return int(_lib.lib().bmpc_gather_epoch(self._h))
 
-    def gather_wait(self, epoch):
-        """Enqueue the consumer-side wait for period ``epoch`` of every rank; returns the slot that then holds it."""
-        slot = C.c_int32(0)
-        check(_lib.lib().bmpc_gather_wait(self._h, int(epoch), C.byref(slot)))
-        return slot.value
+    def gather_pull(self, epoch, dst_ptr, stream_ptr=None):
+        """Enqueue the one-sided gather of period ``epoch`` into the device array at ``dst_ptr`` ([rows_total, n])."""
+        check(_lib.lib().bmpc_gather_pull(self._h, int(epoch), C.c_void_p(int(dst_ptr)) if dst_ptr else None,
+                                          C.c_void_p(int(stream_ptr)) if stream_ptr else None))
 
     def gather_timed_out(self):
         return int(_lib.lib().bmpc_gather_timed_out(self._h))

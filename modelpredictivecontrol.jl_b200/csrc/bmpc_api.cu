@@ -100,11 +100,15 @@ struct bmpc_handle {
     bool e_has_fx = false;
     double* zg[8] = {nullptr};  // peer-mapped gather buffers (bmpc_set_gather / bmpc_set_gather_flags)
     int zg_world = 0, zg_rank = 0;
-    unsigned long long* zg_flag[8] = {nullptr};  // epoch-flag protocol: every peer's flag array [world]
+    unsigned long long* zg_flag[8] = {nullptr};  // pull protocol: every peer's flag array [2 world] (data epochs, ack epochs)
     long zg_row_offset = 0, zg_rows_total = 0;
+    int zg_row_off[9] = {0};
     int zg_slots = 1;
+    bool zg_pull = false, zg_consumer = false;
+    cudaEvent_t zg_ev = nullptr;
     int64_t zg_epoch = 0;   // periods published so far
     DevBuf<int> zg_timeout;
+    DevBuf<unsigned int> zg_done;
     int order_cur = 0;       // order[order_cur] drives the next launch
     bool order_valid = false;
     int warm_start = 1;
@@ -517,6 +521,7 @@ int bmpc_destroy(bmpc_handle* h) {
     cudaDeviceSynchronize();
     // every DevBuf member frees its allocation in its destructor (delete h below)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->zg_ev) cudaEventDestroy(h->zg_ev);
     delete h;
     return BMPC_OK;
 }
@@ -998,7 +1003,15 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     if (h->zg_world > 0) {
         h->zg_epoch++;
         P.zg_epoch = (unsigned long long)h->zg_epoch;
-        P.zg_base = ((long)(h->zg_epoch % h->zg_slots) * h->zg_rows_total + h->zg_row_offset) * (long)n;
+        P.zg_pull = h->zg_pull ? 1 : 0;
+        P.zg_timeout = h->zg_timeout.p;
+        if (h->zg_pull) {  // this rank's own slot buffer: [slots x N x n]
+            P.zg_base = (long)(h->zg_epoch % h->zg_slots) * (long)d.N * (long)n;
+            P.zg_need_ack = h->zg_consumer ? (long long)h->zg_epoch - h->zg_slots : 0;  // the period that lived in this slot
+        } else {
+            P.zg_base = h->zg_row_offset * (long)n;
+            P.zg_need_ack = 0;
+        }
     }
     cudaError_t le;
     const bool kf = fused_est && h->kf_on;
@@ -1015,6 +1028,8 @@ int bmpc_step(bmpc_handle* h, const bmpc_step_io* io) {
     }
     if (h->warp) {
         bmpc::WarpParams Q = h->wp;
+        Q.static_first = 1;
+        if (const char* e = getenv("BMPC_STATIC_FIRST")) Q.static_first = atoi(e);  // (study override)
         Q.order = h->order_valid ? h->order[h->order_cur].p : nullptr;
         Q.order_next = h->order[h->order_cur ^ 1].p;
         Q.ocnt = h->ocnt.p;
@@ -1170,62 +1185,107 @@ int bmpc_get_state(bmpc_handle* h, double* xhat0, double* xhat0_corrected) {
     return BMPC_OK;
 }
 
-int bmpc_set_gather_flags(bmpc_handle* h, void* const* peer_bufs, void* const* peer_flags, int32_t world, int32_t rank,
-                          int32_t row_offset, int32_t rows_total, int32_t slots) {
+int bmpc_set_gather_pull(bmpc_handle* h, void* const* peer_bufs, void* const* peer_flags, int32_t world, int32_t rank,
+                         const int32_t* row_offsets, int32_t slots) {
     if (!h) return fail(BMPC_ERR_ARG, "null handle");
     if (world == 0 || !peer_bufs) {
         h->zg_world = 0;
+        h->zg_pull = false;
         return BMPC_OK;
     }
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BMPC_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
-    if (row_offset < 0 || rows_total < 1 || (long)row_offset + h->d.N > rows_total)
-        return fail(BMPC_ERR_ARG, "rows [row_offset, row_offset + N) must lie inside [0, rows_total)");
-    if (slots < 1 || (peer_flags && slots < 3))
-        return fail(BMPC_ERR_ARG, "slots must be >= 1 (>= 3 with epoch flags: a peer may run one period ahead of a reader one period behind)");
+    if (!peer_flags || !row_offsets) return fail(BMPC_ERR_ARG, "null argument");
+    if (slots < 2) return fail(BMPC_ERR_ARG, "slots must be >= 2 (the period being written and the one being read)");
+    for (int pr = 0; pr < world; ++pr)
+        if (row_offsets[pr + 1] < row_offsets[pr]) return fail(BMPC_ERR_ARG, "row_offsets must be non-decreasing");
+    if (row_offsets[rank + 1] - row_offsets[rank] != h->d.N)
+        return fail(BMPC_ERR_ARG, "row_offsets[rank+1] - row_offsets[rank] must equal this handle's N");
     for (int pr = 0; pr < world; ++pr) {
-        if (!peer_bufs[pr] || (peer_flags && !peer_flags[pr])) return fail(BMPC_ERR_ARG, "null peer buffer");
+        if (!peer_bufs[pr] || !peer_flags[pr]) return fail(BMPC_ERR_ARG, "null peer buffer");
         h->zg[pr] = static_cast<double*>(peer_bufs[pr]);
-        h->zg_flag[pr] = peer_flags ? static_cast<unsigned long long*>(peer_flags[pr]) : nullptr;
+        h->zg_flag[pr] = static_cast<unsigned long long*>(peer_flags[pr]);
     }
     for (int pr = world; pr < 8; ++pr) { h->zg[pr] = nullptr; h->zg_flag[pr] = nullptr; }
+    for (int pr = 0; pr <= world; ++pr) h->zg_row_off[pr] = row_offsets[pr];
     CK(cudaSetDevice(h->d.device));
     CK(h->zg_timeout.alloc(1));
+    CK(h->zg_done.alloc(1));
     CK(cudaMemsetAsync(h->zg_timeout.p, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->zg_done.p, 0, sizeof(unsigned int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     h->zg_world = world;
     h->zg_rank = rank;
-    h->zg_row_offset = row_offset;
-    h->zg_rows_total = rows_total;
     h->zg_slots = slots;
+    h->zg_pull = true;
+    h->zg_consumer = false;
     h->zg_epoch = 0;
     return BMPC_OK;
 }
 
 int bmpc_set_gather(bmpc_handle* h, void* const* peer_bufs, int32_t world, int32_t rank) {
     if (!h) return fail(BMPC_ERR_ARG, "null handle");
-    // barrier protocol, one slot, EQUAL shard sizes on every rank (row block `rank` of [world x N x n])
-    return bmpc_set_gather_flags(h, peer_bufs, nullptr, world, rank, rank * h->d.N, (world > 0 ? world : 1) * h->d.N, 1);
+    if (world == 0 || !peer_bufs) {
+        h->zg_world = 0;
+        h->zg_pull = false;
+        return BMPC_OK;
+    }
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(BMPC_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
+    // push protocol: the epilogue stores into row block `rank` of EVERY peer's [world x N x n] buffer (equal shard sizes);
+    // the caller supplies the cross-rank barrier before reading
+    for (int pr = 0; pr < world; ++pr) {
+        if (!peer_bufs[pr]) return fail(BMPC_ERR_ARG, "null peer buffer");
+        h->zg[pr] = static_cast<double*>(peer_bufs[pr]);
+        h->zg_flag[pr] = nullptr;
+    }
+    for (int pr = world; pr < 8; ++pr) { h->zg[pr] = nullptr; h->zg_flag[pr] = nullptr; }
+    h->zg_world = world;
+    h->zg_rank = rank;
+    h->zg_row_offset = (long)rank * h->d.N;
+    h->zg_slots = 1;
+    h->zg_pull = false;
+    h->zg_epoch = 0;
+    return BMPC_OK;
 }
 
 int64_t bmpc_gather_epoch(bmpc_handle* h) { return h ? h->zg_epoch : 0; }
 
-int bmpc_gather_wait(bmpc_handle* h, int64_t epoch, int32_t* slot) {
+int bmpc_gather_pull(bmpc_handle* h, int64_t epoch, double* dst, void* stream) {
     if (!h) return fail(BMPC_ERR_ARG, "null handle");
-    if (h->zg_world <= 0 || !h->zg_flag[h->zg_rank]) return fail(BMPC_ERR_STATE, "bmpc_gather_wait needs bmpc_set_gather_flags");
+    if (h->zg_world <= 0 || !h->zg_pull) return fail(BMPC_ERR_STATE, "bmpc_gather_pull needs bmpc_set_gather_pull");
     if (epoch < 1 || epoch > h->zg_epoch) return fail(BMPC_ERR_ARG, "epoch must be 1..bmpc_gather_epoch()");
+    if (epoch + h->zg_slots <= h->zg_epoch + 1 && !h->zg_consumer)
+        return fail(BMPC_ERR_STATE, "that period's slot has already been overwritten (pull every period, or use more slots)");
     CK(cudaSetDevice(h->d.device));
-    // ~2 s at 2 GHz: a peer that never publishes must not hang the device
-    bmpc::k_gather_wait<<<1, 32, 0, h->stream>>>(h->zg_flag[h->zg_rank], h->zg_world, (unsigned long long)epoch, 4000000000LL,
-                                               h->zg_timeout.p);
+    bmpc::PullParams Q{};
+    for (int pr = 0; pr < h->zg_world; ++pr) {
+        Q.src[pr] = h->zg[pr];
+        Q.flags[pr] = h->zg_flag[pr];
+    }
+    for (int pr = 0; pr <= h->zg_world; ++pr) Q.row_off[pr] = h->zg_row_off[pr];
+    Q.world = h->zg_world; Q.rank = h->zg_rank; Q.n = h->n; Q.slots = h->zg_slots; Q.parts = 8;
+    Q.epoch = (unsigned long long)epoch;
+    Q.limit = 4000000000LL;  // ~2 s at 2 GHz: a peer that never publishes must not hang the device
+    Q.timed_out = h->zg_timeout.p;
+    Q.done = h->zg_done.p;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (s != h->stream) {
+        // a side stream: the pull starts once this rank's own step kernel of `epoch` has finished, so its spinning
+        // CTAs never take SM residency away from that launch
+        if (!h->zg_ev) CK(cudaEventCreateWithFlags(&h->zg_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->zg_ev, h->stream));
+        CK(cudaStreamWaitEvent(s, h->zg_ev, 0));
+    }
+    bmpc::k_gather_pull<<<h->zg_world * Q.parts, 256, 0, s>>>(Q, dst);
     CK(cudaGetLastError());
     h->launches++;
-    if (slot) *slot = (int32_t)(epoch % h->zg_slots);
+    h->zg_consumer = true;  // from now on a launch waits for every reader's ack before it reuses a slot
     return BMPC_OK;
 }
 
 int bmpc_gather_timed_out(bmpc_handle* h) {
     if (!h || !h->zg_timeout.p) return 0;
     int v = 0;
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpy(&v, h->zg_timeout.p, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
 }

@@ -84,9 +84,13 @@ struct StepParams {
     // epilogue stores this instance's Z̃ straight into slot (rank, inst) of EVERY peer's buffer (world = 0: off)
     double* zg[8];
     int zg_world, zg_rank;
-    long zg_base;                    // offset (doubles) of this rank's first row in the current slot: (slot * rows_total + row_offset) * n
-    unsigned long long* zg_flag[8];  // epoch-flag protocol (bmpc_set_gather_flags): peer p's flag array [world]; nullptr: barrier protocol
-    unsigned long long zg_epoch;     // period number this launch publishes (st.release.sys by the last CTA out, after every peer store)
+    long zg_base;                    // offset (doubles) of this launch's first row inside the destination buffer(s)
+    unsigned long long* zg_flag[8];  // pull protocol (bmpc_set_gather_pull): peer p's flag array [2 world] = data epochs, then ack
+                                     // epochs; nullptr: push protocol (bmpc_set_gather, the caller supplies the barrier)
+    unsigned long long zg_epoch;     // period number this launch publishes (st.release.sys by the last CTA out)
+    int zg_pull;                     // 1: Z̃ goes to THIS rank's slot buffer only (zg[zg_rank]); peers pull it over NVLink
+    long long zg_need_ack;           // > 0: slot reuse needs every reader's ack epoch >= this value before the launch may store
+    int* zg_timeout;                 // set to 1 if the ack wait gave up
     // fused observer (SteadyKalmanFilter, kalman.jl:284-309): correct before the step, predict after it.
     // est_on: x̂0 is STATE OF THE HANDLE (xstate, in/out); the corrected estimate used by the step goes to xcorr.
     int est_on, nym;
@@ -141,16 +145,46 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Fused all-gather, epoch-flag protocol: called by ONE thread of the last CTA out, after it has observed every other
-// CTA's arrival (each preceded by a system-scope fence after that CTA's peer stores).  The release store of the period
-// number into slot `rank` of every peer's flag array makes this launch's rows visible to a consumer that acquires it.
+// Fused all-gather, pull protocol: called by ONE thread of the last CTA out, after it has observed every other CTA's
+// arrival (each preceded by a fence after that CTA's stores into this rank's slot buffer).  The release store of the
+// period number into entry `rank` of this rank's OWN flag array makes this launch's rows visible to a reader that acquires
+// it and then loads them over NVLink.
 __device__ __forceinline__ void publish_epoch(const StepParams& P) {
     if (P.zg_world <= 0 || !P.zg_flag[0]) return;
+    if (P.zg_pull) {
+        // pull protocol: the period number goes into THIS rank's own flag array only (entry `rank`); the readers poll
+        // it over NVLink.  The launch never touches remote memory, so nothing has to drain before it can retire.
+        unsigned long long* f = P.zg_flag[P.zg_rank] + P.zg_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.zg_epoch) : "memory");
+        return;
+    }
     __threadfence_system();
     for (int pr = 0; pr < P.zg_world; ++pr) {
         unsigned long long* f = P.zg_flag[pr] + P.zg_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.zg_epoch) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(P.zg_epoch) : "memory");
     }
+}
+
+// Back-pressure of the pull protocol: before a launch overwrites slot (epoch % slots) every reader must have pulled the
+// epoch that lived there (its ack epoch >= zg_need_ack).  Lanes 0..world-1 of ONE warp per CTA spin on the LOCAL ack
+// entries (the readers write them remotely); normally satisfied on the first load.  Gives up after ~2 s.
+__device__ __forceinline__ void gather_wait_acks(const StepParams& P, int lane) {
+    if (P.zg_need_ack <= 0 || !P.zg_flag[P.zg_rank]) return;
+    if (lane < P.zg_world) {
+        const unsigned long long* a = P.zg_flag[P.zg_rank] + P.zg_world + lane;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+            if ((long long)v >= P.zg_need_ack) break;
+            if (clock64() - t0 > 4000000000LL) {
+                *P.zg_timeout = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
 }
 
 // Fw of the custom linear constraints (linconstraint_custom! + linconstraint_custom_outputs!, execute.jl:337-366), in
@@ -1199,6 +1233,8 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
     T.sync();
     uint32_t phase = 0;
 
+    if (threadIdx.x < 32) gather_wait_acks(P, threadIdx.x);
+    __syncthreads();
     for (;;) {
         // ---- fetch the next instance (dynamic scheduling: iteration counts differ) ----
         if (T.tid == 0) *slot = (int)atomicAdd(&P.counters[0], 1u);
@@ -1472,9 +1508,9 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
         jacc = T.sum(jacc) + rconst;
         for (int j = T.tid; j < nz; j += TEAM) gZ[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
         if (neps && T.tid == 0) gZ[nz] = c.x[nz];
-        if (P.zg_world > 0) {  // fused all-gather: peer stores over NVLink
+        if (P.zg_world > 0) {  // fused all-gather: this rank's slot buffer (pull protocol) or peer stores over NVLink (push)
             const long off = P.zg_base + (long)inst * n;
-            for (int pr = 0; pr < P.zg_world; ++pr) {
+            for (int pr = P.zg_pull ? P.zg_rank : 0; pr < (P.zg_pull ? P.zg_rank + 1 : P.zg_world); ++pr) {
                 double* dst = P.zg[pr] + off;
                 for (int j = T.tid; j < nz; j += TEAM) dst[j] = c.x[j] - (j >= nu ? c.x[j - nu] : 0.0);
                 if (neps && T.tid == 0) dst[nz] = c.x[nz];
@@ -1507,7 +1543,7 @@ __global__ void __launch_bounds__(CtaThreads<TEAM>::value, TEAM == 128 ? 6 : ((T
     // ---- reset the work counters for the next launch (last CTA out) ----
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (P.zg_world > 0) __threadfence_system(); else __threadfence();  // this CTA's peer stores before its arrival
+        if (P.zg_world > 0 && !P.zg_pull) __threadfence_system(); else __threadfence();  // this CTA's (peer) stores before its arrival
         const unsigned done = atomicAdd(&P.counters[1], 1u);
         if (done == gridDim.x - 1) {
             P.counters[0] = 0u;

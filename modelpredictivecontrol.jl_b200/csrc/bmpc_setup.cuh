@@ -273,22 +273,85 @@ __global__ void k_make_warp(const double* __restrict__ Pd, long sPd, int nDb, co
     }
 }
 
-// Consumer side: one warp spins (acquire loads) until every rank's flag has reached `epoch`; gives up after `limit`
-// cycles (a rank that died must not hang the device) and reports it in *timed_out.
-__global__ void k_gather_wait(const unsigned long long* flags, int world, unsigned long long epoch, long long limit,
-                              int* timed_out) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
-        if (v >= epoch) break;
-        if (clock64() - t0 > limit) {
-            *timed_out = 1;
-            break;
+// Consumer side of the pull protocol: CTA (p, part) waits until rank p has published `epoch` (acquire on the LOCAL flag
+// entry p), then copies rank p's rows of slot epoch % slots from p's buffer (peer loads over NVLink, 16-byte accesses)
+// into dst rows [row_off[p], row_off[p+1]).  The last CTA out publishes this rank's ack (= epoch) to every peer: the
+// slot may be overwritten.  A one-sided all-gather: no sender-side work beyond the step kernel's own epilogue.
+struct PullParams {
+    const double* src[8];           // every rank's slot buffer [slots x rows_p x n]
+    unsigned long long* flags[8];   // every rank's flag array [2 world]
+    int row_off[9];
+    int world, rank, n, slots, parts;
+    unsigned long long epoch;
+    long long limit;
+    int* timed_out;
+    unsigned int* done;             // CTA counter (zero before the launch, reset by the last CTA)
+};
+__global__ void k_gather_pull(const __grid_constant__ PullParams Q, double* __restrict__ dst) {
+    const int p = blockIdx.x / Q.parts, part = blockIdx.x % Q.parts;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long* f = Q.flags[p] + p;  // rank p's own data epoch, polled over NVLink (p != rank)
+        const long long t0 = clock64();
+        int good = 1;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= Q.epoch) break;
+            if (clock64() - t0 > Q.limit) {
+                *Q.timed_out = 1;
+                good = 0;
+                break;
+            }
+            __nanosleep(200);
         }
-        __nanosleep(64);
+        ok = good;
+    }
+    __syncthreads();
+    if (ok && dst) {
+        const int rows = Q.row_off[p + 1] - Q.row_off[p];
+        const long cnt = (long)rows * Q.n;  // doubles
+        const double* s = Q.src[p] + (long)(Q.epoch % Q.slots) * cnt;
+        double* d = dst + (long)Q.row_off[p] * Q.n;
+        const long per = (((cnt + Q.parts - 1) / Q.parts) + 1) & ~1L;  // even: every part keeps the 16-byte alignment
+        const long lo = min(cnt, part * per), hi = min(cnt, lo + per);
+        const bool al = (((size_t)(s + lo) | (size_t)(d + lo)) & 15) == 0;
+        if (al) {
+            // 16-byte loads, 8 in flight per thread: the copy is one or two NVLink round trips, not a dependent chain
+            const long n2 = (hi - lo) >> 1;
+            const double2* s2 = reinterpret_cast<const double2*>(s + lo);
+            double2* d2 = reinterpret_cast<double2*>(d + lo);
+            const long stride = blockDim.x;
+            for (long i0 = threadIdx.x; i0 < n2; i0 += 8 * stride) {
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long i = i0 + u * stride;
+                    if (i < n2) asm volatile("ld.global.relaxed.sys.v2.f64 {%0, %1}, [%2];" : "=d"(v[u].x), "=d"(v[u].y) : "l"(s2 + i) : "memory");
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long i = i0 + u * stride;
+                    if (i < n2) d2[i] = v[u];
+                }
+            }
+            if (((hi - lo) & 1) && threadIdx.x == 0) d[hi - 1] = s[hi - 1];
+        } else {
+            for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = s[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(Q.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *Q.done = 0u;
+            __threadfence_system();
+            for (int pr = 0; pr < Q.world; ++pr) {  // ack: every rank may reuse the slot of `epoch` as far as this reader goes
+                unsigned long long* a = Q.flags[pr] + Q.world + Q.rank;
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a), "l"(Q.epoch) : "memory");  // (after the fence above)
+            }
+        }
     }
 }
 

@@ -52,6 +52,7 @@ struct WarpParams {
     int* order_next;    // written by this launch: slow instances first
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
     int long_thresh;    // iterations from which an instance counts as slow
+    int static_first;   // 1: the first slot of every CTA is its block index (all CTAs resident), 0: every slot from the counter
     int m;              // inequality rows (without the eps >= 0 row)
     int mD;             // dense rows = positions 0..mD-1; the unit rows follow
     int GR;             // rows of Gw (mD rounded up for the half-warp split and the DMMA k-steps)
@@ -200,20 +201,24 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
     }
     const int up0 = isvar ? Q.upos[lane] : MP, up1 = isvar ? Q.upos[16 + lane] : MP;
 
+    gather_wait_acks(P, lane);
     PCLK_DECL;
     bool first_pass = true;
     for (;;) {
         PCLK(23);
         // work queue: the first instance of every CTA is its block index (no 2368-way atomic storm at launch), the
-        // rest come from the shared counter
+        // rest come from the shared counter.  (A pull kernel of an earlier period can only be resident here while it
+        // waits for a slower peer, i.e. when this rank has slack anyway, so the static first slot stays on with the
+        // fused gather: measured 2-3 us per period better than all-dynamic at 2 GPUs.)
+        const bool static_first = Q.static_first != 0;
         int slot = 0;
-        if (first_pass) {
+        if (first_pass && static_first) {
             slot = (int)blockIdx.x;
-            first_pass = false;
         } else {
-            if (lane == 0) slot = (int)gridDim.x + (int)atomicAdd(&P.counters[0], 1u);
+            if (lane == 0) slot = (static_first ? (int)gridDim.x : 0) + (int)atomicAdd(&P.counters[0], 1u);
             slot = __shfl_sync(WFULL, slot, 0);
         }
+        first_pass = false;
         if (__all_sync(WFULL, slot >= P.N)) break;  // vote: provably warp-uniform branch (no divergent-shuffle paths)
         const int inst = Q.order ? Q.order[slot] : slot;
 
@@ -892,7 +897,11 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
         if (P.zg_world > 0 && lane < nr) {  // fused all-gather of Z̃: peer stores over NVLink (slot (rank, inst) of every peer)
             const double zv = isreal ? x - (lane >= nu ? vx[lane - nu] : 0.0) : x;
             const long off = P.zg_base + (long)inst * nr + lane;
-            for (int pr = 0; pr < P.zg_world; ++pr) P.zg[pr][off] = zv;
+            if (P.zg_pull) {
+                P.zg[P.zg_rank][off] = zv;
+            } else {
+                for (int pr = 0; pr < P.zg_world; ++pr) P.zg[pr][off] = zv;
+            }
         }
         if (isreal) {
             gZ[lane] = x - (lane >= nu ? vx[lane - nu] : 0.0);
@@ -952,7 +961,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
     // ---- reset the work counters for the next launch (last CTA out) ----
     __syncwarp();  // the other lanes' (peer) stores are ordered before lane 0's fence
     if (lane == 0) {
-        if (P.zg_world > 0) __threadfence_system(); else __threadfence();
+        if (P.zg_world > 0 && !P.zg_pull) __threadfence_system(); else __threadfence();
         const unsigned done = atomicAdd(&P.counters[1], 1u);
         if (done == gridDim.x - 1) {
             P.counters[0] = 0u;

@@ -286,42 +286,45 @@ def test_fused_kalman_filter_equals_host_and_oracle(team):
         assert np.abs(P - np.stack([o.Phat for o in okf])).max() < 1e-10 * (1 + np.abs(P).max())
 
 
-def test_fused_gather_epoch_flags_two_handles_uneven_shards():
-    """bmpc_set_gather_flags / bmpc_gather_wait: two handles on one device play ranks 0 and 1 of a world of 2 with UNEVEN
-    shards (5 and 8 controllers): every period each "rank" finds all 13 rows of Z̃ of that period in the slot
-    bmpc_gather_wait names, in both buffers, with no barrier between the launches."""
+def test_fused_gather_pull_two_handles_uneven_shards():
+    """bmpc_set_gather_pull / bmpc_gather_pull: two handles on one device play ranks 0 and 1 of a world of 2 with UNEVEN
+    shards (5 and 8 controllers).  Every period each "rank" pulls all 13 rows of Z̃ of that period -- no barrier between
+    the launches, the flags carry the dependency -- and the ack back-pressure lets only 2 slots suffice."""
     import torch
     from helpers import batch_from_oracle, c1_controllers
     mpcs, plants, rng = c1_controllers(13, seed=21)
     shards = [mpcs[:5], mpcs[5:]]
     bs = [batch_from_oracle(sh) for sh in shards]
-    n, slots, rows = bs[0].n, 3, 13
-    bufs = [torch.zeros((slots, rows, n), dtype=torch.float64, device="cuda") for _ in range(2)]
-    flags = [torch.zeros(8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    n, slots, rows, offs = bs[0].n, 2, 13, [0, 5, 13]
+    bufs = [torch.zeros((slots, b.N, n), dtype=torch.float64, device="cuda") for b in bs]
+    flags = [torch.zeros(4, dtype=torch.int64, device="cuda") for _ in range(2)]
+    dst = [torch.zeros((rows, n), dtype=torch.float64, device="cuda") for _ in range(2)]
     torch.cuda.synchronize()
-    offs = [0, 5]
     for r, b in enumerate(bs):
-        b.set_gather_flags([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], r, offs[r], rows, slots)
+        b.set_gather_pull([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], r, offs, slots)
     nxh = mpcs[0].estim.nxhat
-    for k in range(5):
+    for k in range(6):
         ry = rng.choice([-1.0, 1.0], (13, 2))
         xh = rng.standard_normal((13, nxh)) * 0.3
         Z = []
         for r, b in enumerate(bs):
-            sl = slice(offs[r], offs[r] + b.N)
+            sl = slice(offs[r], offs[r + 1])
             b.step(xh[sl], ry=ry[sl])
             Z.append(b.Ztilde.copy())
         Zall = np.concatenate(Z)
         for r, b in enumerate(bs):
             assert b.gather_epoch() == k + 1
-            slot = b.gather_wait(k + 1)
-            assert slot == (k + 1) % slots and b.gather_timed_out() == 0
-            torch.cuda.synchronize()
-            assert np.array_equal(bufs[r][slot].cpu().numpy(), Zall), (k, r)
+            b.gather_pull(k + 1, dst[r].data_ptr())
+        torch.cuda.synchronize()
+        for r, b in enumerate(bs):
+            assert b.gather_timed_out() == 0
+            assert np.array_equal(dst[r].cpu().numpy(), Zall), (k, r)
+    assert flags[0].cpu().numpy().tolist() == [6, 0, 6, 6]   # rank 0's data epoch, (unused), acks of readers 0 and 1
+    assert flags[1].cpu().numpy().tolist() == [0, 6, 6, 6]
     with pytest.raises(Exception):
-        bs[0].gather_wait(99)  # a period that was never published
+        bs[0].gather_pull(99, dst[0].data_ptr())  # a period that was never published
     with pytest.raises(Exception):
-        bs[0].set_gather_flags([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], 0, 10, rows, slots)  # rows overflow
+        bs[0].set_gather_pull([t.data_ptr() for t in bufs], [t.data_ptr() for t in flags], 0, [0, 4, 13], slots)  # N mismatch
 
 
 def test_create_destroy_does_not_leak_device_memory():
