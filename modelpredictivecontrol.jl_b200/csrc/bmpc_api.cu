@@ -123,7 +123,11 @@ int choose_team(const bmpc_handle* h) {
     if (const char* e = getenv("BMPC_TEAM")) return atoi(e);  // tuning override
     const int n = h->n;
     if (n <= 16) return 16;
-    if (n <= 96) return 128;   // CTA teams: Hessian build on the FP64 tensor pipe (DMMA), several CTAs per SM
+    // CTA teams: Hessian build on the FP64 tensor pipe (DMMA), several CTAs per SM.  Throughput follows the number of
+    // resident instances per SM, which shared memory caps: two warps per instance with the packed Hessian left in L2
+    // (8 CTAs/SM at n = 41) measured 776 k steps/s on C2 against 700 k for four warps with the Hessian staged (6 CTAs/SM)
+    if (n <= 48) return 64;
+    if (n <= 96) return 128;
     return 256;
 }
 
@@ -187,7 +191,7 @@ int configure(bmpc_handle* h) {
     size_t pd_limit = TEAM >= 64 ? 24 * 1024 : 96 * 1024;
     if (const char* e = getenv("BMPC_PD_LIMIT")) pd_limit = (size_t)atol(e);  // tuning override (bytes)
     bool in_smem = h->rt.nDb > 0 && pd_bytes <= pd_limit;
-    bool hv_smem = true;
+    bool hv_smem = TEAM != 64;  // 64-thread teams: residency matters more than the Hessian's latency (see choose_team)
     if (const char* e = getenv("BMPC_HV_SMEM")) hv_smem = atoi(e) != 0;  // tuning override
     for (int attempt = 0; attempt < 3; ++attempt) {
         layout_smem(h, in_smem, hv_smem);

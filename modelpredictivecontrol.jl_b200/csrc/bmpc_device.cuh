@@ -318,9 +318,24 @@ __device__ __forceinline__ int chol_packed(const Team<TEAM>& T, double* A, doubl
                     const double lik = A[pidx(i, k)] * invdk;
                     double* row = A + pidx(i, k + 1);
                     int pj = pidx(k + 1 + tx, k);  // A[k+1+b][k], advanced by TX rows per step
-                    for (int b = tx; b <= a; b += TX) {
-                        row[b] = fma(-lik, A[pj], row[b]);
-                        pj += TX * (k + 1 + b) + TX * (TX + 1) / 2;  // pidx(r+TX,k) - pidx(r,k) with r = k+1+b
+                    // four entries per trip, ALL loads before the first store: `row` and the column alias in A, so a plain
+                    // read-modify-write loop serialises one shared-memory round trip per entry (measured: the update, not the
+                    // barriers, was 80 % of the 1400 cycles per column at n = 41)
+                    for (int b = tx; b <= a; b += 4 * TX) {
+                        double cv[4], rv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int bb = b + u * TX;
+                            const bool ok = bb <= a;
+                            cv[u] = ok ? A[pj] : 0.0;
+                            rv[u] = ok ? row[bb] : 0.0;
+                            pj += TX * (k + 1 + bb) + TX * (TX + 1) / 2;  // pidx(r+TX,k) - pidx(r,k) with r = k+1+bb
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int bb = b + u * TX;
+                            if (bb <= a) row[bb] = fma(-lik, cv[u], rv[u]);
+                        }
                     }
                 }
             }
@@ -677,25 +692,37 @@ __device__ __forceinline__ void gt_apply(const Team<TEAM>& T, const Ctx& c, cons
     if (c.P->neps)
         for (int r = T.tid; r < rt.m; r += TEAM) ce = fma(rt.row_c[r], w[r], ce);
     T.sync();
-    if constexpr (TEAM >= 256) {
-        // long columns (large problems): one warp per column of Pd, lanes stride over the rows (coalesced 256-byte
-        // requests instead of 32 scattered sectors), shuffle reduction; the few sparse rows in a second pass
+    if (TEAM >= 256 || (TEAM >= 64 && !c.P->pd_in_smem)) {
+        // Pd in L1/L2 (long columns, or CTA teams that keep it out of shared memory): one warp per PAIR of columns of Pd,
+        // lanes stride over the rows (coalesced 256-byte requests instead of 32 scattered sectors, up to 8 loads in flight
+        // per lane), shuffle reduction of both sums together; the few sparse rows in a second pass.  (The one-thread-per-
+        // column loop below left 88 of 128 threads idle at n = 41 and walked each column two dependent loads at a time.)
         const int warp = T.tid >> 5, lane = T.tid & 31;
-        for (int j = warp; j < nz; j += TEAM / 32) {
+        constexpr int NW = (TEAM >= 32 ? TEAM / 32 : 1);
+        for (int j = warp; j < nz; j += 2 * NW) {
+            const int j2 = j + NW;
+            const bool two = j2 < nz;
             const double* col = c.Pd + (long)nDb * j;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = lane;
-            for (; k + 96 < nDb; k += 128) {
-                a0 = fma(col[k], c.wd[k], a0);
-                a1 = fma(col[k + 32], c.wd[k + 32], a1);
-                a2 = fma(col[k + 64], c.wd[k + 64], a2);
-                a3 = fma(col[k + 96], c.wd[k + 96], a3);
+            const double* col2 = c.Pd + (long)nDb * (two ? j2 : j);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            for (int k = lane; k < nDb; k += 128) {
+                const bool o1 = k + 32 < nDb, o2 = k + 64 < nDb, o3 = k + 96 < nDb;
+                const double p0 = col[k], p1 = o1 ? col[k + 32] : 0.0, p2 = o2 ? col[k + 64] : 0.0, p3 = o3 ? col[k + 96] : 0.0;
+                const double q0 = col2[k], q1 = o1 ? col2[k + 32] : 0.0, q2 = o2 ? col2[k + 64] : 0.0, q3 = o3 ? col2[k + 96] : 0.0;
+                const double w0 = c.wd[k], w1 = o1 ? c.wd[k + 32] : 0.0, w2 = o2 ? c.wd[k + 64] : 0.0, w3 = o3 ? c.wd[k + 96] : 0.0;
+                a0 = fma(p0, w0, a0); a1 = fma(p1, w1, a1); a2 = fma(p2, w2, a2); a3 = fma(p3, w3, a3);
+                b0 = fma(q0, w0, b0); b1 = fma(q1, w1, b1); b2 = fma(q2, w2, b2); b3 = fma(q3, w3, b3);
             }
-            for (; k < nDb; k += 32) a0 = fma(col[k], c.wd[k], a0);
-            double acc = (a0 + a1) + (a2 + a3);
+            double acc = (a0 + a1) + (a2 + a3), acc2 = (b0 + b1) + (b2 + b3);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) out[j] = acc;
+            for (int o = 16; o > 0; o >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+            }
+            if (lane == 0) {
+                out[j] = acc;
+                if (two) out[j2] = acc2;
+            }
         }
         T.sync();
         for (int j = T.tid; j < nz; j += TEAM) {
@@ -866,25 +893,34 @@ __device__ __forceinline__ void build_phi(const Team<TEAM>& T, const Ctx& c, dou
             const double* pjb = c.Pd + (long)nDb * (ojb ? jb : 0) + ft;
             const bool diag = bi == bj;
             double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
-#pragma unroll 4
-            for (int k0 = 0; k0 < nDb; k0 += 4) {
-                const bool okk = k0 + ft < nDb;
-                const int kk = okk ? k0 : 0;  // clamp (the value is masked)
-                const double w = okk ? c.wd[k0 + ft] : 0.0;
-                const double a0 = (okk && oia) ? pia[kk] : 0.0;
-                const double a1 = (okk && oib) ? pib[kk] : 0.0;
-                double b0, b1;
-                if (diag) {
-                    b0 = a0 * w;
-                    b1 = a1 * w;
-                } else {
-                    b0 = ((okk && oja) ? pja[kk] : 0.0) * w;
-                    b1 = ((okk && ojb) ? pjb[kk] : 0.0) * w;
+            // batches of four k-steps: the 16 (8 on a diagonal block) fragment loads of a batch are all issued before its
+            // first DMMA, so a batch costs ONE L1/L2 round trip (a k-step at a time cost one each: ~780 cycles per k-step
+            // measured with Pd in L2)
+            for (int k0 = 0; k0 < nDb; k0 += 16) {
+                double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ks = k0 + 4 * u;
+                    const bool okk = ks + ft < nDb;
+                    const int kk = okk ? ks : 0;  // clamp (the value is masked)
+                    const double w = okk ? c.wd[kk + ft] : 0.0;
+                    a0[u] = (okk && oia) ? pia[kk] : 0.0;
+                    a1[u] = (okk && oib) ? pib[kk] : 0.0;
+                    if (diag) {
+                        b0[u] = a0[u] * w;
+                        b1[u] = a1[u] * w;
+                    } else {
+                        b0[u] = ((okk && oja) ? pja[kk] : 0.0) * w;
+                        b1[u] = ((okk && ojb) ? pjb[kk] : 0.0) * w;
+                    }
                 }
-                dmma884(c00a, c00b, a0, b0);
-                dmma884(c10a, c10b, a1, b0);
-                dmma884(c11a, c11b, a1, b1);
-                if (!diag) dmma884(c01a, c01b, a0, b1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    dmma884(c00a, c00b, a0[u], b0[u]);
+                    dmma884(c10a, c10b, a1[u], b0[u]);
+                    dmma884(c11a, c11b, a1[u], b1[u]);
+                    if (!diag) dmma884(c01a, c01b, a0[u], b1[u]);
+                }
             }
             // write back the lower-triangle entries this lane holds: rows i = 16bi + 8ti + fg, cols j = 16bj + 8tj + 2ft (+1)
             auto put = [&](int i, int j, double v0, double v1) {

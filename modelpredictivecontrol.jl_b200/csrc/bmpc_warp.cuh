@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
                     const int p = lane + 32 * t;
-                    isR[t] = okR[t] ? __drcp_rn(sR[t]) : 0.0;
+                    isR[t] = okR[t] ? __drcp_rn(okR[t] ? sR[t] : 1.0) : 0.0;  // (a padding row's 0 would send the whole warp through drcp's slow path)
                     dR[t] = lamR[t] * isR[t];
                     w1[p] = lamR[t];
                     w2[p] = dR[t] * rpR[t];
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                             rl = okR[t] ? 1.0 - rs_ : 0.0;  // -dl/lam = 1 + ds/s in the affine step
                         } else {
                             dlR[t] = -(rcR[t] + lamR[t] * dsR[t]) * isR[t];
-                            rl = okR[t] ? -dlR[t] * __drcp_rn(lamR[t]) : 0.0;
+                            rl = okR[t] ? -dlR[t] * __drcp_rn(okR[t] ? lamR[t] : 1.0) : 0.0;
                         }
                         rho = fmax(rho, fmax(rs_, rl));
                         sdd = fma(dsR[t], dlR[t], sdd);

@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 import torch, bench
 W, K = 5, 60
-mpc, model, rec = bench.build_workload(0, W + K)
+mpc, model, rec = bench.build_linmpc("C1", 0, 1, W + K, 0)
 b = mpc.batch; est = mpc.estim; N = 4096
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); b.set_stream(stream.cuda_stream)

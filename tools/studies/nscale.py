@@ -8,7 +8,7 @@ from mpc_b200 import workloads
 for N in [int(a) for a in sys.argv[1:]] or [512, 2368, 4096, 8192, 16384]:
     workloads.CONFIGS["C1"] = (N, 4, 2, 2, 20, 5, 1)
     W, K = 5, 40
-    mpc, model, rec = bench.build_workload(0, W + K)
+    mpc, model, rec = bench.build_linmpc("C1", 0, 1, W + K, 0)
     b = mpc.batch
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); b.set_stream(stream.cuda_stream)

@@ -23,7 +23,7 @@ NAMES = {0: "row weights -> smem", 1: "H x + G'[lam, d rp]", 2: "reduction + con
 for N in [int(a) for a in sys.argv[1:]] or [4096, 296]:
     workloads.CONFIGS["C1"] = (N, 4, 2, 2, 20, 5, 1)
     W, K = 5, 40
-    mpc, model, rec = bench.build_workload(0, W + K)
+    mpc, model, rec = bench.build_linmpc("C1", 0, 1, W + K, 0)
     b = mpc.batch
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); b.set_stream(stream.cuda_stream)

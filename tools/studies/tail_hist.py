@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 import bench
 W, K = 5, 100
-mpc, model, rec = bench.build_workload(0, W + K)
+mpc, model, rec = bench.build_linmpc("C1", 0, 1, W + K, 0)
 b = mpc.batch
 N = rec["iters"].shape[1]
 dev = torch.device("cuda", 0)
