@@ -151,8 +151,6 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.rhs = take(n);
     L.dx = take(n);
     L.invd = take(n);
-    L.F = take(nY);
-    L.tY = take(nY);
     L.fx = take(nx);
     L.yb = take(nDb);
     L.ybd = take(nDb);
@@ -161,9 +159,13 @@ void layout_smem(bmpc_handle* h, bool pd_in_smem, bool hv_in_smem = true) {
     L.lam = take(m);
     L.h = take(m);
     L.rp = take(m);
-    L.t = take(m);
-    L.ds = take(m);
+    L.t = take(std::max(m, nY));
+    L.ds = take(std::max(m, nY));
     L.dl = take(std::max(m, nY));
+    // F and tY live only until the bound vector h and the gradient q are built (stage 1); t and ds only inside the
+    // interior-point solve: they share storage (1.9 KB per instance at C2 = one more resident CTA per SM)
+    L.F = L.ds;
+    L.tY = L.t;
     L.xhat = take(nx);
     L.lastu = take(h->d.nu);
     L.dd = take(h->d.nd);
