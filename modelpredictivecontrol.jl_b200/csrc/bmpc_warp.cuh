@@ -52,6 +52,7 @@ struct WarpParams {
     int* order_next;    // written by this launch: slow instances first
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
     int long_thresh;    // iterations from which an instance counts as slow
+    int l2_prefetch;    // 1: every CTA prefetches into L2 the constants of the instance one queue wave ahead of its own
     int static_first;   // 1: the first slot of every CTA is its block index (all CTAs resident), 0: every slot from the counter
     int m;              // inequality rows (without the eps >= 0 row)
     int mD;             // dense rows = positions 0..mD-1; the unit rows follow
@@ -221,6 +222,10 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
         first_pass = false;
         if (__all_sync(WFULL, slot >= P.N)) break;  // vote: provably warp-uniform branch (no divergent-shuffle paths)
         const int inst = Q.order ? Q.order[slot] : slot;
+        // the instance some CTA will fetch about one instance-time from now (one wave of the queue ahead): its constants are
+        // pulled into L2 below, so that CTA's prologue and TMA copy find them there instead of in HBM
+        const int pslot = slot + (int)gridDim.x;
+        const int pinst = (Q.l2_prefetch && pslot < P.N) ? (Q.order ? Q.order[pslot] : pslot) : -1;
 
         // ---- stage 0: TMA bulk loads of this instance's matrices ----
         const int lv_ok = P.lv_ok[P.sH ? inst : 0];
@@ -323,6 +328,26 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
 #pragma unroll 1
             for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
             finish_row(t, f, gM[t], P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)], gyop[t % ny]);
+        }
+        if (pinst >= 0) {  // (placed after the first use of this instance's own loads: pinst has arrived by now)
+            auto pf = [&](const double* base, long stride, int count) {
+                if (stride == 0 || count <= 0) return;  // shared by all instances: resident anyway
+                const size_t lo = (size_t)(base + (long)pinst * stride), hi = lo + (size_t)count * 8;
+                for (size_t a = (lo & ~(size_t)127) + (size_t)lane * 128; a < hi; a += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            };
+            pf(P.K, P.sK, nY * nx);
+            pf(P.V, P.sV, nY * nu);
+            pf(P.B, P.sB, nY);
+            pf(P.Mw, P.sM, nY);
+            pf(P.dbound, nDr, nDr);
+            pf(P.sbase, nS, nS);
+            if (P.use_ws) pf(P.lam_ws, P.ws_stride, m);
+            if (lane == 0) {
+                const uint32_t bG = (uint32_t)(Q.GR * LDG) * 8u, bH = (uint32_t)(2 * NT * LDH) * 8u;
+                if (Q.sHL) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Q.HL + (long)pinst * Q.sHL), "r"(bH) : "memory");
+                if (Q.sGw && bG) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Q.Gw + (long)pinst * Q.sGw), "r"(bG) : "memory");
+            }
         }
         if (P.has_terminal) {
             const double* gkx = P.kx + (long)inst * P.skx;
@@ -821,7 +846,11 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                             rl = okR[t] ? 1.0 - rs_ : 0.0;  // -dl/lam = 1 + ds/s in the affine step
                         } else {
                             dlR[t] = -(rcR[t] + lamR[t] * dsR[t]) * isR[t];
-                            rl = okR[t] ? -dlR[t] * __drcp_rn(okR[t] ? lamR[t] : 1.0) : 0.0;
+                            // (a padding row's lam = 0 would send the whole warp through drcp's slow path every iteration; the
+                            // empty asm keeps the compiler from folding the guard back into the outer select)
+                            double lden = okR[t] ? lamR[t] : 1.0;
+                            asm volatile("" : "+d"(lden));
+                            rl = okR[t] ? -dlR[t] * __drcp_rn(lden) : 0.0;
                         }
                         rho = fmax(rho, fmax(rs_, rl));
                         sdd = fma(dsR[t], dlR[t], sdd);
