@@ -59,8 +59,16 @@ def init_predmat_mhe(A, Bu, Cm, Bd, Ddm, f, He, direct=True):
 class MovingHorizonEstimator:
     def __init__(self, model, He, i_ym=None, sigmaP_0=None, sigmaQ=None, sigmaR=None, nint_u=0, nint_ym=None,
                  sigmaPint_ym_0=None, sigmaQint_ym=None, Cwt=np.inf, shared_model=False, device=0, max_iter=0,
-                 tol=0.0, direct=True, P0hat=None, Qhat=None, Rhat=None):
+                 tol=0.0, direct=True, P0hat=None, Qhat=None, Rhat=None, transcription="SingleShooting"):
         self.model, self.He, self.direct = model, int(He), bool(direct)
+        # transcription = "MultipleShooting" (MovingHorizonEstimator(...; transcription=MultipleShooting()),
+        # src/estimator/mhe/construct.jl:546): same estimates -- the equality-constrained problem and the condensed one the
+        # kernel solves have the same minimiser --, but `Ztilde` is returned in the reference's MultipleShooting layout
+        # [ε; x̂0(k-Nk+p); X̂0; Ŵ] (get_nZ_mhe, mhe/transcription.jl:3), unused entries zero (fill0unused!, :1084-1090)
+        if transcription not in ("SingleShooting", "MultipleShooting"):
+            raise ValueError("transcription must be 'SingleShooting' or 'MultipleShooting' for a LinModel")
+        self.transcription = transcription
+        self._nk = 0
         self.__dict__.update(augment_model(model, nint_u, nint_ym, i_ym))
         N, nx, nxh = model.N, model.nx, self.nxhat
         self.nym = len(self.i_ym)
@@ -100,13 +108,27 @@ class MovingHorizonEstimator:
                         wmax=np.full((N, nxh), inf), vmin=np.full((N, self.nym), -inf), vmax=np.full((N, self.nym), inf))
         self.soft = dict(c_x=np.zeros(2 * nxh), c_w=np.zeros(2 * nxh), c_v=np.zeros(2 * self.nym))
         self.xhat0 = np.zeros((N, nxh))
-        self.Ztilde = np.zeros((N, self.neps + nxh * (1 + self.He)))
+        self._Zss = np.zeros((N, self.neps + nxh * (1 + self.He)))  # the kernel's (SingleShooting) layout [ε; x̂arr; Ŵ]
         self.J = np.zeros(N)
         self.status = np.zeros(N, dtype=np.int32)
         self.iters = np.zeros(N, dtype=np.int32)
         self.Vhat = np.zeros((N, self.nym * self.He))
         self.X0 = np.zeros((N, nxh * self.He))
         self._solved = False
+
+    @property
+    def Ztilde(self):
+        """The decision vector of the last solve in the reference's layout for the chosen transcription."""
+        if self.transcription == "SingleShooting":
+            return self._Zss
+        N, nxh, He, neps = self.model.N, self.nxhat, self.He, self.neps
+        nk = min(self._nk, He)
+        Z = np.zeros((N, neps + nxh + 2 * nxh * He))
+        nxt = neps + nxh
+        Z[:, :nxt] = self._Zss[:, :nxt]
+        Z[:, nxt:nxt + nxh * nk] = self.X0[:, :nxh * nk]
+        Z[:, nxt + nxh * He:nxt + nxh * He + nxh * nk] = self._Zss[:, nxt:nxt + nxh * nk]
+        return Z
 
     def close(self):
         if self._h:
@@ -149,7 +171,7 @@ class MovingHorizonEstimator:
 
     def _io(self):
         p32 = lambda a: a.ctypes.data_as(_lib.c_int32_p)
-        return [dptr(self.xhat0), dptr(self.Ztilde), dptr(self.J), p32(self.status), p32(self.iters), dptr(self.Vhat),
+        return [dptr(self.xhat0), dptr(self._Zss), dptr(self.J), p32(self.status), p32(self.iters), dptr(self.Vhat),
                 dptr(self.X0)]
 
     def _dev(self, ym, d):
@@ -165,6 +187,7 @@ class MovingHorizonEstimator:
         check(_lib.lib().bmhe_correct(self._h, dptr(y0m), dptr(d0) if d0 is not None else None, *self._io()))
         if self.direct:
             self._solved = True
+            self._nk += 1
         return self.xhat0 + self.xophat
 
     def updatestate(self, u, ym=None, d=None):
@@ -179,8 +202,10 @@ class MovingHorizonEstimator:
             check(_lib.lib().bmhe_update_solve(self._h, dptr(u0), dptr(y0m), dptr(d0) if d0 is not None else None,
                                                *self._io()))
             self._solved = True
+            self._nk += 1
         return self.xhat0 + self.xophat
 
     def reset(self):
         check(_lib.lib().bmhe_reset(self._h))
+        self._nk = 0
         self.xhat0[:] = 0

@@ -258,3 +258,29 @@ def test_mhe_dense_covariances_match_oracle():
         g.updatestate(u, y)
     assert nact > 5
     print("MHE dense covariances worst", worst, "active solves", nact)
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_mhe_multiple_shooting_layout_matches_ms_oracle(direct):
+    """MovingHorizonEstimator(...; transcription=MultipleShooting()) (test/2_test_state_estim.jl:1126-1139): the handle
+    solves the condensed problem, the host mirror returns Z̃ = [x̂0(k-Nk+p); X̂0; Ŵ] in the reference's MultipleShooting
+    layout.  Checked against oracle/mhe_ms.py, which solves the equality-constrained problem (defect constraints) by a
+    generic null-space method: estimate, the whole Z̃ (stage states included, unused entries zero) and J, over the
+    growing and the moving window, with state / noise bounds active."""
+    import mpc_b200
+    from oracle.mhe_ms import MovingHorizonEstimatorMS as OMS
+    N, He = 5, 4
+    gm, oms, rng = make(N, 6, nd=1)
+    # soft bounds: every window stays feasible.  (On an INFEASIBLE window the reference's fallback differs by transcription
+    # -- MultipleShooting keeps the shifted stage states of the previous solution, transcription.jl:1037-1076 --, while the
+    # handle always returns the open-loop rebuild of the SingleShooting fallback: documented divergence, DESIGN.md section 8.)
+    kw = dict(xhatmin=[-0.6] * 3, xhatmax=[0.6] * 3, whatmin=[-0.3] * 3, whatmax=[0.3] * 3,
+              vhatmin=[-2.5] * 2, vhatmax=[2.5] * 2, c_xhatmin=[1] * 3, c_xhatmax=[1] * 3, c_whatmin=[1] * 3,
+              c_whatmax=[1] * 3, c_vhatmin=[1] * 2, c_vhatmax=[1] * 2)
+    g = mpc_b200.MovingHorizonEstimator(gm, He=He, nint_ym=[0, 0], direct=direct, Cwt=1e5,
+                                        transcription="MultipleShooting").setconstraint(**kw)
+    os_ = [OMS(m, He=He, nint_ym=0, direct=direct, Cwt=1e5).setconstraint(**kw) for m in oms]
+    assert g.Ztilde.shape == (N, 1 + 3 + 2 * 3 * He) and os_[0].Ztilde.shape == (1 + 3 + 2 * 3 * He,)
+    worst, nact = run_both(g, os_, rng, 2 * He + 3, 1, 2, 2, tol_active=2e-6)
+    assert nact > 10
+    print("MHE MultipleShooting worst", worst, "active solves", nact)
