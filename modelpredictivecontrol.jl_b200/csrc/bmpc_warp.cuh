@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 sDh[k] = P.Dhat0 ? P.Dhat0[(long)inst * nd * P.Hp + k] : P.d0[(long)inst * nd + (k % nd)];
         }
         __syncwarp();
+        PCLK(18);
         if (__any_sync(WFULL, P.est_on != 0)) skf_correct(P, inst, lane, 32, sxh, sd0, smem + L.ev, [] { __syncwarp(); });
         double racc = 0.0;
         // measured-disturbance terms and the bookkeeping every prediction row shares
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             for (int k = 0; k < nu; ++k) f = fma(gV[t + (long)nY * k], slu[k], f);
             finish_row(t, f, gM[t], P.Rhat_y ? P.Rhat_y[(long)inst * nY + t] : P.ry[(long)inst * ny + (t % ny)], gyop[t % ny]);
         }
+        PCLK(19);
         if (pinst >= 0) {  // (placed after the first use of this instance's own loads: pinst has arrived by now)
             auto pf = [&](const double* base, long stride, int count) {
                 if (stride == 0 || count <= 0) return;  // shared by all instances: resident anyway
@@ -376,6 +378,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             custom_fw(P, inst, lane, 32, sxh, slu, sd0, sDh, sF, smem + L.Fw);
             __syncwarp();
         }
+        PCLK(20);
         // ---- linconstraint!  (transcription.jl:811-848): right-hand sides of this lane's rows ----
         double hR[RPL], sR[RPL], lamR[RPL];
         double hmax = 0.0;
