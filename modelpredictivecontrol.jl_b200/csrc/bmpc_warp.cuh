@@ -227,6 +227,10 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
         const int pslot = slot + (int)gridDim.x;
         const int pinst = (Q.l2_prefetch && pslot < P.N) ? (Q.order ? Q.order[pslot] : pslot) : -1;
 
+#ifdef BMPC_PHASE_CLK
+        if (inst < 0) break;  // (consumes `inst`: the clock below then reads after the order entry has arrived)
+#endif
+        PCLK(21);
         // ---- stage 0: TMA bulk loads of this instance's matrices ----
         const int lv_ok = P.lv_ok[P.sH ? inst : 0];
         if (lane == 0) {
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             rypre[h] = okt ? (P.Rhat_y ? P.Rhat_y[(long)inst * nY + tc] : P.ry[(long)inst * ny + (tc % ny)]) : 0.0;
             yoppre[h] = okt ? gyop[tc % ny] : 0.0;
         }
+        PCLK(22);
         if (lane < nx) sxh[lane] = pxh;
         for (int k = lane + 32; k < nx; k += 32) sxh[k] = gxh[(long)inst * nx + k];
         if (lane < nu) slu[lane] = plu;

@@ -18,7 +18,7 @@ NAMES = {0: "row weights -> smem", 1: "H x + G'[lam, d rp]", 2: "reduction + con
          4: "Cholesky", 5: "factor rows -> smem -> columns", 6: "solve (predictor)", 7: "G dx, step lengths, reduction (pred)",
          8: "corrector rhs G'w", 9: "solve (corrector)", 10: "G dx, step lengths, reduction (corr)", 11: "update x, s, lam (loop tail)",
          12: "stage 1 (initpred!, linconstraint!)", 13: "wait for the TMA copy", 14: "q, unconstrained exit, feasibility",
-         15: "IPM start (incl. warm start)", 16: "loop exit", 17: "stage 4 (getinput!, outputs)", 23: "work-queue fetch", 18: "stage 1a: prologue loads arrive (x̂0, u, Z̃, bounds, K/V columns)", 19: "stage 1b: prediction rows F, tY", 20: "stage 1c: L2 prefetch / terminal / custom rows", 12: "stage 1d: linconstraint! (h, q weights)"}
+         15: "IPM start (incl. warm start)", 16: "loop exit", 17: "stage 4 (getinput!, outputs)", 23: "work-queue fetch", 21: "stage 0a: order entry -> instance index", 22: "stage 0b: TMA issue + prologue loads issued", 18: "stage 1a: prologue loads arrive (x̂0, u, Z̃, bounds, K/V columns)", 19: "stage 1b: prediction rows F, tY", 20: "stage 1c: L2 prefetch / terminal / custom rows", 12: "stage 1d: linconstraint! (h, q weights)"}
 
 for N in [int(a) for a in sys.argv[1:]] or [4096, 296]:
     workloads.CONFIGS["C1"] = (N, 4, 2, 2, 20, 5, 1)
@@ -55,6 +55,6 @@ for N in [int(a) for a in sys.argv[1:]] or [4096, 296]:
     print(f"  cycles per IPM iteration: {it_tot / nit:.0f}   per instance outside the loop: {(sum(clk[12:24])) / ninst:.0f}")
     for i in range(12):
         print(f"    [{i:2d}] {NAMES[i]:45s} {clk[i] / nit:8.0f} cycles/iteration  {100 * clk[i] / it_tot:5.1f} %")
-    for i in (23, 18, 19, 20, 12, 13, 14, 15, 16, 17):
+    for i in (23, 21, 22, 18, 19, 20, 12, 13, 14, 15, 16, 17):
         print(f"    [{i:2d}] {NAMES[i]:45s} {clk[i] / ninst:8.0f} cycles/instance")
     b.close()
