@@ -283,15 +283,18 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     bmpc::WarpLayout& L = h->wp.L;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += even(std::max(cnt, 1)); return at; };
-    L.G = take(GR * E.ldg);
+    // (the arrays up to G sit at the compile-time offsets of WarpSmem<NT, RPL>, bmpc_warp.cuh)
     L.H = take(NT * E.ldh);
     L.L = take(NT * E.ldh);
     L.phi = take(std::max((8 * ((NT + 7) / 8) + 1) * E.ldp, 2 * NT * E.ldn));  // DMMA C tiles + the rhs row, then the columns of L and of M
     L.vx = take(16);
     L.vy = take(16);
+    take(16);             // reciprocal pivots (WarpSmem::DV)
     L.w1 = take(MP + 2);  // (+ the "no unit row" slot that reads as zero)
     L.w2 = take(MP + 2);
     L.wd = take(MP + 2);
+    L.G = take(GR * E.ldg);
+    if (L.G != E.off_g) return fail(BMPC_ERR_CUDA, "warp kernel shared-memory layout mismatch (G at %d, kernel expects %d)", L.G, E.off_g);
     // F and M*Cy are dead before the interior-point loop first writes wd / w2: share the storage when they fit
     if (nY <= MP) {
         L.F = L.wd;

@@ -70,6 +70,27 @@ struct WarpDims {
     static constexpr int LDP = 8 * NB + 2;
 };
 
+// Shared-memory offsets (doubles) of the arrays the interior-point loop touches: compile-time constants, so their
+// addresses are immediates instead of a constant-bank load + LEA at every use (the host lays the CTA out in the same
+// order, configure_warp in bmpc_api.cu, and checks G against WarpEntry::off_g).  The per-instance sized arrays follow G.
+template <int NT, int RPL>
+struct WarpSmem {
+    using D = WarpDims<NT>;
+    static constexpr int even_(int v) { return (v + 1) & ~1; }
+    static constexpr int MP = 32 * RPL;
+    static constexpr int H = 0;
+    static constexpr int L = H + NT * D::LDH;  // (H and its factor are one TMA copy)
+    static constexpr int PHI = L + NT * D::LDH;
+    static constexpr int PHI_SZ = even_((8 * D::NB + 1) * D::LDP > 2 * NT * D::LDN ? (8 * D::NB + 1) * D::LDP : 2 * NT * D::LDN);
+    static constexpr int VX = PHI + PHI_SZ;
+    static constexpr int VY = VX + 16;
+    static constexpr int DV = VY + 16;  // reciprocal pivots of the factorisation
+    static constexpr int W1 = DV + 16;
+    static constexpr int W2 = W1 + MP + 2;
+    static constexpr int WD = W2 + MP + 2;
+    static constexpr int G = WD + MP + 2;
+};
+
 constexpr unsigned WFULL = 0xffffffffu;
 
 // Study builds (-DBMPC_PHASE_CLK, tools/studies/phase_clk.py): lane 0 accumulates the cycles spent between marks.
@@ -98,6 +119,16 @@ __device__ __forceinline__ double wmin(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(WFULL, v, o));
     return v;
 }
+// 1/d without the rounding guarantees (and the slow path) of __drcp_rn: the hardware seed (MUFU.RCP64H, ~20 bits) and
+// ONE third-order step r (1 + e + e^2), e = 1 - d r: three dependent DFMAs instead of four plus fix-up code, relative
+// error e^3 < 1e-17 before rounding (a few ulp).  For positive normal d only (0 / denormals give Inf / NaN): every
+// caller guards its argument.
+__device__ __forceinline__ double rcp_fast(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
 // three maxima and one sum in ONE butterfly (the shuffles of the four values overlap).  The maxima feed thresholds
 // and scale estimates only: they are reduced in fp32 (one shuffle + one FMNMX each, rounded UP so that a convergence
 // test can only become stricter); the sum stays fp64.
@@ -109,6 +140,18 @@ __device__ __forceinline__ float wmax_nonneg_f32(float v) {
 }
 __device__ __forceinline__ void wred_mmms(double& a, double& b, double& c, double& s) {
     const float fa = wmax_nonneg_f32(f32_up(a)), fb = wmax_nonneg_f32(f32_up(b)), fc = wmax_nonneg_f32(f32_up(c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(WFULL, s, o);
+    a = (double)fa;
+    b = (double)fb;
+    c = (double)fc;
+}
+// same with the lane-local maxima already in fp32 (rounded up value by value: rounding is monotone, so the result is
+// the one above bit for bit, without fp64 maximum sequences on the way)
+__device__ __forceinline__ void wred_mmms_f(float fa, float fb, float fc, double& a, double& b, double& c, double& s) {
+    fa = wmax_nonneg_f32(fa);
+    fb = wmax_nonneg_f32(fb);
+    fc = wmax_nonneg_f32(fc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(WFULL, s, o);
     a = (double)fa;
@@ -146,15 +189,16 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
     const int nz = P.nz, nr = P.n;  // real sizes: move variables, move variables + slack
     const int nY = P.nY, nu = P.nu, ny = P.ny, nx = P.nx, nd = P.nd;
     const int nS = P.rt.nS, nDr = P.rt.nDr, m = Q.m, mD = Q.mD;
-    double* sG = smem + L.G;
-    double* sH = smem + L.H;
-    double* sL = smem + L.L;
-    double* sPhi = smem + L.phi;  // C tiles of Phi (+ the rhs row), then the factor's columns, then W = D^-1 L^-1
-    double* vx = smem + L.vx;
-    double* vy = smem + L.vy;
-    double* w1 = smem + L.w1;
-    double* w2 = smem + L.w2;
-    double* wd = smem + L.wd;
+    using SM = WarpSmem<NT, RPL>;
+    double* sG = smem + SM::G;
+    double* sH = smem + SM::H;
+    double* sL = smem + SM::L;
+    double* sPhi = smem + SM::PHI;  // C tiles of Phi (+ the rhs row), then the factor's columns
+    double* vx = smem + SM::VX;
+    double* vy = smem + SM::VY;
+    double* w1 = smem + SM::W1;
+    double* w2 = smem + SM::W2;
+    double* wd = smem + SM::WD;
     double* sF = smem + L.F;
     double* stY = smem + L.tY;
     double* sfx = smem + L.fx;
@@ -622,21 +666,22 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             double rpR[RPL];
 #pragma unroll
             for (int t = 0; t < RPL; ++t) rpR[t] = okR[t] ? gx[t] + sR[t] - hR[t] : 0.0;
-            const double inv_tol_p = 1.0 / (P.tol * hscale), inv_tol_mu = 1.0 / (P.tol_mu * qs * hscale);
+            const double inv_tol = 1.0 / P.tol, inv_tol_p = 1.0 / (P.tol * hscale), inv_tol_mu = 1.0 / (P.tol_mu * qs * hscale);
             PCLK(15);
             for (int it = 0; it <= P.max_iter; ++it) {
                 PCLK(11);
                 double dR[RPL], isR[RPL];
                 double e_p = 0.0, musum = 0.0;
+                float e_pf = 0.f;
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
                     const int p = lane + 32 * t;
-                    isR[t] = okR[t] ? __drcp_rn(okR[t] ? sR[t] : 1.0) : 0.0;  // (a padding row's 0 would send the whole warp through drcp's slow path)
+                    isR[t] = okR[t] ? rcp_fast(okR[t] ? sR[t] : 1.0) : 0.0;  // (a padding row's s = 0 has no reciprocal)
                     dR[t] = lamR[t] * isR[t];
                     w1[p] = lamR[t];
                     w2[p] = dR[t] * rpR[t];
                     wd[p] = dR[t];
-                    e_p = fmax(e_p, fabs(rpR[t]));
+                    e_pf = fmaxf(e_pf, f32_up(fabs(rpR[t])));
                     musum = fma(sR[t], lamR[t], musum);
                 }
                 __syncwarp();
@@ -651,19 +696,20 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 }
                 PCLK(1);
                 const double rd = Hxq + Gtl;
-                double e_d = fabs(rd), dsc = fmax(fabs(Hxq), fabs(Gtl));
-                wred_mmms(e_d, dsc, e_p, musum);
+                double e_d, dsc;
+                wred_mmms_f(f32_up(fabs(rd)), fmaxf(f32_up(fabs(Hxq)), f32_up(fabs(Gtl))), e_pf, e_d, dsc, e_p, musum);
                 const double qd = qs + dsc;  // scale of the dual residual's terms
                 const double mu = musum * minv;
+                const double imu = rcp_fast(fmax(mu, 1e-300));  // (needed after the affine step: off its dependent chain)
                 rp_inf = e_p;
                 if (__any_sync(WFULL, !(e_d == e_d) || !(e_p == e_p) || !(mu == mu) || e_d > 1e250 || e_p > 1e250)) {
                     status = ST_INFEASIBLE;
                     break;
                 }
                 // (the scales of the primal residual and of the gap are loop invariants: multiplications, one reciprocal)
-                const double merit = fmax(fmax(e_d * __drcp_rn(P.tol * qd), e_p * inv_tol_p), musum * inv_tol_mu);
+                kk1 = e_d * rcp_fast(qd);  // (qd >= 1)
+                const double merit = fmax(fmax(kk1 * inv_tol, e_p * inv_tol_p), musum * inv_tol_mu);
                 kk0 = e_p * inv_tol_p * P.tol;
-                kk1 = e_d * __drcp_rn(qd);
                 kk2 = musum * inv_tol_mu * P.tol_mu;
                 if (__any_sync(WFULL, merit <= 1.0 || (best_merit <= 1e3 && merit >= best_merit) ||
                                               (it == P.max_iter && merit <= 1e3))) {
@@ -749,14 +795,9 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                         phi[2 * jj + 1] = p2.y;
                     }
                 }
-                double pdiag = 0.0;
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    if (j == lane) {
-                        phi[j] += dunit;
-                        pdiag = phi[j];
-                    }
-                }
+                // this lane's pivot; the diagonal entry of its register row is never read (the column updates only use the
+                // entries below the diagonal), so the unit rows' term goes into the pivot alone
+                double pdiag = sPhi[(lane < NT ? lane : 0) * (LDP + 1)] + dunit;
                 __syncwarp();
                 PCLK(3);
                 // ---- Cholesky: right-looking, rows in registers; column k goes through shared memory (one store, then
@@ -764,35 +805,37 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 // (unit diagonal) is kept in shared memory, column k contiguous, for the substitutions: they then run on
                 // raw broadcasts, without a multiply by 1/L_jj on their dependent chains, and nothing of the factor stays
                 // in registers during the row phases ----
-                double invd = 1.0;
+                // (LDL' form: column k travels through shared memory UNSCALED, so its store, the warp barrier and the
+                // broadcast loads are issued while the pivot's reciprocal is still in flight; M = L D^-1 entries above and
+                // on the diagonal are stored as zeros, so the substitutions below need no selects)
                 double* colbuf = sPhi;
                 double* mbuf = sPhi + NT * LDN;
+                double* dinv = smem + SM::DV;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) {
-                    const double dk = bcast(pdiag, k);
-                    // guarded pivot (non-positive or NaN -> huge pivot = the variable is frozen); the test runs beside the
-                    // reciprocal square root, not before it
-                    const double rs = (dk > 1e-280) ? rsqrt(dk) : 1e-100;
-                    // column k of L.  Lanes <= k (and the idle lanes) compute finite-or-NaN garbage here: it only ever
-                    // lands in their own upper-triangle entries and spent pivots, which nothing reads.
-                    const double lik = phi[k] * rs;
-                    if (lane == k) invd = rs;
-                    pdiag = fma(-lik, lik, pdiag);
-                    const double mik = lik * rs;
-                    if (lane < NT) {
-                        if (k + 1 < NT) colbuf[k * LDN + lane] = lik;
-                        mbuf[k * LDN + lane] = mik;
-                    }
+                    const double uk = phi[k];
                     if (k + 1 < NT) {
+                        if (lane < NT) colbuf[k * LDN + lane] = uk;
                         __syncwarp();
+                    }
+                    const double dk = bcast(pdiag, k);
+                    // guarded pivot (non-positive or NaN -> huge pivot = the variable is frozen)
+                    const double rk = (dk > 1e-280) ? rcp_fast(dk > 1e-280 ? dk : 1.0) : 1e-200;
+                    // column k of M.  Lanes <= k (and the idle lanes) compute finite-or-NaN garbage here: it only ever
+                    // lands in their own upper-triangle entries and spent pivots, which nothing reads.
+                    const double mik = uk * rk;
+                    dinv[k] = rk;  // (same value from every lane)
+                    pdiag = fma(-mik, uk, pdiag);
+                    if (lane < NT) mbuf[k * LDN + lane] = lane > k ? mik : 0.0;
+                    if (k + 1 < NT) {
 #pragma unroll
                         for (int jp = (k + 1) / 2; jp <= (NT - 1) / 2; ++jp) {
                             const double2 c2 = *reinterpret_cast<const double2*>(colbuf + k * LDN + 2 * jp);
-                            if (2 * jp > k) phi[2 * jp] = fma(-lik, c2.x, phi[2 * jp]);
-                            if (2 * jp + 1 < NT) phi[2 * jp + 1] = fma(-lik, c2.y, phi[2 * jp + 1]);
+                            if (2 * jp > k) phi[2 * jp] = fma(-mik, c2.x, phi[2 * jp]);
+                            if (2 * jp + 1 < NT) phi[2 * jp + 1] = fma(-mik, c2.y, phi[2 * jp + 1]);
                         }
                     }
-                    phi[k] = mik;  // (the rhs lane ends up with z = D^-2 M^-1 rhs: its forward substitution came for free)
+                    phi[k] = mik;  // (the rhs lane ends up with z = D^-1 M^-1 rhs: its forward substitution came for free)
                 }
                 PCLK(4);
                 if (lane == NT) {
@@ -801,14 +844,14 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 }
                 __syncwarp();
                 const double z0 = isvar ? vy[iv] : 0.0;
+                const double invd2 = dinv[iv];  // 1 / d_lane
                 PCLK(5);
                 // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b.  Row `lane` / column `lane` of M are re-read from
                 // shared memory at every sweep (independent loads, issued ahead of the dependent shuffle + FMA chain)
-                const double invd2 = invd * invd;
                 auto solve_fwd = [&](double b) -> double {
                     double mr[NT];
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) mr[j] = (lane > j && isvar) ? mbuf[j * LDN + iv] : 0.0;
+                    for (int j = 0; j < NT; ++j) mr[j] = mbuf[j * LDN + iv];  // (zero for j >= lane and on the idle lanes: row 0)
 #pragma unroll
                     for (int j = 0; j < NT; ++j) b = fma(-mr[j], bcast(b, j), b);  // M^-1 (unit lower)
                     return b * invd2;
@@ -819,8 +862,8 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
 #pragma unroll
                     for (int jp = 0; jp < NV2; ++jp) {
                         const double2 c2 = ccol[jp];
-                        mc[2 * jp] = (lane < 2 * jp) ? c2.x : 0.0;
-                        mc[2 * jp + 1] = (lane < 2 * jp + 1) ? c2.y : 0.0;
+                        mc[2 * jp] = c2.x;  // (zero for rows <= lane; the idle lanes read column 0 and are masked below)
+                        mc[2 * jp + 1] = c2.y;
                     }
 #pragma unroll
                     for (int j = NT - 1; j >= 0; --j) b = fma(-mc[j], bcast(b, j), b);  // M'^-1 (unit upper)
@@ -842,7 +885,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                     if (lane < 16) vx[lane] = dx;
                     __syncwarp();
                     row_products(gx);
-                    rho = 0.0;  // max over rows of -ds/s and -dl/lambda (step to the boundary = 1/rho)
+                    float rhof = 0.f;  // max over rows of -ds/s and -dl/lambda (step to the boundary = 1/rho), rounded up
                     double sdd = 0.0;  // sum ds*dl
 #pragma unroll
                     for (int t = 0; t < RPL; ++t) {
@@ -858,23 +901,20 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                             // empty asm keeps the compiler from folding the guard back into the outer select)
                             double lden = okR[t] ? lamR[t] : 1.0;
                             asm volatile("" : "+d"(lden));
-                            rl = okR[t] ? -dlR[t] * __drcp_rn(lden) : 0.0;
+                            rl = okR[t] ? -dlR[t] * rcp_fast(lden) : 0.0;
                         }
-                        rho = fmax(rho, fmax(rs_, rl));
+                        rhof = fmaxf(rhof, fmaxf(f32_up(rs_), f32_up(rl)));
                         sdd = fma(dsR[t], dlR[t], sdd);
                     }
-                    if (pass == 0) {
-                        wred_ms(rho, sdd);
-                    } else {
-                        rho = (double)wmax_nonneg_f32(f32_up(rho));  // (the sum is only needed after the affine step)
-                    }
+                    rho = (double)wmax_nonneg_f32(rhof);
+                    if (pass == 0) sdd = wsum(sdd);  // (the sum is only needed after the affine step)
                     PCLK(7 + 3 * pass);
                     if (pass == 0) {
                         // affine step: s*dl + lam*ds = -s*lam exactly, so
                         //   sum (s + a ds)(lam + a dl) = (1 - a) sum s*lam + a^2 sum ds*dl   -- no second reduction
-                        const double a_aff = rho > 1.0 ? __drcp_rn(rho) : 1.0;
+                        const double a_aff = rho > 1.0 ? rcp_fast(rho) : 1.0;
                         const double mua = fmax(((1.0 - a_aff) * musum + a_aff * a_aff * sdd) * minv, 0.0);
-                        ratio = mua * __drcp_rn(mu);
+                        ratio = mua * imu;
                         const double sig = ratio * ratio * ratio;
 #pragma unroll
                         for (int t = 0; t < RPL; ++t) {
@@ -889,7 +929,7 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 }
                 // fraction to the boundary: 0.99, tending to 1 as the affine step closes the gap
                 const double tau = fmin(fmax(0.99, 1.0 - ratio), 1.0 - 1e-6);  // never exactly onto the boundary
-                const double a = rho > tau ? tau * __drcp_rn(rho) : 1.0;
+                const double a = rho > tau ? tau * rcp_fast(rho) : 1.0;
                 // infeasibility: two collapsed steps with the primal residual still open end the solve (ipm_solve,
                 // bmpc_device.cuh)
                 stall = (a < 1e-8 && rp_inf > 1e-6 * hscale) ? stall + 1 : 0;

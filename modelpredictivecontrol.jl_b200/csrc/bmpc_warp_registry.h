@@ -14,6 +14,7 @@ typedef cudaError_t (*WarpLaunchFn)(const StepParams&, const WarpParams&, int gr
 
 struct WarpEntry {
     int nt, rpl, ldg, ldh, ldn, ldp;
+    int off_g;  // WarpSmem<NT, RPL>::G: where the kernel expects the dense rows (the arrays before it have fixed offsets)
     WarpLaunchFn launch;
     const void* func;  // kernel symbol, for cudaFuncSetAttribute / occupancy queries
 };
@@ -27,7 +28,7 @@ cudaError_t warp_launch(const StepParams& P, const WarpParams& Q, int grid, int 
 template <int NT, int RPL>
 WarpEntry warp_entry() {
     using D = WarpDims<NT>;
-    return WarpEntry{NT, RPL, D::LDG, D::LDH, D::LDN, D::LDP, &warp_launch<NT, RPL>,
+    return WarpEntry{NT, RPL, D::LDG, D::LDH, D::LDN, D::LDP, WarpSmem<NT, RPL>::G, &warp_launch<NT, RPL>,
                      reinterpret_cast<const void*>(&step_warp<NT, RPL>)};
 }
 
