@@ -846,14 +846,21 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                 const double z0 = isvar ? vy[iv] : 0.0;
                 const double invd2 = dinv[iv];  // 1 / d_lane
                 PCLK(5);
-                // Phi = M D^2 M' with D = diag(L):  x = M'^-1 D^-2 M^-1 b.  Row `lane` / column `lane` of M are re-read from
-                // shared memory at every sweep (independent loads, issued ahead of the dependent shuffle + FMA chain)
+                // Phi = M D M':  x = M'^-1 D^-1 M^-1 b.  Row `lane` / column `lane` of M are re-read from shared memory at every
+                // sweep (independent loads, issued ahead of the dependent shuffle + FMA chain).  A sweep advances TWO variables
+                // per step: both raw entries of a column pair are broadcast at once and every lane finishes the second one
+                // itself with the pair's coupling entry M[2b+1][2b] -- NT/2 dependent steps of (broadcasts, 2 FMAs), the same
+                // operations in the same order as a one-variable-per-step sweep
                 auto solve_fwd = [&](double b) -> double {
                     double mr[NT];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) mr[j] = mbuf[j * LDN + iv];  // (zero for j >= lane and on the idle lanes: row 0)
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) b = fma(-mr[j], bcast(b, j), b);  // M^-1 (unit lower)
+                    for (int k = 0; k + 1 < NT; k += 2) {  // M^-1 (unit lower); the last column of an odd NT has no entries
+                        const double y1 = bcast(b, k), b2 = bcast(b, k + 1);
+                        const double y2 = fma(-mbuf[k * LDN + k + 1], y1, b2);
+                        b = fma(-mr[k + 1], y2, fma(-mr[k], y1, b));
+                    }
                     return b * invd2;
                 };
                 auto solve_back = [&](double b) -> double {
@@ -865,8 +872,13 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
                         mc[2 * jp] = c2.x;  // (zero for rows <= lane; the idle lanes read column 0 and are masked below)
                         mc[2 * jp + 1] = c2.y;
                     }
+                    if (NT & 1) b = fma(-mc[NT - 1], bcast(b, NT - 1), b);  // (the last column of an odd NT is on its own)
 #pragma unroll
-                    for (int j = NT - 1; j >= 0; --j) b = fma(-mc[j], bcast(b, j), b);  // M'^-1 (unit upper)
+                    for (int k = (NT & ~1) - 2; k >= 0; k -= 2) {  // M'^-1 (unit upper)
+                        const double x2 = bcast(b, k + 1), b1 = bcast(b, k);
+                        const double x1 = fma(-mbuf[k * LDN + k + 1], x2, b1);
+                        b = fma(-mc[k], x1, fma(-mc[k + 1], x2, b));
+                    }
                     return isvar ? b : 0.0;
                 };
                 // ---- predictor (pass 0) and corrector (pass 1) share one copy of the code ----
