@@ -365,7 +365,12 @@ int configure_warp(bmpc_handle* h, const bmpc::WarpEntry& E) {
     CK(cudaMemsetAsync(h->clk.p, 0, 32 * sizeof(long long), h->stream));
     h->wp.clk = h->clk.p;
 #endif
-    h->wp.long_thresh = 12;  // (measured: 7 / 9 / 12 -> 0.1719 / 0.1721 / 0.1686 ms on C1)
+    // Next launch's order.  Every instance is filed from the BACK of the list as it completes, so the next launch starts
+    // the instances in reverse completion order -- the ones that finished last (the long solves, which stay long from one
+    // period to the next) start first: longest-processing-time-first scheduling without a sort.  BMPC_LONG = t restores
+    // the two-class variant (>= t iterations to the front, the rest to the back); measured on C1 with the round-2 kernel
+    // (tools/studies/env_sweep.sh, same box): t = 12 0.1418-0.1429 ms, 14 0.1404, 18 0.1398, none (this default) 0.1397
+    h->wp.long_thresh = 1 << 30;
     if (const char* e = getenv("BMPC_LONG")) h->wp.long_thresh = atoi(e);
     CK(cudaStreamSynchronize(h->stream));  // (the host vectors uploaded above go out of scope)
     return BMPC_OK;

@@ -51,7 +51,7 @@ struct WarpParams {
     const int* order;   // processing order of this launch (nullptr: 0..N-1)
     int* order_next;    // written by this launch: slow instances first
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
-    int long_thresh;    // iterations from which an instance counts as slow
+    int long_thresh;    // iterations from which an instance is filed at the front of order_next (default: never)
     int l2_prefetch;    // 1: every CTA prefetches into L2 the constants of the instance one queue wave ahead of its own
     int static_first;   // 1: the first slot of every CTA is its block index (all CTAs resident), 0: every slot from the counter
     int m;              // inequality rows (without the eps >= 0 row)
@@ -1032,7 +1032,8 @@ __global__ void __launch_bounds__(32, BMPC_WARP_MINB)
             P.status[inst] = status;
             P.iters[inst] = iters;
             if (Q.order_next) {
-                // next launch's order: slow instances first (front), the rest from the back
+                // next launch's order: filed from the back in completion order, so the last to finish start first next time
+                // (long_thresh, normally never reached, sends instances with that many iterations to the front instead)
                 if (iters >= Q.long_thresh)
                     Q.order_next[atomicAdd(&Q.ocnt[0], 1u)] = inst;
                 else
