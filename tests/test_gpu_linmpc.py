@@ -73,6 +73,21 @@ def test_c1_closed_loop_parity(team):
     print("C1 worst", worst, "active solves", n_active, b.launch_info())
 
 
+@pytest.mark.parametrize("nu,ny,Hc,nt", [(1, 1, 2, 3), (2, 2, 2, 5), (2, 2, 3, 7), (2, 2, 4, 9), (3, 2, 4, 13), (3, 3, 5, 16), (2, 2, 7, 16)])
+def test_warp_kernel_every_specialisation(nu, ny, Hc, nt):
+    """Every compiled size of the warp-per-controller kernel (NT = 3 ... 16; C1 above is NT = 11), odd and even: the
+    LDL' factorisation's last-column case and the two-variables-per-step substitutions differ between them.  The decision
+    vector has nu*Hc + 1 entries (NT is the smallest specialisation that holds it: 15 rides on 16)."""
+    mpcs, plants, rng = c1_controllers(8, seed=10 + nt + Hc, nx=4, nu=nu, ny=ny, Hp=12, Hc=Hc)
+    b = batch_from_oracle(mpcs)
+    assert nt - 3 < nu * Hc + 1 <= nt
+    worst, n_active = closed_loop_compare(mpcs, plants, b, rng, steps=20, switch=10)
+    assert n_active > 10
+    info = b.launch_info()  # (the launch is configured by the first step)
+    assert info["team"] == 32 and info["teams_per_cta"] == 1 and info["pd_in_smem"] > 0  # really the warp kernel
+    print("NT", nt, "worst", worst, "active solves", n_active, info)
+
+
 def test_c2_shapes_parity():
     """Config C2 recipe (4x4, nx=8, Hp=30, Hc=10 -> n=41)."""
     mpcs, plants, rng = c1_controllers(6, seed=2, nx=8, nu=4, ny=4, Hp=30, Hc=10)
