@@ -11,13 +11,16 @@
 //   * lane l owns positions l, l+32, ... (s, lambda, h, r_p in registers) and, for l < n, decision variable l;
 //   * Phi = H + Gt' D Gt is formed on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) tiles A = Gt' (8 variables x 4
 //     rows), B = D*Gt, accumulators initialised with H; only the lower block-triangle is computed;
-//   * Cholesky: right-looking, one row per lane in registers, column k broadcast through shared memory.  The matrix
-//     is BORDERED by the predictor's right-hand side (lane NT): the same column updates leave D^-2 M^-1 rhs there, so
-//     the predictor's forward substitution costs no extra instruction.  The column-scaled factor M = L diag(L)^-1 stays
-//     in shared memory (column-major); each substitution sweep re-reads its row / column of M with independent loads
-//     and then runs n dependent shuffle + FMA steps.  (An explicit W = D^-1 L^-1 from identity border rows, solves as
-//     two mat-vecs, was measured: 7 % shorter iterations but the late, ill-conditioned iterations of the degenerate
-//     instances lose accuracy -- per-period maximum 27 instead of 21 iterations, non-optimal exits -- rejected);
+//   * factorisation Phi = M D M' (LDL', M unit lower): right-looking, one row per lane in registers, column k
+//     broadcast through shared memory UNSCALED (its store, the warp barrier and the broadcast loads run while the
+//     pivot's reciprocal is in flight); reciprocals by rcp_fast (hardware seed + one third-order step).  The matrix is
+//     BORDERED by the predictor's right-hand side (lane NT): the same column updates leave D^-1 M^-1 rhs there, so the
+//     predictor's forward substitution costs no extra instruction.  M stays in shared memory (column-major, zeros on
+//     and above the diagonal); each substitution sweep re-reads its row / column of M with independent loads and then
+//     runs n/2 dependent (shuffle, 2 FMA) steps, two variables at a time.  (Measured and rejected: an explicit
+//     W = D^-1 L^-1 with the solves as two mat-vecs, and 2 x 2 pivot blocks with an explicit block inverse -- shorter
+//     iterations, but the late, ill-conditioned iterations of the degenerate instances lose accuracy: more
+//     iterations, non-optimal exits);
 //   * G'w products read Gt columns from shared memory with the row range split between the two half-warps;
 //   * the redundant  eps >= 0  row of the reference QP is NOT compiled: every softness weight is
 //     non-negative (construct.jl:456-506), so any point with eps < 0 is dominated by the same point with
@@ -25,8 +28,9 @@
 //     complementarity whenever no soft constraint is active) is what slows interior-point convergence.
 // Algorithm, tolerances, status policy and outputs are those of the general kernel (bmpc_device.cuh),
 // with two refinements: the step-to-boundary fraction tends to 1 as the affine step closes the gap
-// (tau = max(0.99, 1 - mu_aff/mu)), and work is handed out longest-expected-first (the previous period's
-// slow instances start first) so that the few 20-iteration solves do not start late in a launch.
+// (tau = max(0.99, 1 - mu_aff/mu)), and work is handed out in the REVERSE of the previous launch's completion order
+// (the long solves, which finished last and stay long from one period to the next, start first) so that the few
+// 20-iteration solves do not start late in a launch.
 #pragma once
 #include "bmpc_device.cuh"
 
@@ -49,7 +53,7 @@ struct WarpParams {
                         //   w = unit rows: the variable
     const int* upos;    // [2 x 16] position of the max-side / min-side unit row of each variable (32 RPL = none)
     const int* order;   // processing order of this launch (nullptr: 0..N-1)
-    int* order_next;    // written by this launch: slow instances first
+    int* order_next;    // written by this launch: the next launch's order (filed from the back in completion order)
     unsigned int* ocnt; // [2] fill counters of order_next (front, back)
     int long_thresh;    // iterations from which an instance is filed at the front of order_next (default: never)
     int l2_prefetch;    // 1: every CTA prefetches into L2 the constants of the instance one queue wave ahead of its own
