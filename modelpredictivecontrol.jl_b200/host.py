@@ -40,6 +40,27 @@ def _b(a, N, shape):
     return np.ascontiguousarray(a)
 
 
+def expand_softness(small, big, n, reps, name):
+    """Softness (ECR) weights of one constraint family over the horizon: the per-sample form ``c_xxx`` (length ``n``,
+    repeated ``reps`` times) or the whole-horizon form ``C_xxx`` (length ``n * reps``), which wins when both are given
+    (``setconstraint!``, src/controller/construct.jl:440-506).  Returns None when neither is given; raises ValueError for a
+    wrong size (the reference's DimensionMismatch) or a negative weight."""
+    if big is not None:
+        v = np.asarray(big, dtype=np.float64).reshape(-1)
+        if v.size != n * reps:
+            raise ValueError(f"C_{name} size must be ({n * reps},)")
+    elif small is not None:
+        v = np.asarray(small, dtype=np.float64).reshape(-1)
+        if v.size != n:
+            raise ValueError(f"c_{name} size must be ({n},)")
+        v = np.tile(v, reps)
+    else:
+        return None
+    if (v < 0).any():
+        raise ValueError(f"C_{name} weights should be non-negative")
+    return v.copy()
+
+
 class LinModel:
     """Batch of N linear plants ``x0(k+1) = A x0 + Bu u0 + Bd d0 + fop - xop``, ``y0 = C x0 + Dd d0``
     (reference src/model/linmodel.jl:1-66, direct-matrix constructor :252-253; operating points

@@ -8,7 +8,7 @@ work is one call into libbmpc.so; there is no Python/CPU implementation of the s
 import numpy as np
 
 from .batch import BatchLinMPC
-from .host import LinModel, ManualEstimator, SteadyKalmanFilter, _b, move_blocking
+from .host import LinModel, ManualEstimator, SteadyKalmanFilter, _b, expand_softness, move_blocking
 
 DEFAULT_HP0, DEFAULT_HC, DEFAULT_MWT, DEFAULT_NWT, DEFAULT_LWT, DEFAULT_CWT = 10, 2, 1.0, 0.1, 0.0, 1e5
 
@@ -152,8 +152,10 @@ class LinMPC:
                       xhatmax=None, Umin=None, Umax=None, DUmin=None, DUmax=None, Ymin=None, Ymax=None,
                       c_umin=None, c_umax=None, c_dumin=None, c_dumax=None, c_ymin=None, c_ymax=None,
                       c_xhatmin=None, c_xhatmax=None, wmin=None, wmax=None, Wmin=None, Wmax=None, c_wmin=None,
-                      c_wmax=None):
-        """``setconstraint!``: bounds are per instance ((N, len) or (len,)), softness is shared."""
+                      c_wmax=None, C_umin=None, C_umax=None, C_dumin=None, C_dumax=None, C_ymin=None, C_ymax=None,
+                      C_wmin=None, C_wmax=None):
+        """``setconstraint!`` (src/controller/construct.jl:324-559): bounds are per instance ((N, len) or (len,)), softness
+        is shared.  Lower-case keywords hold for every sample of the horizon, capitalised ones give the whole horizon."""
         N, Hp, Hc = self.model.N, self.Hp, self.Hc
         nu, ny, nx = self.model.nu, self.model.ny, self.estim.nxhat
         c = self.con
@@ -179,30 +181,23 @@ class LinMPC:
         elif Wmax is not None: c["Wmax"] = _b(Wmax, N, (nw * (Hp + 1),)).copy()
         if xhatmin is not None: c["xhat0min"] = _b(xhatmin, N, (nx,)) - self.estim.xophat
         if xhatmax is not None: c["xhat0max"] = _b(xhatmax, N, (nx,)) - self.estim.xophat
-        ecr = dict(C_umin=(c_umin, nu, Hp), C_umax=(c_umax, nu, Hp), C_dumin=(c_dumin, nu, Hc),
-                   C_dumax=(c_dumax, nu, Hc), C_ymin=(c_ymin, ny, Hp), C_ymax=(c_ymax, ny, Hp),
-                   c_xmin=(c_xhatmin, nx, 1), c_xmax=(c_xhatmax, nx, 1))
-        for key, val in (("C_wmin", c_wmin), ("C_wmax", c_wmax)):
-            if val is not None:
-                if not self.batch.neps:
-                    raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
-                if self._solved:
-                    raise RuntimeError("Cannot set softness parameters after calling moveinput!")
-                val = np.asarray(val, dtype=np.float64).reshape(nw)
-                if (val < 0).any():
-                    raise ValueError(f"{key} weights should be non-negative")
-                self.soft_w[key] = np.tile(val, Hp + 1)
-        if any(v[0] is not None for v in ecr.values()):
+        # softness: sizes and signs are checked before anything is stored
+        ecr = dict(C_umin=expand_softness(c_umin, C_umin, nu, Hp, "umin"), C_umax=expand_softness(c_umax, C_umax, nu, Hp, "umax"),
+                   C_dumin=expand_softness(c_dumin, C_dumin, nu, Hc, "dumin"), C_dumax=expand_softness(c_dumax, C_dumax, nu, Hc, "dumax"),
+                   C_ymin=expand_softness(c_ymin, C_ymin, ny, Hp, "ymin"), C_ymax=expand_softness(c_ymax, C_ymax, ny, Hp, "ymax"),
+                   c_xmin=expand_softness(c_xhatmin, None, nx, 1, "xhatmin"), c_xmax=expand_softness(c_xhatmax, None, nx, 1, "xhatmax"))
+        ecr_w = dict(C_wmin=expand_softness(c_wmin, C_wmin, nw, Hp + 1, "wmin"), C_wmax=expand_softness(c_wmax, C_wmax, nw, Hp + 1, "wmax"))
+        if any(v is not None for v in list(ecr.values()) + list(ecr_w.values())):
             if not self.batch.neps:
                 raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
             if self._solved:
                 raise RuntimeError("Cannot set softness parameters after calling moveinput!")
-            for k, (v, n, reps) in ecr.items():
+            for k, v in ecr.items():
                 if v is not None:
-                    v = np.asarray(v, dtype=np.float64).reshape(n)
-                    if (v < 0).any():
-                        raise ValueError(f"{k} weights should be non-negative")
-                    self.soft[k] = np.tile(v, reps)
+                    self.soft[k] = v
+            for k, v in ecr_w.items():
+                if v is not None:
+                    self.soft_w[k] = v
         self._push()
         return self
 

@@ -666,12 +666,14 @@ class LinMPC:
             if self.solved_once:
                 raise RuntimeError("Cannot set softness parameters after calling moveinput!")
         if not self.solved_once:
-            rep = lambda small, big, k: np.tile(a(small), k) if (big is None and small is not None) else (None if big is None else a(big))
-            for name, small, big, k in (("C_umin", c_umin, C_umin, Hp), ("C_umax", c_umax, C_umax, Hp),
-                                        ("C_dumin", c_dumin, C_dumin, Hc), ("C_dumax", c_dumax, C_dumax, Hc),
-                                        ("C_ymin", c_ymin, C_ymin, Hp), ("C_ymax", c_ymax, C_ymax, Hp),
-                                        ("C_wmin", c_wmin, C_wmin, Hp + 1), ("C_wmax", c_wmax, C_wmax, Hp + 1)):
-                v = rep(small, big, k)
+            # sizes are checked before anything is stored (DimensionMismatch, construct.jl:440-506)
+            rep = lambda small, big, n1, k, nm: (np.tile(chk(small, n1, nm.lower()), k) if (big is None and small is not None)
+                                                 else (None if big is None else chk(big, n1 * k, nm)))
+            for name, small, big, n1, k in (("C_umin", c_umin, C_umin, nu, Hp), ("C_umax", c_umax, C_umax, nu, Hp),
+                                            ("C_dumin", c_dumin, C_dumin, nu, Hc), ("C_dumax", c_dumax, C_dumax, nu, Hc),
+                                            ("C_ymin", c_ymin, C_ymin, ny, Hp), ("C_ymax", c_ymax, C_ymax, ny, Hp),
+                                            ("C_wmin", c_wmin, C_wmin, nw, Hp + 1), ("C_wmax", c_wmax, C_wmax, nw, Hp + 1)):
+                v = rep(small, big, n1, k, name)
                 if v is not None:
                     if (v < 0).any():
                         raise ValueError(f"{name} weights should be non-negative")

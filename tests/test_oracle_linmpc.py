@@ -358,3 +358,130 @@ def test_internalmodel_estimator_methods():
     assert im.initstate([10, 50], [50, 30]) == pytest.approx(np.zeros(2)) and im.xs == pytest.approx(np.zeros(2))
     with pytest.raises(ValueError):
         InternalModel(LinModel(np.eye(1), np.ones((1, 1)), np.ones((1, 1))))  # integrating model
+
+
+def _setup_sys_model_id3():
+    """SetupMPCtests' `sys` (test/0_test_module.jl:3-5) as LinModel(sys, Ts, i_d=[3]) builds it (src/model/linmodel.jl:165-198):
+    zero-order hold for the two manipulated inputs, Tustin for the measured disturbance -- their poles differ, so the minimal
+    realisation keeps four states and the default estimator has nx̂ = 6."""
+    Ts = 400.0
+    a1, b1, c1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, c2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+
+    def tustin(k, tau):
+        al = Ts / (2 * tau)
+        p = (1 - al) / (1 + al)
+        g = k * al / (1 + al)
+        return p, g * (1 + p), g  # x+ = p x + d,  y = c x + Dd d  <=>  g (z + 1) / (z - p)
+    p1, cd1, dd1 = tustin(1.90, 1800.0)
+    p2, cd2, dd2 = tustin(-0.74, 800.0)
+    A = np.diag([a1, a2, p1, p2])
+    Bu = np.array([[b1, b1], [-b2, b2], [0, 0], [0, 0]])
+    Bd = np.array([[0.0], [0.0], [1.0], [1.0]])
+    C = np.array([[c1, 0, cd1, 0], [0, c2, 0, cd2]])
+    Dd = np.array([[dd1], [dd2]])
+    return LinModel(A, Bu, C, Bd=Bd, Dd=Dd, Ts=Ts)
+
+
+def test_setconstraint_known_answers():
+    """test/3_test_predictive_control.jl:259-389 ("LinMPC set constraints"): defaults, every bound and softness keyword in
+    its per-sample and whole-horizon form, the softness column of every block of A (construct.jl:999-1199), and the error
+    cases (sizes, negative softness, softness / +-Inf pattern frozen after the first moveinput!, softness with Cwt = Inf)."""
+    model = _setup_sys_model_id3()
+    mpc = LinMPC(model, Hp=1, Hc=1, Wr=np.ones((2, 2)))
+    c, nu, ny, nw, nx = mpc.con, 2, 2, 2, 6
+    assert mpc.estim.nxhat == nx and mpc.nw == nw
+    inf = np.inf
+
+    def blocks(m):
+        """softness columns -A[:, end] of (Umin, Umax, DUmin, DUmax, Ymin, Ymax, Wmin, Wmax, xmin, xmax)"""
+        sizes = [m.model.nu * m.Hp] * 2 + [m.model.nu * m.Hc] * 2 + [m.model.ny * m.Hp] * 2 + [m.nw * (m.Hp + 1)] * 2 + [m.estim.nxhat] * 2
+        out, o = [], 0
+        for s in sizes:
+            out.append(-m.con.A[o:o + s, -1])
+            o += s
+        assert o == m.con.A.shape[0]
+        return out
+    for v, n, val in ((c.U0min, nu, -inf), (c.U0max, nu, inf), (c.DUmin, nu, -inf), (c.DUmax, nu, inf), (c.Y0min, ny, -inf),
+                      (c.Y0max, ny, inf), (c.Wmin, 2 * nw, -inf), (c.Wmax, 2 * nw, inf), (c.xhat0min, nx, -inf), (c.xhat0max, nx, inf)):
+        assert v.shape == (n,) and (v == val).all()
+    b = blocks(mpc)
+    for i in (0, 1, 2, 3):
+        assert (b[i] == 0.0).all()      # inputs and increments: hard by default
+    for i in (4, 5, 6, 7, 8, 9):
+        assert (b[i] == 1.0).all()      # outputs, custom rows, terminal states: soft by default
+    mpc.setconstraint(umin=[-5, -9.9], umax=[100, 99])
+    assert np.allclose(c.U0min, [-5, -9.9]) and np.allclose(c.U0max, [100, 99])
+    mpc.setconstraint(dumin=[-5, -10], dumax=[6, 11])
+    assert np.allclose(c.DUmin, [-5, -10]) and np.allclose(c.DUmax, [6, 11])
+    mpc.setconstraint(ymin=[-6, -11], ymax=[55, 35])
+    assert np.allclose(c.Y0min, [-6, -11]) and np.allclose(c.Y0max, [55, 35])
+    mpc.setconstraint(wmin=[-7, -12], wmax=[75, 65])
+    assert np.allclose(c.Wmin, [-7, -12, -7, -12]) and np.allclose(c.Wmax, [75, 65, 75, 65])
+    mpc.setconstraint(xhatmin=[-21, -22, -23, -24, -25, -26], xhatmax=[21, 22, 23, 24, 25, 26])
+    assert np.allclose(c.xhat0min, [-21, -22, -23, -24, -25, -26]) and np.allclose(c.xhat0max, [21, 22, 23, 24, 25, 26])
+    mpc.setconstraint(c_umin=[0.01, 0.02], c_umax=[0.03, 0.04])
+    mpc.setconstraint(c_dumin=[0.05, 0.06], c_dumax=[0.07, 0.08])
+    mpc.setconstraint(c_ymin=[1.00, 1.01], c_ymax=[1.02, 1.03])
+    mpc.setconstraint(c_wmin=[2.00, 2.01], c_wmax=[2.02, 2.03])
+    mpc.setconstraint(c_xhatmin=[0.21, 0.22, 0.23, 0.24, 0.25, 0.26], c_xhatmax=[0.31, 0.32, 0.33, 0.34, 0.35, 0.36])
+    expect = [[0.01, 0.02], [0.03, 0.04], [0.05, 0.06], [0.07, 0.08], [1.00, 1.01], [1.02, 1.03],
+              [2.00, 2.01, 2.00, 2.01], [2.02, 2.03, 2.02, 2.03],
+              [0.21, 0.22, 0.23, 0.24, 0.25, 0.26], [0.31, 0.32, 0.33, 0.34, 0.35, 0.36]]
+    for got, want in zip(blocks(mpc), expect):
+        assert np.allclose(got, want)
+
+    mpc2 = LinMPC(LinModel(*zoh_first_order(2, 10, 3.0), Ts=3.0), Hp=50, Hc=5, Wr=[[1]])
+    c2 = mpc2.con
+    r50, r5, r51 = np.arange(1, 51.0), np.arange(1, 6.0), np.arange(1, 52.0)
+    mpc2.setconstraint(Umin=-r50 - 1, Umax=r50 + 1)
+    assert np.allclose(c2.U0min, -r50 - 1) and np.allclose(c2.U0max, r50 + 1)
+    mpc2.setconstraint(DUmin=-r5 - 2, DUmax=r5 + 2)
+    assert np.allclose(c2.DUmin, -r5 - 2) and np.allclose(c2.DUmax, r5 + 2)
+    mpc2.setconstraint(Ymin=-r50 - 3, Ymax=r50 + 3)
+    assert np.allclose(c2.Y0min, -r50 - 3) and np.allclose(c2.Y0max, r50 + 3)
+    mpc2.setconstraint(Wmin=-r51 - 4, Wmax=r51 + 4)
+    assert np.allclose(c2.Wmin, -r51 - 4) and np.allclose(c2.Wmax, r51 + 4)
+    mpc2.setconstraint(C_umin=r50 + 5, C_umax=r50 + 5)
+    mpc2.setconstraint(C_dumin=r5 + 6, C_dumax=r5 + 6)
+    mpc2.setconstraint(C_ymin=r50 + 7, C_ymax=r50 + 7)
+    mpc2.setconstraint(C_wmin=r51 + 8, C_wmax=r51 + 8)
+    b2 = blocks(mpc2)
+    for i, want in ((0, r50 + 5), (1, r50 + 5), (2, r5 + 6), (3, r5 + 6), (4, r50 + 7), (5, r50 + 7), (6, r51 + 8), (7, r51 + 8)):
+        assert np.allclose(b2[i], want)
+    mpc2.setconstraint(c_umin=[0], c_umax=[0], c_dumin=[0], c_dumax=[0], c_ymin=[1], c_ymax=[1], c_wmin=[1], c_wmax=[1])
+
+    for kw in ("umin", "umax", "dumin", "dumax", "ymin", "ymax", "wmin", "wmax",
+               "c_umin", "c_umax", "c_dumin", "c_dumax", "c_ymin", "c_ymax", "c_wmin", "c_wmax"):
+        with pytest.raises(ValueError):       # DimensionMismatch
+            mpc.setconstraint(**{kw: [0, 0, 0]})
+    for kw in ("c_umin", "c_umax", "c_dumin", "c_dumax", "c_ymin", "c_ymax", "c_wmin", "c_wmax"):
+        with pytest.raises(ValueError):       # negative softness
+            mpc.setconstraint(**{kw: [-1, -1]})
+    mpc.preparestate(model.yop, model.dop)
+    mpc.moveinput([0, 0], [0])
+    with pytest.raises(RuntimeError):         # softness is frozen after the first solve
+        mpc.setconstraint(c_umin=[1, 1], c_umax=[1, 1])
+    with pytest.raises(RuntimeError):         # ... and so is the +-Inf pattern
+        mpc.setconstraint(umin=[-inf, -inf], umax=[inf, inf])
+    mpc3 = LinMPC(model, Cwt=inf)
+    for kw in ("c_umin", "c_umax", "c_dumin", "c_dumax", "c_ymin", "c_ymax"):
+        with pytest.raises(ValueError):       # ArgumentError: no slack variable
+            mpc3.setconstraint(**{kw: [1, 1]})
+
+
+@pytest.mark.parametrize("kw", [dict(nint_u=[1]), dict(nint_ym=[1])])
+def test_steady_kalman_filter_step_disturbance_rejection(kw):
+    """test/3_test_predictive_control.jl:177-208 ("LinMPC step disturbance rejection", SteadyKalmanFilter with an input or
+    an output integrator): a constant output disturbance of -5 is rejected, the loop settles at ym = r = 15 with u = 2
+    (plant gain 5, yop = 10; the controller's own model has no operating point, as in the reference)."""
+    plant = LinModel(*zoh_first_order(5, 2, 3.0), Ts=3.0, yop=[10])
+    mpc = LinMPC(SteadyKalmanFilter(LinModel(*zoh_first_order(5, 2, 3.0), Ts=3.0), **kw))
+    u = ym = None
+    for i in range(25):
+        ym = plant.evaloutput() - 5
+        mpc.preparestate(ym)
+        u = mpc.moveinput([15])
+        mpc.updatestate(u, ym)
+        plant.updatestate(u)
+    assert u == pytest.approx([2], abs=1e-2) and ym == pytest.approx([15], abs=1e-2)
