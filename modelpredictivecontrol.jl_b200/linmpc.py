@@ -28,6 +28,13 @@ class LinMPC:
             if nk.min() != nk.max():
                 raise ValueError("default Hp: the instances have different delay estimates; pass Hp explicitly")
             Hp = DEFAULT_HP0 + int(nk.max())
+        # validate_weights (construct.jl:105-123): ArgumentError / DimensionMismatch -> ValueError
+        if Hp < 1:
+            raise ValueError("Prediction horizon Hp should be >= 1")
+        if np.ndim(Cwt) != 0:
+            raise ValueError("Cwt should be a real scalar")
+        if Cwt < 0:
+            raise ValueError("Cwt weight should be >= 0")
         self.nb = move_blocking(Hp, Hc)
         self.Hp, self.Hc = Hp, len(self.nb)
         w = lambda v, dflt, n: np.full(n, dflt) if v is None else np.asarray(v, dtype=np.float64).reshape(n)

@@ -399,6 +399,22 @@ def move_blocking(Hp, Hc):
     return nb
 
 
+def validate_weights(nu, ny, Hp, Hc, M_Hp, N_Hc, L_Hp, Cwt):
+    """src/controller/construct.jl:105-123 (ArgumentError / DimensionMismatch -> ValueError)."""
+    if Hp < 1: raise ValueError("Prediction horizon Hp should be >= 1")
+    if Hc < 1: raise ValueError("Control horizon Hc should be >= 1")
+    if Hc > Hp: raise ValueError("Control horizon Hc should be <= prediction horizon Hp")
+    for M, n, name, wname in ((M_Hp, ny * Hp, "M_Hp", "Mwt"), (N_Hc, nu * Hc, "N_Hc", "Nwt"), (L_Hp, nu * Hp, "L_Hp", "Lwt")):
+        if M.shape != (n, n):
+            raise ValueError(f"{name} size {M.shape} != ({n}, {n})")
+        if np.count_nonzero(M - np.diag(np.diag(M))) == 0 and (np.diag(M) < 0).any():
+            raise ValueError(f"{wname} values should be nonnegative")
+        if not np.array_equal(M, M.T):
+            raise ValueError(f"{name} should be hermitian")
+    if np.ndim(Cwt) != 0: raise ValueError("Cwt should be a real scalar")
+    if Cwt < 0: raise ValueError("Cwt weight should be >= 0")
+
+
 def init_ZtoDU(nu, Hc, nZ):
     """src/controller/construct.jl:733-741."""
     P = np.zeros((nu * Hc, nZ))
@@ -518,9 +534,13 @@ class LinMPC:
         Mwt = np.full(ny, DEFAULT_MWT) if Mwt is None else np.asarray(Mwt, float)
         Nwt = np.full(nu, DEFAULT_NWT) if Nwt is None else np.asarray(Nwt, float)
         Lwt = np.full(nu, DEFAULT_LWT) if Lwt is None else np.asarray(Lwt, float)
-        self.M_Hp = np.diag(np.tile(Mwt, Hp)) if M_Hp is None else np.asarray(M_Hp, float)
+        for v, n, name in ((Mwt, ny, "Mwt"), (Nwt, nu, "Nwt"), (Lwt, nu, "Lwt")):  # linmpc.jl:229-316 (DimensionMismatch)
+            if v.shape != (n,):
+                raise ValueError(f"{name} size {v.shape} != ({n},)")
+        self.M_Hp = np.diag(np.tile(Mwt, max(Hp, 0))) if M_Hp is None else np.asarray(M_Hp, float)
         self.N_Hc = np.diag(np.tile(Nwt, Hc)) if N_Hc is None else np.asarray(N_Hc, float)
-        self.L_Hp = np.diag(np.tile(Lwt, Hp)) if L_Hp is None else np.asarray(L_Hp, float)
+        self.L_Hp = np.diag(np.tile(Lwt, max(Hp, 0))) if L_Hp is None else np.asarray(L_Hp, float)
+        validate_weights(nu, ny, Hp, Hc, self.M_Hp, self.N_Hc, self.L_Hp, Cwt)
         self.Cwt = float(Cwt)
         self.neps = 0 if np.isinf(self.Cwt) else 1  # construct.jl:903
         neps = self.neps
@@ -546,8 +566,17 @@ class LinMPC:
         # validate_custom_lincon (construct.jl:666-695): nw rows, missing matrices are zero
         given = [np.atleast_2d(np.asarray(W, float)) for W in (Wy, Wu, Wd, Wr) if W is not None]
         nw = given[0].shape[0] if given else 0
-        mat = lambda W, ncol: np.zeros((nw, ncol)) if W is None else np.atleast_2d(np.asarray(W, float)).reshape(nw, ncol)
-        self.Wy, self.Wu, self.Wd, self.Wr = mat(Wy, ny), mat(Wu, nu), mat(Wd, nd), mat(Wr, ny)
+
+        def mat(W, ncol, name):
+            if W is None:
+                return np.zeros((nw, ncol))
+            W = np.atleast_2d(np.asarray(W, float))
+            if W.shape[1] != ncol:
+                raise ValueError(f"{name} must have {ncol} columns.")
+            if W.shape[0] != nw:
+                raise ValueError("all custom linear constraint matrices must have the same number of rows.")
+            return W
+        self.Wy, self.Wu, self.Wd, self.Wr = mat(Wy, ny, "Wy"), mat(Wu, nu, "Wu"), mat(Wd, nd, "Wd"), mat(Wr, ny, "Wr")
         self.nw = nw
         rd = lambda W: np.kron(np.eye(Hp + 1), W)                    # repeatdiag(W, Hp+1), construct.jl:922-925
         self.Wbar_y, self.Wbar_u, self.Wbar_d, self.Wbar_r = rd(self.Wy), rd(self.Wu), rd(self.Wd), rd(self.Wr)

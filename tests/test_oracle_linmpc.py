@@ -485,3 +485,55 @@ def test_steady_kalman_filter_step_disturbance_rejection(kw):
         mpc.updatestate(u, ym)
         plant.updatestate(u)
     assert u == pytest.approx([2], abs=1e-2) and ym == pytest.approx([15], abs=1e-2)
+
+
+def test_linmpc_construction_known_answers():
+    """test/3_test_predictive_control.jl:1-91 ("LinMPC construction"): sizes of Ẽ with and without the slack column, the
+    weight matrices built from Mwt / Nwt / Lwt / Cwt and given whole (M_Hp, N_Hc, L_Hp), the estimator choices, the
+    MultipleShooting decision vector and defect matrix, move-blocking vectors, the custom-constraint block matrices, and
+    the constructor's error cases (ArgumentError / DimensionMismatch -> ValueError)."""
+    from oracle.linmpc_ms import LinMPCMultipleShooting
+    from oracle.mhe import KalmanFilter
+    model = _setup_sys_model_id3()
+    nu, ny, nd = model.nu, model.ny, model.nd
+    mpc1 = LinMPC(model, Hp=15)
+    assert isinstance(mpc1.estim, SteadyKalmanFilter) and mpc1.Etilde.shape[0] == 15 * ny
+    assert LinMPC(model, Hc=4, Cwt=np.inf).Etilde.shape[1] == 4 * nu
+    mpc3 = LinMPC(model, Hc=4, Cwt=1e4)
+    assert mpc3.Etilde.shape[1] == 4 * nu + 1 and mpc3.Ntilde_Hc[-1, -1] == 1e4
+    assert np.array_equal(LinMPC(model, Mwt=[1, 2], Hp=15).M_Hp, np.diag(np.tile([1.0, 2.0], 15)))
+    assert np.array_equal(LinMPC(model, Nwt=[3, 4], Cwt=1e3, Hc=5).Ntilde_Hc, np.diag(np.r_[np.tile([3.0, 4.0], 5), 1e3]))
+    assert np.array_equal(LinMPC(model, Lwt=[0, 1], Hp=15).L_Hp, np.diag(np.tile([0.0, 1.0], 15)))
+    assert isinstance(LinMPC(KalmanFilter(model)).estim, KalmanFilter)
+    mpc9 = LinMPC(model, nint_u=[1, 1], nint_ym=[0, 0])
+    assert list(mpc9.estim.nint_u) == [1, 1] and list(mpc9.estim.nint_ym) == [0, 0]
+    d20 = np.diag(np.linspace(1.01, 1.2, 20))
+    assert np.allclose(LinMPC(model, M_Hp=d20).M_Hp, d20)
+    d4 = np.diag([0.1, 0.11, 0.12, 0.13])
+    assert np.allclose(LinMPC(model, N_Hc=d4, Cwt=np.inf).Ntilde_Hc, d4)
+    l20 = np.diag(np.linspace(0.001, 0.02, 20))
+    assert np.allclose(LinMPC(model, L_Hp=l20).L_Hp, l20)
+    model2 = LinModel(0.5 * np.ones((1, 1)), np.ones((1, 1)), np.ones((1, 1)), Ts=1.0)
+    mpc14 = LinMPCMultipleShooting(model2)
+    assert mpc14.Ztilde.size == model2.nu * mpc14.Hc + mpc14.estim.nxhat * mpc14.Hp + mpc14.neps
+    assert mpc14.Aeq.shape[0] == mpc14.estim.nxhat * mpc14.Hp
+    for Hc in ([1, 2, 3], [1, 2, 3, 6, 6, 6]):  # a block is appended / the blocks past Hp are dropped
+        m = LinMPC(model, Hc=Hc, Hp=10, Cwt=np.inf)
+        assert m.Hc == 4 and m.Ptilde_u.shape == (10 * nu, 4 * nu)
+    rd = lambda W, n: np.kron(np.eye(n), W)
+    mpc17 = LinMPC(model, Wy=np.ones((3, ny)))
+    n1 = mpc17.Hp + 1
+    assert np.array_equal(mpc17.Wbar_y, rd(np.ones((3, ny)), n1))
+    assert mpc17.Wbar_u.shape == (3 * n1, nu * n1) and not mpc17.Wbar_u.any()
+    assert mpc17.Wbar_d.shape == (3 * n1, nd * n1) and not mpc17.Wbar_d.any()
+    assert mpc17.Wbar_r.shape == (3 * n1, ny * n1) and not mpc17.Wbar_r.any()
+    Wy, Wu, Wd, Wr = np.ones((2, ny)), 2 * np.ones((2, nu)), 3 * np.ones((2, nd)), 0.5 * np.ones((2, ny))
+    mpc18 = LinMPC(model, Wy=Wy, Wu=Wu, Wd=Wd, Wr=Wr)
+    for got, W in ((mpc18.Wbar_y, Wy), (mpc18.Wbar_u, Wu), (mpc18.Wbar_d, Wd), (mpc18.Wbar_r, Wr)):
+        assert np.array_equal(got, rd(W, mpc18.Hp + 1))
+    for kw in (dict(Hp=0), dict(Hc=0), dict(Hp=1, Hc=2), dict(Mwt=[1]), dict(Nwt=[1]), dict(Lwt=[1]), dict(Cwt=[1]),
+               dict(Mwt=[-1, 1]), dict(Nwt=[-1, 1]), dict(Lwt=[-1, 1]), dict(Cwt=-1),
+               dict(Wy=np.ones((2, ny + 1))), dict(Wu=np.ones((2, nu - 1))), dict(Wd=np.ones((2, nd + 1))),
+               dict(Wr=np.ones((2, ny - 1))), dict(Wy=np.ones((2, ny)), Wu=np.ones((3, nu)))):
+        with pytest.raises((ValueError, TypeError)):
+            LinMPC(model, **kw)
