@@ -927,3 +927,7 @@ class ExplicitMPC(LinMPC):
         self.Ztilde = -np.linalg.solve(self.Htilde, self.qtilde)
         self.solved_once = True
         return self.Ztilde
+
+    def setconstraint(self, **kw):
+        """src/controller/explicitmpc.jl:181."""
+        raise RuntimeError("ExplicitMPC does not support constraints.")

@@ -104,6 +104,8 @@ class MovingHorizonEstimator(StateEstimator):
         if Qhat is not None: self.Qhat = np.atleast_2d(np.asarray(Qhat, float))
         if Rhat is not None: self.Rhat = np.atleast_2d(np.asarray(Rhat, float))
         self.Cwt = float(Cwt)
+        if self.Cwt < 0:
+            raise ValueError("Cwt weight should be >= 0")  # mhe/construct.jl (ArgumentError)
         self.neps = 0 if np.isinf(self.Cwt) else 1
         f = self.fophat - self.xophat
         (self.E, self.G, self.J, self.B, self.exbar, self.EX, self.GX, self.JX, self.BX) = init_predmat_mhe(
@@ -144,35 +146,75 @@ class MovingHorizonEstimator(StateEstimator):
 
     def setconstraint(self, xhatmin=None, xhatmax=None, whatmin=None, whatmax=None, vhatmin=None, vhatmax=None,
                       c_xhatmin=None, c_xhatmax=None, c_whatmin=None, c_whatmax=None, c_vhatmin=None,
-                      c_vhatmax=None):
-        """src/estimator/mhe/construct.jl:858-1046 (per-variable forms)."""
+                      c_vhatmax=None, Xhatmin=None, Xhatmax=None, Whatmin=None, Whatmax=None, Vhatmin=None, Vhatmax=None,
+                      C_xhatmin=None, C_xhatmax=None, C_whatmin=None, C_whatmax=None, C_vhatmin=None, C_vhatmax=None):
+        """src/estimator/mhe/construct.jl:858-1046.  Lower-case keywords hold for every stage of the window, capitalised
+        ones give the whole window: X̂ over He+1 stages (the first one is the arrival state x̂0(k-Nk+p)), Ŵ and V̂ over He."""
         c, He, nxh, nym = self.con, self.He, self.nxhat, self.nym
-        a = lambda v, n: np.asarray(v, float).reshape(n)
+
+        def a(v, n, name):
+            v = np.asarray(v, float).reshape(-1)
+            if v.size != n:
+                raise ValueError(f"{name} size must be ({n},)")  # DimensionMismatch
+            return v
         Xop = np.tile(self.xophat, He)
-        if xhatmin is not None:
-            c["xhat0min"] = a(xhatmin, nxh) - self.xophat
-            c["X0min"] = np.tile(a(xhatmin, nxh), He) - Xop
-        if xhatmax is not None:
-            c["xhat0max"] = a(xhatmax, nxh) - self.xophat
-            c["X0max"] = np.tile(a(xhatmax, nxh), He) - Xop
-        if whatmin is not None: c["Wmin"] = np.tile(a(whatmin, nxh), He)
-        if whatmax is not None: c["Wmax"] = np.tile(a(whatmax, nxh), He)
-        if vhatmin is not None: c["Vmin"] = np.tile(a(vhatmin, nym), He)
-        if vhatmax is not None: c["Vmax"] = np.tile(a(vhatmax, nym), He)
-        ecr = [c_xhatmin, c_xhatmax, c_whatmin, c_whatmax, c_vhatmin, c_vhatmax]
-        if any(e is not None for e in ecr):
-            if not self.neps:
-                raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
-            if self.solved_once:
-                raise RuntimeError("Cannot set softness parameters after calling updatestate!")
-            if c_xhatmin is not None:
-                c["c_xmin"], c["C_xmin"] = a(c_xhatmin, nxh), np.tile(a(c_xhatmin, nxh), He)
-            if c_xhatmax is not None:
-                c["c_xmax"], c["C_xmax"] = a(c_xhatmax, nxh), np.tile(a(c_xhatmax, nxh), He)
-            if c_whatmin is not None: c["C_wmin"] = np.tile(a(c_whatmin, nxh), He)
-            if c_whatmax is not None: c["C_wmax"] = np.tile(a(c_whatmax, nxh), He)
-            if c_vhatmin is not None: c["C_vmin"] = np.tile(a(c_vhatmin, nym), He)
-            if c_vhatmax is not None: c["C_vmax"] = np.tile(a(c_vhatmax, nym), He)
+        pattern = lambda: tuple(np.isfinite(c[k]).tobytes() for k in ("xhat0min", "xhat0max", "X0min", "X0max", "Wmin", "Wmax",
+                                                                      "Vmin", "Vmax"))
+        old_pattern, old = pattern(), {k: np.array(v, copy=True) for k, v in c.items()}
+        try:
+            if Xhatmin is not None:
+                v = a(Xhatmin, nxh * (He + 1), "Xhatmin")
+                c["xhat0min"], c["X0min"] = v[:nxh] - self.xophat, v[nxh:] - Xop
+            elif xhatmin is not None:
+                v = a(xhatmin, nxh, "xhatmin")
+                c["xhat0min"], c["X0min"] = v - self.xophat, np.tile(v, He) - Xop
+            if Xhatmax is not None:
+                v = a(Xhatmax, nxh * (He + 1), "Xhatmax")
+                c["xhat0max"], c["X0max"] = v[:nxh] - self.xophat, v[nxh:] - Xop
+            elif xhatmax is not None:
+                v = a(xhatmax, nxh, "xhatmax")
+                c["xhat0max"], c["X0max"] = v - self.xophat, np.tile(v, He) - Xop
+            for key, small, big, n in (("Wmin", whatmin, Whatmin, nxh), ("Wmax", whatmax, Whatmax, nxh),
+                                       ("Vmin", vhatmin, Vhatmin, nym), ("Vmax", vhatmax, Vhatmax, nym)):
+                if big is not None:
+                    c[key] = a(big, n * He, key).copy()
+                elif small is not None:
+                    c[key] = np.tile(a(small, n, key), He)
+            ecr = [c_xhatmin, c_xhatmax, c_whatmin, c_whatmax, c_vhatmin, c_vhatmax,
+                   C_xhatmin, C_xhatmax, C_whatmin, C_whatmax, C_vhatmin, C_vhatmax]
+            if any(e is not None for e in ecr):
+                if not self.neps:
+                    raise ValueError("Slack variable weight Cwt must be finite to set softness parameters")
+                if self.solved_once:
+                    raise RuntimeError("Cannot set softness parameters after calling updatestate!")
+
+                def soft(small, big, n, reps, name):
+                    if big is not None:
+                        v = a(big, n * reps, "C_" + name)
+                    elif small is not None:
+                        v = np.tile(a(small, n, "c_" + name), reps)
+                    else:
+                        return None
+                    if (v < 0).any():
+                        raise ValueError(f"C_{name} weights should be non-negative")
+                    return v
+                for lo, hi, small, big, name in (("c_xmin", "C_xmin", c_xhatmin, C_xhatmin, "xhatmin"),
+                                                 ("c_xmax", "C_xmax", c_xhatmax, C_xhatmax, "xhatmax")):
+                    v = soft(small, big, nxh, He + 1, name)
+                    if v is not None:
+                        c[lo], c[hi] = v[:nxh].copy(), v[nxh:].copy()
+                for key, small, big, n, name in (("C_wmin", c_whatmin, C_whatmin, nxh, "whatmin"),
+                                                 ("C_wmax", c_whatmax, C_whatmax, nxh, "whatmax"),
+                                                 ("C_vmin", c_vhatmin, C_vhatmin, nym, "vhatmin"),
+                                                 ("C_vmax", c_vhatmax, C_vhatmax, nym, "vhatmax")):
+                    v = soft(small, big, n, He, name)
+                    if v is not None:
+                        c[key] = v
+            if self.solved_once and pattern() != old_pattern:  # construct.jl:1037-1039
+                raise RuntimeError("Cannot modify +-Inf constraints after first solve of estimation problem")
+        except Exception:
+            c.update(old)  # nothing is stored by a call that fails
+            raise
         return self
 
     # ---- windows (add_data_windows!, execute.jl:497-547) ----

@@ -537,3 +537,64 @@ def test_linmpc_construction_known_answers():
                dict(Wr=np.ones((2, ny - 1))), dict(Wy=np.ones((2, ny)), Wu=np.ones((3, nu)))):
         with pytest.raises((ValueError, TypeError)):
             LinMPC(model, **kw)
+
+
+def test_explicitmpc_known_answers():
+    """test/3_test_predictive_control.jl:640-781 (ExplicitMPC: "moves and getinfo", "step disturbance rejection",
+    "constraints", "set model"): the unconstrained closed form Z̃ = -H̃⁻¹q̃ (explicitmpc.jl:209) -- what stage 2 of the CUDA
+    step kernels computes with the cached factor."""
+    from oracle.linmpc import InternalModel
+    from oracle.mhe import KalmanFilter
+    model = first_order(5, 2, 3.0)
+    mpc1 = ExplicitMPC(model, Nwt=[0], Hp=1000, Hc=1)
+    r, y = [5], [0]
+    mpc1.preparestate(y)
+    assert mpc1.moveinput(r) == pytest.approx([1], abs=1e-2)
+    u = mpc1.moveinput(r, lastu=[-1])
+    assert u == pytest.approx([1], abs=1e-2)
+    info = mpc1.getinfo()
+    assert info["u"] == pytest.approx(u) and info["Yhat"][-1] == pytest.approx(5, abs=1e-2)
+    assert info["DU"] == pytest.approx([2.0], abs=1e-2)
+    mpc3 = ExplicitMPC(model, Mwt=[0], Nwt=[0], Lwt=[1])
+    mpc3.preparestate(y)
+    assert mpc3.moveinput([0], Rhat_u=np.full(mpc3.Hp, 12.0)) == pytest.approx([12], abs=1e-2)
+    mpc4 = ExplicitMPC(LinModel(0.5 * np.ones((1, 1)), np.ones((1, 1)), np.ones((1, 1)), Ts=1.0))
+    mpc4.preparestate(y)
+    assert mpc4.moveinput([0]) == pytest.approx([0.0], abs=1e-12)
+    mpc5 = ExplicitMPC(model, Hp=10, Hc=[1, 2, 3, 4], Nwt=[10])
+    mpc5.preparestate(y)
+    mpc5.moveinput(r)
+    assert np.diff(mpc5.getinfo()["U"])[[1, 3, 4, 6, 7, 8]] == pytest.approx(np.zeros(6), abs=1e-9)
+    # step disturbance rejection (:676-727): InternalModel, input integrator, output integrator
+    for make in (lambda: InternalModel(first_order(5, 2, 3.0, yop=[10])),
+                 lambda: SteadyKalmanFilter(first_order(5, 2, 3.0), nint_u=[1]),
+                 lambda: SteadyKalmanFilter(first_order(5, 2, 3.0), nint_ym=[1])):
+        plant, mpc = first_order(5, 2, 3.0, yop=[10]), ExplicitMPC(make())
+        u = ym = None
+        for i in range(25):
+            ym = plant.evaloutput() - 5
+            mpc.preparestate(ym)
+            u = mpc.moveinput([15])
+            mpc.updatestate(u, ym)
+            plant.updatestate(u)
+        assert u == pytest.approx([2], abs=1e-2) and ym == pytest.approx([15], abs=1e-2)
+    with pytest.raises(RuntimeError):  # :743-748
+        ExplicitMPC(_setup_sys_model_id3(), Hp=1, Hc=1).setconstraint(umin=[0.0, 0.0])
+    # set model (:750-781)
+    mpc = ExplicitMPC(KalmanFilter(first_order(5, 2, 3.0, yop=[10], uop=[1])), Nwt=[0], Hp=1000, Hc=1)
+    assert np.array_equal(mpc.Yop, np.full(1000, 10.0)) and np.array_equal(mpc.Uop, np.full(1000, 1.0))
+    mpc.preparestate([10])
+    assert mpc.moveinput([15]) == pytest.approx([2], abs=1e-2)
+    assert mpc.lastu0 == pytest.approx([2 - 1], abs=1e-2)
+    mpc.setmodel(first_order(5, 2, 3.0, yop=[20], uop=[11]))
+    assert np.array_equal(mpc.Yop, np.full(1000, 20.0)) and np.array_equal(mpc.Uop, np.full(1000, 11.0))
+    assert mpc.lastu0 == pytest.approx([2 - 11], abs=1e-2)
+    assert mpc.moveinput([40]) == pytest.approx([15], abs=1e-2)
+    mpc.setmodel(first_order(10, 2, 3.0, yop=[20], uop=[11]))
+    assert mpc.moveinput([40]) == pytest.approx([13], abs=1e-2)
+    mpc.setmodel(Mwt=[100], Nwt=[200], Lwt=[300])
+    assert np.array_equal(mpc.M_Hp, np.diag(np.full(1000, 100.0))) and np.array_equal(mpc.Ntilde_Hc, [[200.0]])
+    assert np.array_equal(mpc.L_Hp, np.diag(np.full(1000, 300.0)))
+    mpc.setmodel(M_Hp=np.diag(np.arange(1, 1001.0)), Ntilde_Hc=[0.1], L_Hp=np.diag(np.arange(1.1, 1000.2)))
+    assert np.allclose(mpc.M_Hp, np.diag(np.arange(1, 1001.0))) and np.allclose(mpc.Ntilde_Hc, [[0.1]])
+    assert np.allclose(mpc.L_Hp, np.diag(np.arange(1.1, 1000.2)))

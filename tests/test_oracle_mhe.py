@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import qp
-from oracle.linmpc import LinModel
+from oracle.linmpc import LinModel, SteadyKalmanFilter
 from oracle.mhe import KalmanFilter, MovingHorizonEstimator
 
 
@@ -125,3 +125,179 @@ def test_host_kalman_filter_mirror_equals_oracle():
             o.updatestate(u[i], y[i], d[i])
         g.updatestate(u, y, d)
         assert np.abs(g.Phat - np.stack([o.Phat for o in os_])).max() < 1e-12
+
+
+def _setup_linmodel_tustin_d():
+    """SetupMPCtests' `sys` as LinModel(sys, Ts, i_u=[1,2], i_d=[3]) builds it (src/model/linmodel.jl:165-198): zero-order
+    hold for the manipulated inputs, Tustin for the measured disturbance (four states, so the default estimators have
+    nx̂ = 6 as the reference's assertions expect), with the operating points of test/2_test_state_estim.jl:1037."""
+    from oracle.linmpc import zoh_first_order
+    Ts = 400.0
+    a1, b1, c1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, c2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+
+    def tustin(k, tau):
+        al = Ts / (2 * tau)
+        p, g = (1 - al) / (1 + al), k * al / (1 + al)
+        return p, g * (1 + p), g
+    p1, cd1, dd1 = tustin(1.90, 1800.0)
+    p2, cd2, dd2 = tustin(-0.74, 800.0)
+    return LinModel(np.diag([a1, a2, p1, p2]), np.array([[b1, b1], [-b2, b2], [0, 0], [0, 0]]),
+                    np.array([[c1, 0, cd1, 0], [0, c2, 0, cd2]]), Bd=np.array([[0.0], [0.0], [1.0], [1.0]]),
+                    Dd=np.array([[dd1], [dd2]]), Ts=Ts, uop=[10, 50], yop=[50, 30], dop=[5])
+
+
+@pytest.mark.parametrize("kw,tol", [(dict(), 1e-3), (dict(nint_u=[1, 1], nint_ym=[0, 0], direct=False), 1e-2)])
+def test_mhe_estimation_known_answers(kw, tol):
+    """test/2_test_state_estim.jl:1039-1078 ("MHE estimation and getinfo (LinModel)", SingleShooting): at the operating
+    point the estimate stays zero (atol 1e-9); with a constant input offset, then a constant output offset, the estimated
+    output returns to the measurement within 40 periods (atol 1e-3 in the current form, 1e-2 in the prediction form)."""
+    mhe = MovingHorizonEstimator(_setup_linmodel_tustin_d(), He=2, **kw)
+    assert mhe.nxhat == 6
+    mhe.preparestate([50, 30], [5])
+    xhat = mhe.updatestate([10, 50], [50, 30], [5])
+    assert xhat == pytest.approx(np.zeros(6), abs=1e-9) and mhe.xhat0 == pytest.approx(np.zeros(6), abs=1e-9)
+    for u, ym in (([11, 52], [50, 30]), ([10, 50], [51, 32])):
+        for _ in range(40):
+            mhe.preparestate(ym, [5])
+            mhe.updatestate(u, ym, [5])
+        if kw.get("direct", True):
+            mhe.preparestate(ym, [5])
+        assert mhe.evaloutput([5]) == pytest.approx(ym, abs=tol)
+
+
+def test_mhe_covariance_constructor_and_nan_measurement():
+    """test/2_test_state_estim.jl:1080-1093 (full Q̂ / R̂ matrices and P̂_0 taken from a SteadyKalmanFilter, no integrators:
+    the estimate stays zero at the operating point) and :1109-1118 (a NaN measurement is left out of the objective,
+    mhe/execute.jl:436-441: the estimate at the operating point is still zero)."""
+    model = _setup_linmodel_tustin_d()
+    Qhat, Rhat = np.diag(np.full(4, 0.25) ** 2), np.eye(2)
+    skf = SteadyKalmanFilter(model, sigmaQ=np.full(4, 0.25), sigmaR=[1, 1], nint_u=0, nint_ym=0)
+    mhe3 = MovingHorizonEstimator(model, He=2, nint_u=0, nint_ym=0, P0hat=skf.Phat, Qhat=Qhat, Rhat=Rhat)
+    mhe3.preparestate([50, 30], [5])
+    xhat = mhe3.updatestate([10, 50], [50, 30], [5])
+    assert xhat == pytest.approx(np.zeros(4), abs=1e-9) and mhe3.xhat0 == pytest.approx(np.zeros(4), abs=1e-9)
+    mhe3.preparestate([50, 30], [5])
+    assert mhe3.evaloutput([5]) == pytest.approx([50, 30], abs=1e-9)
+    mhe4 = MovingHorizonEstimator(model, He=2, direct=True)
+    mhe4.preparestate([50, np.nan], [5])
+    assert mhe4.xhat0 == pytest.approx(np.zeros(6), abs=1e-9)
+    mhe5 = MovingHorizonEstimator(model, He=2, direct=False)
+    mhe5.updatestate([10, 50], [50, np.nan], [5])
+    assert np.isfinite(mhe5.xhat0).all()
+
+
+def test_mhe_setconstraint_known_answers():
+    """test/2_test_state_estim.jl:1385-1490 ("MHE set constraints", LinModel parts): per-stage and whole-window bounds and
+    softness weights (the first nx̂ entries of X̂min / C_x̂min belong to the arrival state), size checks, and what is frozen
+    after the first solve (softness, the +-Inf pattern) or without a slack variable (Cwt = Inf)."""
+    from oracle.linmpc import zoh_first_order
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    # LinModel(sys, Ts, i_u=[1,2]) with uop = [10, 50], yop = [50, 30]: two states, no measured disturbance
+    mk = lambda: LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts, uop=[10, 50], yop=[50, 30])
+    mhe1 = MovingHorizonEstimator(mk(), He=1, nint_ym=0, Cwt=1e3)
+    c = mhe1.con
+    mhe1.setconstraint(xhatmin=[-51, -52], xhatmax=[53, 54])
+    assert np.allclose(c["X0min"], [-51, -52]) and np.allclose(c["X0max"], [53, 54])
+    assert np.allclose(c["xhat0min"], [-51, -52]) and np.allclose(c["xhat0max"], [53, 54])
+    mhe1.setconstraint(whatmin=[-55, -56], whatmax=[57, 58])
+    assert np.allclose(c["Wmin"], [-55, -56]) and np.allclose(c["Wmax"], [57, 58])
+    mhe1.setconstraint(vhatmin=[-59, -60], vhatmax=[61, 62])
+    assert np.allclose(c["Vmin"], [-59, -60]) and np.allclose(c["Vmax"], [61, 62])
+    mhe1.setconstraint(c_xhatmin=[0.01, 0.02], c_xhatmax=[0.03, 0.04])
+    assert np.allclose(c["C_xmin"], [0.01, 0.02]) and np.allclose(c["C_xmax"], [0.03, 0.04])
+    assert np.allclose(c["c_xmin"], [0.01, 0.02]) and np.allclose(c["c_xmax"], [0.03, 0.04])
+    mhe1.setconstraint(c_whatmin=[0.05, 0.06], c_whatmax=[0.07, 0.08])
+    assert np.allclose(c["C_wmin"], [0.05, 0.06]) and np.allclose(c["C_wmax"], [0.07, 0.08])
+    mhe1.setconstraint(c_vhatmin=[0.09, 0.10], c_vhatmax=[0.11, 0.12])
+    assert np.allclose(c["C_vmin"], [0.09, 0.10]) and np.allclose(c["C_vmax"], [0.11, 0.12])
+    # the softness weights are the first column of every block of the QP's A (construct.jl:962-995): one solve shows them
+    mhe1.preparestate([50, 30])
+    P = mhe1.build_qp()
+    assert np.allclose(-P["A"][:, 0], [0.01, 0.02, 0.03, 0.04, 0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.10, 0.11, 0.12])
+
+    mhe2 = MovingHorizonEstimator(mk(), He=4, nint_ym=0, Cwt=1e3)
+    c2 = mhe2.con
+    r = lambda lo, hi: np.arange(lo, hi + 1.0)
+    mhe2.setconstraint(Xhatmin=-r(1, 10), Xhatmax=r(1, 10))
+    assert np.allclose(c2["X0min"], -r(3, 10)) and np.allclose(c2["X0max"], r(3, 10))
+    assert np.allclose(c2["xhat0min"], -r(1, 2)) and np.allclose(c2["xhat0max"], r(1, 2))
+    mhe2.setconstraint(Whatmin=-r(11, 18), Whatmax=r(11, 18))
+    assert np.allclose(c2["Wmin"], -r(11, 18)) and np.allclose(c2["Wmax"], r(11, 18))
+    mhe2.setconstraint(Vhatmin=-r(31, 38), Vhatmax=r(31, 38))
+    assert np.allclose(c2["Vmin"], -r(31, 38)) and np.allclose(c2["Vmax"], r(31, 38))
+    mhe2.setconstraint(C_xhatmin=0.01 * r(1, 10), C_xhatmax=0.02 * r(1, 10))
+    assert np.allclose(c2["C_xmin"], 0.01 * r(3, 10)) and np.allclose(c2["C_xmax"], 0.02 * r(3, 10))
+    assert np.allclose(c2["c_xmin"], 0.01 * r(1, 2)) and np.allclose(c2["c_xmax"], 0.02 * r(1, 2))
+    mhe2.setconstraint(C_whatmin=0.03 * r(11, 18), C_whatmax=0.04 * r(11, 18))
+    assert np.allclose(c2["C_wmin"], 0.03 * r(11, 18)) and np.allclose(c2["C_wmax"], 0.04 * r(11, 18))
+    mhe2.setconstraint(C_vhatmin=0.05 * r(31, 38), C_vhatmax=0.06 * r(31, 38))
+    assert np.allclose(c2["C_vmin"], 0.05 * r(31, 38)) and np.allclose(c2["C_vmax"], 0.06 * r(31, 38))
+    for kw in ("xhatmin", "xhatmax", "whatmin", "whatmax", "vhatmin", "vhatmax",
+               "c_xhatmin", "c_xhatmax", "c_whatmin", "c_whatmax", "c_vhatmin", "c_vhatmax"):
+        with pytest.raises(ValueError):       # DimensionMismatch
+            mhe2.setconstraint(**{kw: [1.0]})
+    assert np.allclose(c2["C_vmax"], 0.06 * r(31, 38)) and np.allclose(c2["X0min"], -r(3, 10))  # nothing stored by a failed call
+    mhe1.updatestate([10, 50], [50, 30])
+    inf = np.inf
+    for kw, v in (("xhatmin", [-inf, -inf]), ("xhatmax", [inf, inf]), ("whatmin", [-inf, -inf]), ("whatmax", [inf, inf]),
+                  ("vhatmin", [-inf, -inf]), ("vhatmax", [inf, inf]), ("c_xhatmin", [100, 100]), ("c_xhatmax", [200, 200]),
+                  ("c_whatmin", [300, 300]), ("c_whatmax", [400, 400]), ("c_vhatmin", [500, 500]), ("c_vhatmax", [600, 600])):
+        with pytest.raises(RuntimeError):     # ErrorException: frozen after the first solve
+            mhe1.setconstraint(**{kw: v})
+    mhe1.setconstraint(xhatmin=[-61, -62])    # finite values may still move
+    assert np.allclose(c["xhat0min"], [-61, -62])
+    mhe4 = MovingHorizonEstimator(mk(), He=1, nint_ym=0, Cwt=inf)
+    for kw in ("c_xhatmin", "c_xhatmax", "c_whatmin", "c_whatmax", "c_vhatmin", "c_vhatmax"):
+        with pytest.raises(ValueError):       # ArgumentError: no slack variable
+            mhe4.setconstraint(**{kw: [1, 1]})
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_mhe_unfilled_window_input_disturbance(direct):
+    """test/2_test_state_estim.jl:1313-1336 ("MHE estimation with unfilled window"): x(k+1) = 0.5 x + u, y = x (the
+    reference builds it as a NonLinModel; the dynamics are linear, so the linear MHE solves the same windows), the plant
+    receives u = 0.1 while the estimator is told u = 0: with an input integrator (nint_u = 1) the estimated output equals
+    the plant output within 1e-6, from the growing window (He = 3) on."""
+    mk = lambda: LinModel(np.array([[0.5]]), np.array([[1.0]]), np.array([[1.0]]), Ts=10.0)
+    plant = mk()
+    mhe = MovingHorizonEstimator(mk(), He=3, nint_u=[1], direct=direct)
+    for _ in range(40):
+        y = plant.evaloutput()
+        mhe.preparestate(y)
+        mhe.updatestate([0.0], y)
+        plant.updatestate([0.1])
+    mhe.preparestate(plant.evaloutput())
+    assert mhe.evaloutput() == pytest.approx(plant.evaloutput(), abs=1e-6)
+
+
+def test_mhe_construction_known_answers():
+    """test/2_test_state_estim.jl:886-976 ("MHE construction (LinModel)", the parts of the linear SingleShooting path):
+    sizes of the augmented state and of the decision vector with and without the slack variable, the measured-output
+    selection, covariances built from the standard deviations, window lengths, integrator choices, error cases."""
+    model = _setup_linmodel_tustin_d()
+    mhe1 = MovingHorizonEstimator(model, He=5)
+    assert (mhe1.nym, mhe1.nxhat) == (2, 6) and mhe1.nxhat - model.nx == 2
+    assert mhe1.E.shape[1] == 6 * mhe1.nxhat and mhe1.nZ == mhe1.nxhat + mhe1.nxhat * 5
+    mhe3 = MovingHorizonEstimator(model, He=5, i_ym=[1])                       # the reference's i_ym=[2] (1-based)
+    assert (mhe3.nym, model.ny - mhe3.nym, mhe3.nxhat) == (1, 1, 5)
+    mhe4 = MovingHorizonEstimator(model, He=5, sigmaQ=[1, 2, 3, 4], sigmaQint_ym=[5, 6], sigmaR=[7, 8])
+    assert np.array_equal(mhe4.Qhat, np.diag([1.0, 4, 9, 16, 25, 36])) and np.array_equal(mhe4.Rhat, np.diag([49.0, 64]))
+    assert MovingHorizonEstimator(model, He=5, nint_ym=[2, 2]).nxhat == 8
+    mhe6 = MovingHorizonEstimator(model, He=5, sigmaP_0=[1, 2, 3, 4], sigmaPint_ym_0=[5, 6])
+    assert np.array_equal(mhe6.P0hat, np.diag([1.0, 4, 9, 16, 25, 36])) and np.array_equal(mhe6.Parr_old, mhe6.P0hat)
+    assert mhe6.Parr_old is not mhe6.P0hat
+    assert np.allclose(mhe6.invPbar, np.linalg.inv(np.diag(np.arange(1, 7.0) ** 2)))
+    mhe7 = MovingHorizonEstimator(model, He=10)
+    assert (mhe7.X0_old.size, mhe7.Y0m.size, mhe7.U0.size, mhe7.D0.size) == (60, 20, 20, 11)
+    mhe8 = MovingHorizonEstimator(model, He=5, nint_u=[1, 1], nint_ym=[0, 0])
+    assert mhe8.nxhat == 6 and list(mhe8.nint_u) == [1, 1] and list(mhe8.nint_ym) == [0, 0]
+    mhe12 = MovingHorizonEstimator(model, He=5, Cwt=1e3)
+    assert mhe12.nZ == 6 * mhe12.nxhat + 1 and mhe12.Cwt == 1e3
+    for kw in (dict(He=0), dict(He=5, Cwt=-1)):
+        with pytest.raises(ValueError):
+            MovingHorizonEstimator(model, **kw)
+    with pytest.raises(TypeError):  # He has no default (ArgumentError in the reference)
+        MovingHorizonEstimator(model)
