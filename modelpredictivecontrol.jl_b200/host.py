@@ -227,7 +227,25 @@ class SteadyKalmanFilter:
         y0m = _b(ym, self.model.N, (len(self.i_ym),)) - self.model.yop[:, self.i_ym]
         d0 = self._d0(d)
         v = y0m - (np.einsum("nij,nj->ni", self.Cmhat, self.xhat0) + np.einsum("nij,nj->ni", self.Ddmhat, d0))
+        # an instance with a NaN measurement skips its correction step (kalman.jl:245-251, :478-484)
+        self._nan_ym = np.isnan(y0m).any(axis=1)
+        if self._nan_ym.any():
+            v = np.where(self._nan_ym[:, None], 0.0, v)
         self.xhat0 = self.xhat0 + np.einsum("nij,nj->ni", self.Khat, v)
+        return self.xhat0 + self.xophat
+
+    def initstate(self, u, ym, d=None):
+        """initstate! (init_estimate!, src/estimator/execute.jl:246-259): the steady state of the augmented model for the
+        inputs u, d that reproduces the measurement ym (least squares, one system per instance)."""
+        m, N = self.model, self.model.N
+        u0 = _b(u, N, (m.nu,)) - m.uop
+        y0m = _b(ym, N, (len(self.i_ym),)) - m.yop[:, self.i_ym]
+        d0 = self._d0(d)
+        rhs_x = (self.fophat - self.xophat + np.einsum("nij,nj->ni", self.Buhat, u0) + np.einsum("nij,nj->ni", self.Bdhat, d0))
+        rhs_y = y0m - np.einsum("nij,nj->ni", self.Ddmhat, d0)
+        M = np.concatenate([np.eye(self.nxhat) - self.Ahat, self.Cmhat], axis=1)
+        rhs = np.concatenate([rhs_x, rhs_y], axis=1)
+        self.xhat0 = np.stack([np.linalg.lstsq(M[i], rhs[i], rcond=None)[0] for i in range(N)])
         return self.xhat0 + self.xophat
 
     def updatestate(self, u, ym, d=None):
@@ -275,7 +293,8 @@ class KalmanFilter(SteadyKalmanFilter):
         M = Cm @ PCt + self.Rhat
         self.Khat = np.swapaxes(np.linalg.solve(np.swapaxes(M, 1, 2), np.swapaxes(PCt, 1, 2)), 1, 2)
         out = SteadyKalmanFilter.preparestate(self, ym, d)
-        self.Phat = self._herm_lower((np.eye(self.nxhat) - self.Khat @ Cm) @ P)
+        Pc = self._herm_lower((np.eye(self.nxhat) - self.Khat @ Cm) @ P)
+        self.Phat = np.where(self._nan_ym[:, None, None], P, Pc) if self._nan_ym.any() else Pc  # (no correction on NaN)
         return out
 
     def updatestate(self, u, ym, d=None):

@@ -386,7 +386,21 @@ class KalmanFilter(StateEstimator):
         sQ = np.concatenate([one(sigmaQ, nx, 1 / nx), one(sigmaQint_u, nsu, 1.0), one(sigmaQint_ym, nsy, 1.0)])
         self.Phat, self.Qhat, self.Rhat = np.diag(sP ** 2), np.diag(sQ ** 2), np.diag(one(sigmaR, nym, 1.0) ** 2)
 
+    def setstate(self, xhat, Phat=None):
+        """setstate!(estim, x̂, P̂) (src/estimator/execute.jl:424-438)."""
+        xhat = np.asarray(xhat, float).reshape(-1)
+        if xhat.size != self.nxhat:
+            raise ValueError(f"xhat size must be ({self.nxhat},)")
+        self.xhat0 = xhat - self.xophat
+        if Phat is not None:
+            Phat = np.asarray(Phat, float)
+            if Phat.shape != (self.nxhat, self.nxhat):
+                raise ValueError(f"Phat size must be ({self.nxhat}, {self.nxhat})")
+            self.Phat = np.tril(Phat) + np.tril(Phat, -1).T
+
     def correct_estimate(self, y0m, d0):
+        if np.isnan(y0m).any():  # kalman.jl:478-482: the correction is skipped
+            return
         P, Cm = self.Phat, self.Cmhat
         M = Cm @ P @ Cm.T + self.Rhat
         K = np.linalg.solve(M.T, (P @ Cm.T).T).T

@@ -598,3 +598,48 @@ def test_explicitmpc_known_answers():
     mpc.setmodel(M_Hp=np.diag(np.arange(1, 1001.0)), Ntilde_Hc=[0.1], L_Hp=np.diag(np.arange(1.1, 1000.2)))
     assert np.allclose(mpc.M_Hp, np.diag(np.arange(1, 1001.0))) and np.allclose(mpc.Ntilde_Hc, [[0.1]])
     assert np.allclose(mpc.L_Hp, np.diag(np.arange(1.1, 1000.2)))
+
+
+def test_steady_kalman_filter_estimator_methods():
+    """test/2_test_state_estim.jl:64-127 ("SKF estimator methods"): the observer that feeds x̂0 to moveinput! (and that the
+    step kernels can run fused): zero estimate at the operating point, initstate!, setstate!, convergence of the estimated
+    output under an input offset and an output offset in the current (direct) and prediction forms, NaN measurements
+    skipped (kalman.jl:248-251)."""
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    mk = lambda: LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts, uop=[10, 50], yop=[50, 30])
+    kf1 = SteadyKalmanFilter(mk(), nint_ym=[1, 1])
+    u, y = [10, 50], [50, 30]
+    kf1.preparestate(y)
+    assert kf1.updatestate(u, y) == pytest.approx(np.zeros(4), abs=1e-12)
+    kf1.preparestate(y)
+    assert kf1.evaloutput() == pytest.approx([50, 30])
+    assert kf1.initstate([10, 50], [50, 30 + 1]) == pytest.approx([0, 0, 0, 1], abs=1e-9)
+    # an integrating plant and a first-order one, input integrators, prediction form (:81-85)
+    ad, bd, cd = (m[0, 0] for m in zoh_first_order(2, 10, 1.0))
+    m2 = LinModel(np.diag([1.0, ad]), np.diag([1.0, bd]), np.diag([1.0, cd]), Ts=1.0)
+    kf2 = SteadyKalmanFilter(m2, nint_u=[1, 1], direct=False)
+    x = kf2.initstate([10, 3], [0.5, 6 + 0.1])
+    assert kf2.evaloutput() == pytest.approx([0.5, 6.1])
+    assert kf2.updatestate([10, 3], [0.5, 6 + 0.1]) == pytest.approx(x, abs=1e-9)
+    kf1.setstate([1, 2, 3, 4])
+    assert kf1.xhat0 == pytest.approx([1, 2, 3, 4])
+    for est, prep in ((kf1, True), (SteadyKalmanFilter(mk(), nint_u=[1, 1], direct=False), False)):
+        for uu, ym in (([11, 52], [50, 30]), ([10, 50], [51, 32])):
+            for _ in range(40):
+                est.preparestate(ym)
+                est.updatestate(uu, ym)
+            if prep:
+                est.preparestate(ym)
+            assert est.evaloutput() == pytest.approx(ym, abs=1e-3)
+    kf3 = SteadyKalmanFilter(LinModel(0.5 * np.ones((1, 1)), np.ones((1, 1)), np.ones((1, 1)), Ts=1.0))
+    kf3.preparestate([0])
+    assert kf3.updatestate([0], [0]) == pytest.approx([0, 0], abs=1e-12)
+    kf4 = SteadyKalmanFilter(mk(), nint_ym=[1, 1], direct=True)
+    kf4.xhat0[:] = 7
+    kf4.preparestate([55, np.nan])
+    assert (kf4.xhat0 == 7).all()
+    kf5 = SteadyKalmanFilter(mk(), nint_ym=[1, 1], direct=False)
+    kf5.updatestate([10, 50], [55, np.nan])
+    assert np.isfinite(kf5.xhat0).all()

@@ -301,3 +301,88 @@ def test_mhe_construction_known_answers():
             MovingHorizonEstimator(model, **kw)
     with pytest.raises(TypeError):  # He has no default (ArgumentError in the reference)
         MovingHorizonEstimator(model)
+
+
+def test_kalman_filter_estimator_methods_and_setmodel():
+    """test/2_test_state_estim.jl:207-265 ("KF estimator methods") and :268-294 ("KF set model"): the time-varying
+    KalmanFilter the step kernels can run fused (bmpc_set_estimator_cov) and that `setmodel!` needs."""
+    from oracle.linmpc import zoh_first_order
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    mk = lambda: LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts, uop=[10, 50], yop=[50, 30])
+    kf1 = KalmanFilter(mk())
+    kf1.preparestate([50, 30])
+    assert kf1.updatestate([10, 50], [50, 30]) == pytest.approx(np.zeros(4), abs=1e-12)
+    kf1.preparestate([50, 30])
+    assert kf1.evaloutput() == pytest.approx([50, 30])
+    assert kf1.initstate([10, 50], [50, 30 + 1]) == pytest.approx([0, 0, 0, 1], abs=1e-9)
+    kf1.setstate([1, 2, 3, 4], np.diag([0.1, 0.2, 0.3, 0.4]))
+    assert kf1.xhat0 == pytest.approx([1, 2, 3, 4]) and np.allclose(kf1.Phat, np.diag([0.1, 0.2, 0.3, 0.4]))
+    for est, prep in ((kf1, True), (KalmanFilter(mk(), nint_u=[1, 1], direct=False), False)):
+        for uu, ym in (([11, 52], [50, 30]), ([10, 50], [51, 32])):
+            for _ in range(40):
+                est.preparestate(ym)
+                est.updatestate(uu, ym)
+            if prep:
+                est.preparestate(ym)
+            assert est.evaloutput() == pytest.approx(ym, abs=1e-3)
+    kf4 = KalmanFilter(mk(), direct=True)
+    kf4.xhat0[:] = 7
+    kf4.preparestate([55, np.nan])
+    assert (kf4.xhat0 == 7).all()
+    kf5 = KalmanFilter(mk(), direct=False)
+    kf5.updatestate([10, 50], [55, np.nan])
+    assert np.isfinite(kf5.xhat0).all()
+    # set model
+    lin = lambda a, uop, yop, xop: LinModel([[a]], [[0.3]], [[1.0]], Ts=10.0, uop=[uop], yop=[yop], xop=[xop], fop=[xop])
+    kf = KalmanFilter(lin(0.5, 2.0, 50.0, 3.0), nint_ym=0)
+    assert np.allclose(kf.Ahat, [[0.5]])
+    kf.preparestate([50.0])
+    assert kf.evaloutput() == pytest.approx([50.0])
+    kf.preparestate([50.0])
+    assert kf.updatestate([2.0], [50.0]) == pytest.approx([3.0])
+    kf.setmodel(lin(0.2, 3.0, 55.0, 3.0))
+    assert np.allclose(kf.Ahat, [[0.2]])
+    kf.preparestate([55.0])
+    assert kf.evaloutput() == pytest.approx([55.0])
+    kf.preparestate([55.0])
+    assert kf.updatestate([3.0], [55.0]) == pytest.approx([3.0])
+    kf.setmodel(lin(0.2, 3.0, 55.0, 8.0))
+    assert kf.xhat0 == pytest.approx([3.0 - 8.0])
+    kf.setmodel(kf.model, Qhat=[1e-3], Rhat=[1e-6])
+    assert np.allclose(kf.Qhat, [[1e-3]]) and np.allclose(kf.Rhat, [[1e-6]])
+
+
+def test_host_estimator_mirrors_nan_and_initstate():
+    """Host mirror (modelpredictivecontrol.jl_b200/host.py, runs on the CPU) against the oracle for the estimator behaviour
+    the reference tests in test/2_test_state_estim.jl:77,114-126,220,252-264: `initstate!` and a NaN measurement (the
+    instance that has one skips its correction, the others do not), for SteadyKalmanFilter and KalmanFilter."""
+    import mpc_b200
+    from oracle.linmpc import LinModel as OLinModel
+    from oracle.mhe import KalmanFilter as OKF
+    N = 4
+    rng = np.random.default_rng(3)
+    A = 0.5 * rng.standard_normal((N, 3, 3)) / 2
+    Bu, C = rng.standard_normal((N, 3, 2)), rng.standard_normal((N, 2, 3))
+    op = dict(uop=[1.0, -2.0], yop=[5.0, 3.0])
+    for G, O in ((mpc_b200.SteadyKalmanFilter, SteadyKalmanFilter), (mpc_b200.KalmanFilter, OKF)):
+        g = G(mpc_b200.LinModel(A, Bu, C, N=N, **op))
+        os_ = [O(OLinModel(A[i], Bu[i], C[i], **op)) for i in range(N)]
+        u, y = 1 + rng.standard_normal((N, 2)), 5 + rng.standard_normal((N, 2))
+        xg = g.initstate(u, y)
+        for i, o in enumerate(os_):
+            assert np.abs(xg[i] - o.initstate(u[i], y[i])).max() < 1e-9
+        for k in range(6):
+            y = 5 + rng.standard_normal((N, 2))
+            if k == 2:
+                y[1, 0] = np.nan          # one instance, one channel
+            u = rng.standard_normal((N, 2))
+            xg = g.preparestate(y)
+            for i, o in enumerate(os_):
+                xo = o.preparestate(y[i])
+                assert np.isfinite(xg[i]).all() and np.abs(xg[i] - xo).max() < 1e-11 * (1 + np.abs(xo).max()), (G.__name__, k, i)
+                if hasattr(o, "Phat") and G is mpc_b200.KalmanFilter:
+                    assert np.abs(g.Phat[i] - o.Phat).max() < 1e-11
+                o.updatestate(u[i], y[i])
+            g.updatestate(u, y)
