@@ -30,10 +30,13 @@ def move_blocking(Hp, Hc):
 # Batched host-side constructors (numpy, leading axis = instance).  They mirror the reference's
 # one-off setup code; nothing here runs per control period except the tiny estimator updates.
 # ----------------------------------------------------------------------------------------------
-def _b(a, N, shape):
-    """Broadcast a per-model array to (N, *shape)."""
+def _b(a, N, shape, strict=False):
+    """Broadcast a per-model array to (N, *shape).  ``strict``: a shared array must have exactly ``shape`` (no numpy
+    broadcasting of length-1 axes: the reference's DimensionMismatch for `setconstraint!` arguments)."""
     a = np.asarray(a, dtype=np.float64)
     if a.ndim == len(shape):
+        if strict and a.shape != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
         a = np.broadcast_to(a, (N,) + tuple(shape))
     if a.shape != (N,) + tuple(shape):
         raise ValueError(f"expected shape {(N,) + tuple(shape)}, got {a.shape}")

@@ -166,7 +166,7 @@ class LinMPC:
         N, Hp, Hc = self.model.N, self.Hp, self.Hc
         nu, ny, nx = self.model.nu, self.model.ny, self.estim.nxhat
         c = self.con
-        rep = lambda v, n, k: np.tile(_b(v, N, (n,)), (1, k))
+        rep = lambda v, n, k: np.tile(_b(v, N, (n,), strict=True), (1, k))
         if Umin is None and umin is not None: c["U0min"] = rep(umin, nu, Hp) - self.Uop
         elif Umin is not None: c["U0min"] = _b(Umin, N, (nu * Hp,)) - self.Uop
         if Umax is None and umax is not None: c["U0max"] = rep(umax, nu, Hp) - self.Uop

@@ -145,12 +145,12 @@ class MovingHorizonEstimator:
                       c_xhatmin=None, c_xhatmax=None, c_whatmin=None, c_whatmax=None, c_vhatmin=None, c_vhatmax=None):
         N, nxh, nym = self.model.N, self.nxhat, self.nym
         c = self.con
-        if xhatmin is not None: c["xmin"] = _b(xhatmin, N, (nxh,)) - self.xophat
-        if xhatmax is not None: c["xmax"] = _b(xhatmax, N, (nxh,)) - self.xophat
-        if whatmin is not None: c["wmin"] = _b(whatmin, N, (nxh,)).copy()
-        if whatmax is not None: c["wmax"] = _b(whatmax, N, (nxh,)).copy()
-        if vhatmin is not None: c["vmin"] = _b(vhatmin, N, (nym,)).copy()
-        if vhatmax is not None: c["vmax"] = _b(vhatmax, N, (nym,)).copy()
+        if xhatmin is not None: c["xmin"] = _b(xhatmin, N, (nxh,), strict=True) - self.xophat
+        if xhatmax is not None: c["xmax"] = _b(xhatmax, N, (nxh,), strict=True) - self.xophat
+        if whatmin is not None: c["wmin"] = _b(whatmin, N, (nxh,), strict=True).copy()
+        if whatmax is not None: c["wmax"] = _b(whatmax, N, (nxh,), strict=True).copy()
+        if vhatmin is not None: c["vmin"] = _b(vhatmin, N, (nym,), strict=True).copy()
+        if vhatmax is not None: c["vmax"] = _b(vhatmax, N, (nym,), strict=True).copy()
         ecr = [c_xhatmin, c_xhatmax, c_whatmin, c_whatmax, c_vhatmin, c_vhatmax]
         if any(e is not None for e in ecr):
             if not self.neps:
@@ -158,12 +158,21 @@ class MovingHorizonEstimator:
             if self._solved:
                 raise RuntimeError("Cannot set softness parameters after calling updatestate!")
             s = self.soft
-            if c_xhatmin is not None: s["c_x"][:nxh] = c_xhatmin
-            if c_xhatmax is not None: s["c_x"][nxh:] = c_xhatmax
-            if c_whatmin is not None: s["c_w"][:nxh] = c_whatmin
-            if c_whatmax is not None: s["c_w"][nxh:] = c_whatmax
-            if c_vhatmin is not None: s["c_v"][:nym] = c_vhatmin
-            if c_vhatmax is not None: s["c_v"][nym:] = c_vhatmax
+
+            def w(v, n, name):  # sizes and signs are checked before anything is stored (DimensionMismatch / error)
+                v = np.asarray(v, dtype=np.float64).reshape(-1)
+                if v.size != n:
+                    raise ValueError(f"{name} size must be ({n},)")
+                if (v < 0).any():
+                    raise ValueError(f"{name} weights should be non-negative")
+                return v
+            new = [(k, sl, w(v, n, name)) for k, sl, v, n, name in (
+                ("c_x", slice(0, nxh), c_xhatmin, nxh, "c_xhatmin"), ("c_x", slice(nxh, 2 * nxh), c_xhatmax, nxh, "c_xhatmax"),
+                ("c_w", slice(0, nxh), c_whatmin, nxh, "c_whatmin"), ("c_w", slice(nxh, 2 * nxh), c_whatmax, nxh, "c_whatmax"),
+                ("c_v", slice(0, nym), c_vhatmin, nym, "c_vhatmin"), ("c_v", slice(nym, 2 * nym), c_vhatmax, nym, "c_vhatmax"))
+                   if v is not None]
+            for k, sl, v in new:
+                s[k][sl] = v
         a = [np.ascontiguousarray(c[k]) for k in ("xmin", "xmax", "wmin", "wmax", "vmin", "vmax")]
         sv = [np.ascontiguousarray(self.soft[k]) for k in ("c_x", "c_w", "c_v")]
         check(_lib.lib().bmhe_set_constraints(self._h, *[dptr(x) for x in a], *[dptr(x) for x in sv]))

@@ -90,3 +90,47 @@ def test_mirror_setconstraint_matches_oracle_and_reference_errors():
     nowt = _stand_in(N, nu, ny, nx, Hp, Hc, 0)
     with pytest.raises(ValueError):
         nowt.setconstraint(wmin=[0])
+
+
+def test_mhe_mirror_setconstraint_on_stand_in(monkeypatch):
+    """Same for the estimator mirror (modelpredictivecontrol.jl_b200/mhe.py::setconstraint): the C-ABI call is replaced by
+    a recorder; bounds go out in deviation form per instance, softness as [min; max] pairs; sizes, negative weights, the
+    post-solve freeze and Cwt = Inf raise as in the reference (test/2_test_state_estim.jl:1452-1489)."""
+    from mpc_b200 import _lib, mhe as gmhe
+    calls = []
+
+    class FakeLib:
+        def bmhe_set_constraints(self, h, *ptrs):
+            calls.append(ptrs)
+            return 0
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib())
+    N, nxh, nym = 3, 2, 2
+    inf = np.inf
+    o = types.SimpleNamespace(
+        model=types.SimpleNamespace(N=N), nxhat=nxh, nym=nym, xophat=np.tile([1.0, 2.0], (N, 1)), neps=1, _solved=False, _h=None,
+        con=dict(xmin=np.full((N, nxh), -inf), xmax=np.full((N, nxh), inf), wmin=np.full((N, nxh), -inf),
+                 wmax=np.full((N, nxh), inf), vmin=np.full((N, nym), -inf), vmax=np.full((N, nym), inf)),
+        soft=dict(c_x=np.zeros(2 * nxh), c_w=np.zeros(2 * nxh), c_v=np.zeros(2 * nym)))
+    sc = lambda **kw: gmhe.MovingHorizonEstimator.setconstraint(o, **kw)
+    sc(xhatmin=[-51, -52], xhatmax=[53, 54])
+    assert np.array_equal(o.con["xmin"], np.tile([-52.0, -54.0], (N, 1))) and np.array_equal(o.con["xmax"], np.tile([52.0, 52.0], (N, 1)))
+    sc(whatmin=[-55, -56], whatmax=[57, 58], vhatmin=[-59, -60], vhatmax=[61, 62])
+    assert np.array_equal(o.con["wmin"][1], [-55, -56]) and np.array_equal(o.con["vmax"][2], [61, 62])
+    sc(c_xhatmin=[0.01, 0.02], c_xhatmax=[0.03, 0.04], c_whatmin=[0.05, 0.06], c_whatmax=[0.07, 0.08],
+       c_vhatmin=[0.09, 0.10], c_vhatmax=[0.11, 0.12])
+    assert np.allclose(o.soft["c_x"], [0.01, 0.02, 0.03, 0.04]) and np.allclose(o.soft["c_w"], [0.05, 0.06, 0.07, 0.08])
+    assert np.allclose(o.soft["c_v"], [0.09, 0.10, 0.11, 0.12]) and len(calls) == 3
+    before = {k: v.copy() for k, v in o.soft.items()}
+    for kw in ("xhatmin", "xhatmax", "whatmin", "whatmax", "vhatmin", "vhatmax",
+               "c_xhatmin", "c_xhatmax", "c_whatmin", "c_whatmax", "c_vhatmin", "c_vhatmax"):
+        with pytest.raises(ValueError):
+            sc(**{kw: [1.0]})
+    with pytest.raises(ValueError):
+        sc(c_xhatmin=[-1, 0], c_vhatmax=[5, 5])
+    assert all(np.array_equal(before[k], o.soft[k]) for k in before) and len(calls) == 3
+    o._solved = True
+    with pytest.raises(RuntimeError):
+        sc(c_xhatmin=[100, 100])
+    o._solved, o.neps = False, 0
+    with pytest.raises(ValueError):
+        sc(c_whatmax=[1, 1])
