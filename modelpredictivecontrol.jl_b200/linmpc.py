@@ -208,6 +208,16 @@ class LinMPC:
         self._push()
         return self
 
+    def initstate(self, u, ym, d=None):
+        """``initstate!(mpc, u, ym, d)`` (src/controller/execute.jl:1-13): the estimator's steady state for (u, ym, d), the
+        warm start Z̃ cleared, u - uop stored as u0(k-1)."""
+        if self.fused_estimator:
+            raise NotImplementedError("initstate with the fused estimator: set the state with batch.set_state")
+        m = self.model
+        self.batch.Ztilde[:] = 0.0
+        self.batch.lastu0[:] = _b(u, m.N, (m.nu,)) - m.uop
+        return self.estim.initstate(u, ym, d)
+
     # ---- estimator pass-throughs ----
     def preparestate(self, ym, d=None):
         if self.fused_estimator:

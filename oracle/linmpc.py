@@ -842,9 +842,16 @@ class LinMPC:
     def updatestate(self, u, ym, d=()):
         return self.estim.updatestate(u, ym, d)
 
-    def setstate(self, xhat):
-        self.estim.setstate(xhat)
+    def setstate(self, xhat, *cov):
+        self.estim.setstate(xhat, *cov)
         return self
+
+    def initstate(self, u, ym, d=()):
+        """initstate!(mpc, u, ym, d) (src/controller/execute.jl:11-23): the estimator's steady state, and the warm start of
+        the decision vector cleared."""
+        self.Ztilde[:] = 0.0
+        self.lastu0 = np.asarray(u, float).reshape(-1) - self.model.uop
+        return self.estim.initstate(u, ym, d)
 
 
 def _setmodel_linmpc(self, model=None, Mwt=None, Nwt=None, Lwt=None, M_Hp=None, Ntilde_Hc=None, L_Hp=None, **kw):

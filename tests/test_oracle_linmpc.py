@@ -643,3 +643,31 @@ def test_steady_kalman_filter_estimator_methods():
     kf5 = SteadyKalmanFilter(mk(), nint_ym=[1, 1], direct=False)
     kf5.updatestate([10, 50], [55, np.nan])
     assert np.isfinite(kf5.xhat0).all()
+
+
+def test_linmpc_other_methods_and_moveinput_argument_sizes():
+    """test/3_test_predictive_control.jl:239-257 ("LinMPC other methods": initstate!, setstate!(mpc, x̂, P̂) and a period at
+    the operating point through the controller's pass-throughs, KalmanFilter estimator) and :153-157 (moveinput!'s
+    validate_args, construct.jl:702-710: DimensionMismatch -> ValueError)."""
+    from oracle.mhe import KalmanFilter
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    model = LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts, uop=[10, 50], yop=[50, 30])
+    mpc1 = LinMPC(KalmanFilter(model))
+    assert mpc1.initstate([10, 50], [50, 30 + 1]) == pytest.approx([0, 0, 0, 1], abs=1e-9)
+    mpc1.setstate([1, 2, 3, 4], np.diag([0.1, 0.2, 0.3, 0.4]))
+    assert mpc1.estim.xhat0 == pytest.approx([1, 2, 3, 4]) and np.allclose(mpc1.estim.Phat, np.diag([0.1, 0.2, 0.3, 0.4]))
+    mpc1.setstate([0, 0, 0, 0], np.diag(np.r_[np.full(2, 0.5), 1, 1]) ** 2)
+    mpc1.preparestate([50, 30])
+    mpc1.updatestate(model.uop, [50, 30])
+    assert mpc1.estim.xhat0 == pytest.approx(np.zeros(4), abs=1e-12)
+    with pytest.raises(TypeError):  # updatestate!(mpc1, [0, 0]) without ym: ArgumentError in the reference
+        mpc1.updatestate([0, 0])
+    lin = LinModel(*zoh_first_order(5, 2, 3.0), Ts=3.0, yop=[10])
+    m = LinMPC(lin, Nwt=[0], Hp=1000, Hc=1)
+    m.preparestate([10])
+    for kw in (dict(ry=[0, 0, 0]), dict(ry=[0], d=[0, 0]), dict(Dhat=np.zeros(m.Hp + 1)), dict(Rhat_y=np.zeros(m.Hp + 1)),
+               dict(Rhat_u=np.zeros(m.Hp + 1))):
+        with pytest.raises(ValueError):
+            m.moveinput(**kw)
