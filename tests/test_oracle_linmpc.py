@@ -671,3 +671,109 @@ def test_linmpc_other_methods_and_moveinput_argument_sizes():
                dict(Rhat_u=np.zeros(m.Hp + 1))):
         with pytest.raises(ValueError):
             m.moveinput(**kw)
+
+
+def test_internalmodel_construction_and_setmodel():
+    """test/2_test_state_estim.jl:406-475 ("IM construction": sizes for the default integrators and a measured-output
+    subset, a user stochastic model kept as given, the error cases) and :523-547 ("IM set model")."""
+    from oracle.linmpc import InternalModel
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    linmodel = LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts)
+    im1 = InternalModel(linmodel)
+    assert (len(im1.i_ym), linmodel.ny - len(im1.i_ym), im1.nxs, im1.nxhat) == (2, 0, 2, 2)
+    linmodel2 = _setup_sys_model_id3()
+    im2 = InternalModel(linmodel2, i_ym=[1])                        # the reference's i_ym=[2] (1-based)
+    assert (len(im2.i_ym), linmodel2.ny - len(im2.i_ym), im2.nxs, im2.nxhat) == (1, 1, 1, 4)
+    rng = np.random.default_rng(5)
+    As, Bs, Cs, Ds = 0.4 * rng.standard_normal((4, 4)), rng.standard_normal((4, 2)), rng.standard_normal((2, 4)), np.eye(2)
+    im5 = InternalModel(linmodel2, stoch_ym=(As, Bs, Cs, Ds))
+    assert (im5.nxs, im5.nxhat) == (4, 4)
+    assert np.array_equal(im5.As, As) and np.array_equal(im5.Bs, Bs) and np.array_equal(im5.Cs, Cs) and np.array_equal(im5.Ds, Ds)
+    with pytest.raises(ValueError):   # integrating / unstable plant model
+        InternalModel(LinModel(np.diag([0.5, -0.5, 1.5]), np.ones((3, 1)), np.eye(3), Ts=1.0))
+    with pytest.raises(ValueError):   # one stochastic output for two measured outputs
+        InternalModel(linmodel, stoch_ym=([[1.0]], [[1.0]], [[1.0]], [[1.0]]))
+    with pytest.raises(ValueError):   # no direct transmission
+        InternalModel(linmodel, stoch_ym=(np.eye(2), np.eye(2), np.eye(2), np.zeros((2, 2))))
+    # set model
+    lin = lambda a, uop, yop, xop: LinModel([[a]], [[0.3]], [[1.0]], Ts=10.0, uop=[uop], yop=[yop], xop=[xop], fop=[xop])
+    im = InternalModel(lin(0.5, 2.0, 50.0, 3.0))
+    assert np.allclose(im.Ahat, [[0.5]])
+    im.preparestate([50.0])
+    assert im.evaloutput() == pytest.approx([50.0])
+    im.preparestate([50.0])
+    assert im.updatestate([2.0], [50.0]) == pytest.approx([3.0])
+    im.setmodel(lin(0.2, 3.0, 55.0, 3.0))
+    assert np.allclose(im.Ahat, [[0.2]])
+    im.preparestate([55.0])
+    assert im.evaloutput() == pytest.approx([55.0])
+    im.preparestate([55.0])
+    assert im.updatestate([3.0], [55.0]) == pytest.approx([3.0])
+    im.setmodel(lin(0.2, 3.0, 55.0, 8.0))
+    assert im.xhat0 == pytest.approx([3.0 - 8.0])
+
+
+def test_manual_estimator_construction_and_methods():
+    """test/2_test_state_estim.jl:1889-1960 ("Manual construction", "Manual estimator methods", LinModel parts): the
+    ManualEstimator is the reference's own seam for an externally supplied x̂0 (src/estimator/manual.jl:60-64,150-154) -- the
+    one the C ABI's `xhat0` argument stands for: same augmentation as the other estimators, preparestate! / updatestate!
+    leave the state alone, setstate! sets it."""
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    linmodel = LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts)
+    m1 = ManualEstimator(linmodel)
+    assert (len(m1.i_ym), m1.nxs, m1.nxhat, list(m1.nint_ym)) == (2, 2, 4, [1, 1])
+    m2 = ManualEstimator(_setup_sys_model_id3(), i_ym=[1])           # the reference's i_ym=[2] (1-based)
+    assert (len(m2.i_ym), m2.nxs, m2.nxhat, list(m2.nint_ym)) == (1, 1, 5, [1])
+    m3 = ManualEstimator(linmodel, nint_ym=0)
+    assert (m3.nxs, m3.nxhat, list(m3.nint_ym)) == (0, 2, [0, 0])
+    m4 = ManualEstimator(linmodel, nint_ym=[2, 2])
+    assert (m4.nxs, m4.nxhat) == (4, 6)
+    m5 = ManualEstimator(linmodel, nint_u=[1, 1])
+    assert (m5.nxs, m5.nxhat, list(m5.nint_u), list(m5.nint_ym)) == (2, 4, [1, 1], [0, 0])
+    m1.preparestate([50, 30])
+    assert (m1.xhat0 == 0).all()
+    m1.updatestate([11, 52], [50, 30])
+    assert (m1.xhat0 == 0).all()
+    m1.setstate([1, 2, 3, 4])
+    assert m1.xhat0 == pytest.approx([1, 2, 3, 4])
+
+
+def test_steady_kalman_filter_construction():
+    """test/2_test_state_estim.jl:1-62 ("SKF construction"): augmentation sizes for the default and the given integrators
+    (default_nint leaves an integrating output without one, estimator/construct.jl), covariances from standard deviations,
+    and the error cases (sizes, negative counts, unobservable augmentations)."""
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    linmodel = LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts)
+    k1 = SteadyKalmanFilter(linmodel)
+    assert (len(k1.i_ym), k1.nxs, k1.nxhat, list(k1.nint_ym)) == (2, 2, 4, [1, 1])
+    linmodel2 = _setup_sys_model_id3()
+    k2 = SteadyKalmanFilter(linmodel2, i_ym=[1])
+    assert (len(k2.i_ym), k2.nxs, k2.nxhat, list(k2.nint_ym)) == (1, 1, 5, [1])
+    k3 = SteadyKalmanFilter(linmodel, nint_ym=0)
+    assert (k3.nxs, k3.nxhat, list(k3.nint_ym)) == (0, 2, [0, 0])
+    k4 = SteadyKalmanFilter(linmodel, nint_ym=[2, 2])
+    assert (k4.nxs, k4.nxhat) == (4, 6)
+    k5 = SteadyKalmanFilter(linmodel2, sigmaQ=[1, 2, 3, 4], sigmaQint_ym=[5, 6], sigmaR=[7, 8])
+    assert np.array_equal(k5.Qhat, np.diag([1.0, 4, 9, 16, 25, 36])) and np.array_equal(k5.Rhat, np.diag([49.0, 64]))
+    # append(1/s, 1/(10s+1), 1/(-s+1)) at Ts = 0.1 (zero-order hold): an integrator, a stable and an unstable pole
+    ast, bst, cst = (m[0, 0] for m in zoh_first_order(1, 10, 0.1))
+    au = np.exp(0.1)                                     # 1/(1 - s) = -1/(s - 1): x' = x + u, y = -x
+    linmodel3 = LinModel(np.diag([1.0, ast, au]), np.diag([0.1, bst, au - 1.0]), np.diag([1.0, cst, -1.0]), Ts=0.1)
+    k6 = SteadyKalmanFilter(linmodel3)
+    assert (k6.nxs, k6.nxhat, list(k6.nint_ym)) == (2, 5, [0, 1, 1])
+    k7 = SteadyKalmanFilter(linmodel, nint_u=[1, 1])
+    assert (k7.nxs, k7.nxhat, list(k7.nint_u), list(k7.nint_ym)) == (2, 4, [1, 1], [0, 0])
+    for kw in (dict(nint_ym=[1, 1, 1]), dict(nint_ym=[-1, 0]), dict(nint_ym=0, sigmaQ=[1]), dict(nint_ym=0, sigmaR=[1, 1, 1]),
+               dict(nint_u=[1, 1], nint_ym=[1, 1])):
+        with pytest.raises(ValueError):
+            SteadyKalmanFilter(linmodel, **kw)
+    with pytest.raises(ValueError):                      # an integrator on the already integrating output: unobservable
+        SteadyKalmanFilter(linmodel3, nint_ym=[1, 0, 0])
+    with pytest.raises(ValueError):                      # unobservable plant mode
+        SteadyKalmanFilter(LinModel([[1, 0], [0, 1.5]], [[1], [0]], [[1, 0]], Ts=1.0), nint_ym=[1])
