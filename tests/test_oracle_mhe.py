@@ -386,3 +386,27 @@ def test_host_estimator_mirrors_nan_and_initstate():
                     assert np.abs(g.Phat[i] - o.Phat).max() < 1e-11
                 o.updatestate(u[i], y[i])
             g.updatestate(u, y)
+
+
+def test_kalman_filter_construction():
+    """test/2_test_state_estim.jl:155-205 ("KF construction"): augmentation sizes, covariances from standard deviations."""
+    from oracle.linmpc import zoh_first_order
+    Ts = 400.0
+    a1, b1, g1 = (m[0, 0] for m in zoh_first_order(1.90, 1800.0, Ts))
+    a2, b2, g2 = (m[0, 0] for m in zoh_first_order(0.74, 800.0, Ts))
+    linmodel = LinModel(np.diag([a1, a2]), np.array([[b1, b1], [-b2, b2]]), np.diag([g1, g2]), Ts=Ts, uop=[10, 50], yop=[50, 30])
+    k1 = KalmanFilter(linmodel)
+    assert (len(k1.i_ym), k1.nxs, k1.nxhat, list(k1.nint_ym)) == (2, 2, 4, [1, 1])
+    linmodel2 = _setup_linmodel_tustin_d()
+    k2 = KalmanFilter(linmodel2, i_ym=[1])
+    assert (len(k2.i_ym), k2.nxs, k2.nxhat) == (1, 1, 5)
+    assert (KalmanFilter(linmodel, nint_ym=0).nxs, KalmanFilter(linmodel, nint_ym=0).nxhat) == (0, 2)
+    assert (KalmanFilter(linmodel, nint_ym=[2, 2]).nxs, KalmanFilter(linmodel, nint_ym=[2, 2]).nxhat) == (4, 6)
+    k5 = KalmanFilter(linmodel2, sigmaQ=[1, 2, 3, 4], sigmaQint_ym=[5, 6], sigmaR=[7, 8])
+    assert np.array_equal(k5.Qhat, np.diag([1.0, 4, 9, 16, 25, 36])) and np.array_equal(k5.Rhat, np.diag([49.0, 64]))
+    k6 = KalmanFilter(linmodel2, sigmaP_0=[1, 2, 3, 4], sigmaPint_ym_0=[5, 6])
+    assert np.array_equal(k6.Phat, np.diag([1.0, 4, 9, 16, 25, 36]))
+    k7 = KalmanFilter(linmodel, nint_u=[1, 1])
+    assert (k7.nxs, k7.nxhat, list(k7.nint_u), list(k7.nint_ym)) == (2, 4, [1, 1], [0, 0])
+    with pytest.raises(ValueError):
+        KalmanFilter(linmodel, nint_ym=0, sigmaP_0=[1])
